@@ -1,0 +1,319 @@
+#!/usr/bin/env python
+"""bench.py -- entropy-model images/sec of the DCAE slice loop on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N --steps K --warmup W] [--impl reference] [--math tf32x3|tf32|fp32]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A step = one pass of the channel-slice loop (dcae.py:638-670: 5 x [dictionary cross-attention,
+cc_mean/cc_scale, GaussianConditional quantise+likelihood+index, LRP]) over one batch of synthetic
+Kodak-shaped latents: BASELINE config #2, 16 images of 768x512 per GPU -> y/latent_scales/latent_means
+[16, 320, 32, 48].  Images are independent, so N GPUs run N independent shards (weak scaling, no
+data-path collective); NCCL is used for the barrier, the max-over-ranks time and the bpp reduction.
+
+Printed JSON line: see DESIGN.md section "Measurement".
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+H_IMG, W_IMG = 512, 768          # Kodak
+FLOP_PER_TOKEN = 163.76e6        # whole slice loop, 2*MAC
+GC_BYTES_PER_ELEM = 28           # y, mu, scale in; lik, y_hat, sym, idx out (compress variant)
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm": d["hbm_gbs"], "tc_burst": d["bf16_tflops"], "tc_sustained": d["bf16_tflops_sustained"], "src": "measured"}
+    return {"hbm": 6650.0, "tc_burst": 1590.0, "tc_sustained": 1400.0, "src": "fallback"}
+
+
+def synth_latents(B, h, w, seed=1234, pin=False):
+    """SURVEY §8d 'direct' synthetic inputs: y = 4 randn, latents = randn."""
+    g = torch.Generator().manual_seed(seed)
+    ts = [4.0 * torch.randn(B, 320, h, w, generator=g), torch.randn(B, 320, h, w, generator=g),
+          torch.randn(B, 320, h, w, generator=g)]
+    return [t.pin_memory() for t in ts] if pin else ts
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        busy = [v for v in sm if v > 0]
+        return {"sm_mhz": busy[len(busy) // 2] if busy else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_oracle_rate(n_images, steps, warmup, seed=0):
+    """The reference's CPU implementation of the path (oracle port; /root/reference cannot travel to the
+    GPU box): torch-CPU fp32, all host threads.  Returns (images/s, threads, seconds per step)."""
+    from dcae_b200.params import init_entropy_params
+    from oracle.entropy_model import SliceLoopOracle
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    orc = SliceLoopOracle(init_entropy_params(seed, "lively"))
+    y, ls, lm = synth_latents(n_images, H_IMG // 16, W_IMG // 16)
+    for _ in range(warmup):
+        orc.forward(y, ls, lm)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        orc.forward(y, ls, lm)
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return n_images / dt, threads, dt
+
+
+def run_reference(args):
+    """--impl reference: the reference CPU path on the box's host cores, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_img = args.cpu_images
+    rate, threads, dt = cpu_oracle_rate(n_img, args.steps, min(args.warmup, 1))
+    line = {
+        "impl": "reference", "metric": "entropy-model images/sec @768x512", "value": rate, "unit": "images/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"DCAE entropy-model slice loop, {n_img} x 768x512 per step on host CPU (bounded sample of config #2)",
+                   "batch_per_step": n_img},
+        "cpu_baseline": {"value": rate, "unit": "images/s", "cores": threads, "kind": "port",
+                         "sample": f"{args.steps} steps x {n_img} images of 768x512, torch-CPU fp32 oracle port of dcae.py:638-670"},
+        "e2e": {"value": rate, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--math", default="tf32x3", choices=["tf32x3", "tf32", "fp32"])
+    ap.add_argument("--batch", type=int, default=16, help="images per GPU per step (config #2: 16)")
+    ap.add_argument("--cpu-images", type=int, default=2, help="images per step of the CPU reference arm")
+    ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gc-micro-mb", type=int, default=1024, help="footprint of the kernel-3 HBM microbenchmark")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    from dcae_b200 import _lib
+    from dcae_b200.entropy_model import EntropySliceLoop
+    from dcae_b200.params import init_entropy_params
+
+    B, h, w = args.batch, H_IMG // 16, W_IMG // 16
+    T = B * h * w
+    eng = EntropySliceLoop(init_entropy_params(0, "lively"), device=dev, math=args.math)
+    host_in = synth_latents(B, h, w, seed=1234 + rank, pin=True)
+    dev_in = [t.to(dev) for t in host_in]
+    host_out = [torch.empty(B, 320, h, w).pin_memory() for _ in range(4)]
+    lib = _lib.load()
+
+    def step_resident():
+        return eng.forward(*dev_in)
+
+    def step_e2e():
+        xs = [t.to(dev, non_blocking=True) for t in host_in]
+        out = eng.forward(*xs)
+        for dst, k in zip(host_out, ("y_hat", "means", "scales", "likelihoods")):
+            dst.copy_(out[k], non_blocking=True)
+        return out
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            out = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        barrier()
+        return float(ms) / steps, out
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms_step, out = timed(step_resident, args.steps)
+    clocks = sampler.stop() if sampler else None
+    launches = eng.last_launches
+    for _ in range(2):
+        step_e2e()
+    ms_e2e, _ = timed(step_e2e, args.steps)
+
+    # bpp over all ranks: the only data-path reduction -- one scalar all-reduce
+    red = torch.stack([out["log2_lik_sum"].double().squeeze(), torch.tensor(float(B * H_IMG * W_IMG), device=dev, dtype=torch.double)])
+    if world > 1:
+        dist.all_reduce(red)
+    bpp = float(-red[0] / red[1])
+
+    # per-kernel-family device time of one instrumented step (CUDA events on the launching stream)
+    ms = (C.c_double * 4)(); work = (C.c_double * 4)(); cnt = (C.c_int64 * 4)()
+    lib.dcae_profile_start()
+    for _ in range(2):
+        step_resident()
+    lib.dcae_profile_stop(ms, work, cnt)
+    fam = {n: {"ms_per_step": ms[i] / 2, "launches_per_step": cnt[i] // 2, "work_per_step": work[i] / 2}
+           for i, n in enumerate(("gemm", "attention", "gc", "other"))}
+    peaks = load_peaks()
+    gemm_tflops = fam["gemm"]["work_per_step"] / (fam["gemm"]["ms_per_step"] * 1e-3) / 1e12 if fam["gemm"]["ms_per_step"] else 0.0
+    tc_peak = peaks["tc_sustained"]
+    roofline = {
+        "kernel": "gemm_tcgen05_kernel" if args.math != "fp32" else "gemm_simt_kernel",
+        "bound": "tensor", "achieved": gemm_tflops, "peak": tc_peak, "unit": "TFLOP/s", "frac": gemm_tflops / tc_peak,
+        "traffic": None,
+        "note": (f"achieved = algorithmic 2*T*N*K flop of all {fam['gemm']['launches_per_step']} dense-layer launches of a step / "
+                 f"their summed CUDA-event time; peak = {peaks['src']} sustained dense bf16 (kernel timed inside a long step). "
+                 + {"tf32x3": "Arithmetic is 3 TF32 MMAs per algorithmic MAC at half the bf16 rate: ceiling = 1/6 of this peak.",
+                    "tf32": "Arithmetic is TF32 (half the bf16 rate): ceiling = 1/2 of this peak.",
+                    "fp32": "FFMA reference mode: tensor cores unused."}[args.math]),
+        "share_of_step": fam["gemm"]["ms_per_step"] / max(sum(f["ms_per_step"] for f in fam.values()), 1e-9),
+    }
+
+    # kernel 3 alone at an HBM-sized footprint (per-slice launches are L2-resident at B=16)
+    roofline_gc = None
+    if rank == 0:
+        roofline_gc = gc_microbench(dev, lib, args.gc_micro_mb, peaks)
+        roofline_gc["in_loop"] = {"ms_per_step": fam["gc"]["ms_per_step"], "launches_per_step": fam["gc"]["launches_per_step"],
+                                  "GB/s": fam["gc"]["work_per_step"] / max(fam["gc"]["ms_per_step"], 1e-9) / 1e6}
+
+    cpu_baseline = None
+    if rank == 0 and not args.no_cpu_baseline:
+        rate, threads, dt = cpu_oracle_rate(args.cpu_images, args.cpu_steps, 1)
+        cpu_baseline = {"value": rate, "unit": "images/s", "cores": threads, "kind": "port",
+                        "sample": f"{args.cpu_steps} steps x {args.cpu_images} images of 768x512 (same slice loop, torch-CPU fp32 oracle port)"}
+
+    if rank == 0:
+        imgs = B * world
+        line = {
+            "metric": "entropy-model images/sec @768x512", "value": imgs / (ms_step * 1e-3), "unit": "images/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": {"tf32x3": "f32 (3xTF32 error-compensated tcgen05, fp32 accumulate)", "tf32": "tf32", "fp32": "f32"}[args.math],
+            "data": "synthetic",
+            "config": {"workload": "DCAE entropy-model forward (slice loop), batch 16 synthetic Kodak-shaped 768x512 images per GPU (BASELINE config #2)",
+                       "batch_per_gpu": B, "tokens_per_gpu": T, "math": args.math, "weights": "random-init (seeded, lively profile)",
+                       "l2": "no flush needed: per-step working set 1.8 GB >> 126 MB L2", "parallelism": f"{world} independent image shards"},
+            "e2e": {"value": imgs / (ms_e2e * 1e-3), "unit": "images/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": sum(t.numel() * 4 for t in host_in), "d2h_bytes_per_step": sum(t.numel() * 4 for t in host_out)},
+            "gpu_launches": launches * args.steps,
+            "gpu_launches_per_step": launches,
+            "clocks": clocks,
+            "roofline": roofline,
+            "roofline_gc": roofline_gc,
+            "kernel_families": fam,
+            "step_tflops": FLOP_PER_TOKEN * T / (ms_step * 1e-3) / 1e12,
+            "bpp": bpp,
+            "cpu_baseline": cpu_baseline,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def gc_microbench(dev, lib, mb, peaks):
+    """Kernel 3 timed alone on inputs far larger than L2: algorithmic 28 B/element."""
+    from dcae_b200 import _lib
+    n = mb * (1 << 20) // GC_BYTES_PER_ELEM // 64 * 64
+    rows = n // 64
+    g = torch.Generator(device=dev).manual_seed(1)
+    y = 4 * torch.randn(rows, 64, device=dev, generator=g)
+    mu = 2 * torch.randn(rows, 64, device=dev, generator=g)
+    sc = torch.exp(torch.empty(rows, 64, device=dev).uniform_(-3.0, 5.7, generator=g))
+    from dcae_b200.entropy_model import get_scale_table
+    table = get_scale_table().to(dev)
+    outs = [torch.empty(rows, 64, device=dev), torch.empty(rows, 64, device=dev),
+            torch.empty(rows, 64, device=dev, dtype=torch.int32), torch.empty(rows, 64, device=dev, dtype=torch.int32)]
+    a = _lib.GcArgs()
+    a.y, a.y_ld, a.mu, a.mu_ld, a.scale, a.scale_ld = y.data_ptr(), 64, mu.data_ptr(), 64, sc.data_ptr(), 64
+    a.scale_table, a.n_table, a.scale_bound, a.lik_bound, a.mode = table.data_ptr(), 64, 0.11, 1e-9, 0
+    a.rows, a.inner = rows, 64
+    a.y_hat, a.y_hat_ld, a.lik, a.lik_ld = outs[0].data_ptr(), 64, outs[1].data_ptr(), 64
+    a.sym, a.sym_ld, a.idx, a.idx_ld = outs[2].data_ptr(), 64, outs[3].data_ptr(), 64
+    s = _lib.current_stream(dev)
+    for _ in range(3):
+        _lib.check(lib.dcae_gc_fused(a, s))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 10
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        lib.dcae_gc_fused(a, s)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    gbs = n * GC_BYTES_PER_ELEM / (ms * 1e-3) / 1e9
+    return {"kernel": "gc_fused_kernel", "bound": "hbm", "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s",
+            "frac": gbs / peaks["hbm"], "traffic": None, "elements": n, "ms": ms,
+            "note": f"kernel 3 alone, {n * GC_BYTES_PER_ELEM / 2**20:.0f} MiB algorithmic footprint (28 B/element), peak = {peaks['src']} copy bandwidth"}
+
+
+if __name__ == "__main__":
+    main()

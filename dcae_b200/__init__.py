@@ -1,0 +1,19 @@
+"""dcae_b200: B200 (sm_100a) implementation of the DCAE entropy-model hot path.
+
+Public surface (mirrors the reference's operator interface for this path only):
+  EntropySliceLoop      -- the channel-slice loop of DCAE.forward/compress/decompress
+  GaussianConditional   -- compressai-compatible quantise / likelihood / build_indexes (kernel 3)
+  init_entropy_params   -- deterministic random-init weights with the reference's state-dict keys
+"""
+from .params import init_entropy_params, entropy_param_shapes  # noqa: F401
+
+
+def __getattr__(name):
+    # CUDA-facing classes are imported lazily so that `import dcae_b200` works on a build box
+    if name in ("EntropySliceLoop", "get_scale_table", "bits_per_pixel"):
+        from . import entropy_model
+        return getattr(entropy_model, name)
+    if name == "GaussianConditional":
+        from .gaussian_conditional import GaussianConditional
+        return GaussianConditional
+    raise AttributeError(name)

@@ -1,0 +1,428 @@
+// C ABI glue + the host-side plan of the channel-slice loop
+// (/root/reference/models/dcae.py:638-670 forward, :713-753 compress, :878-906 decompress).
+#include <stdarg.h>
+#include <string.h>
+
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+
+namespace dcae {
+
+thread_local int64_t g_launches = 0;
+static thread_local char g_error[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+}
+
+// ---- event-based per-family timing ----------------------------------------------------------------
+namespace {
+struct ProfRec { int family; double work; cudaEvent_t a, b; };
+std::vector<ProfRec> g_prof;
+std::vector<cudaEvent_t> g_event_pool;
+bool g_prof_on = false;
+size_t g_prof_used = 0;
+cudaEvent_t take_event() {
+  if (g_prof_used < g_event_pool.size()) return g_event_pool[g_prof_used++];
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  g_event_pool.push_back(e);
+  ++g_prof_used;
+  return e;
+}
+}  // namespace
+
+ProfileScope::ProfileScope(int family, double work, void* s) : slot(-1), stream(s) {
+  if (!g_prof_on) return;
+  ProfRec r{family, work, take_event(), take_event()};
+  cudaEventRecord(r.a, (cudaStream_t)stream);
+  slot = (int)g_prof.size();
+  g_prof.push_back(r);
+}
+ProfileScope::~ProfileScope() {
+  if (slot >= 0) cudaEventRecord(g_prof[slot].b, (cudaStream_t)stream);
+}
+
+}  // namespace dcae
+
+using namespace dcae;
+
+extern "C" int dcae_profile_start(void) {
+  g_prof.clear();
+  g_prof_used = 0;
+  g_prof_on = true;
+  return DCAE_OK;
+}
+
+extern "C" int dcae_profile_stop(double* ms, double* work, int64_t* launches) {
+  DCAE_REQUIRE(ms && work && launches, "dcae_profile_stop: null output");
+  g_prof_on = false;
+  DCAE_CUDA(cudaDeviceSynchronize());
+  for (int f = 0; f < DCAE_PROF_FAMILIES; ++f) { ms[f] = 0; work[f] = 0; launches[f] = 0; }
+  for (const ProfRec& r : g_prof) {
+    float t = 0.f;
+    DCAE_CUDA(cudaEventElapsedTime(&t, r.a, r.b));
+    ms[r.family] += t;
+    work[r.family] += r.work;
+    launches[r.family] += 1;
+  }
+  g_prof.clear();
+  g_prof_used = 0;
+  return DCAE_OK;
+}
+
+extern "C" int dcae_version(void) { return DCAE_B200_VERSION; }
+extern "C" const char* dcae_last_error(void) { return g_error; }
+extern "C" int64_t dcae_launch_count(void) { return g_launches; }
+
+extern "C" int dcae_device_check(void) {
+  int dev = 0, major = 0;
+  DCAE_CUDA(cudaGetDevice(&dev));
+  DCAE_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  if (major != 10) {
+    set_error("libdcae_b200 is built for sm_100a only; device %d has compute capability major %d", dev, major);
+    return DCAE_E_DEVICE;
+  }
+  return DCAE_OK;
+}
+
+static int check_gemm_args(const dcae_operand* a, const dcae_weight* w, const dcae_epilogue* e) {
+  DCAE_REQUIRE(a && w && e, "dcae_op_gemm: null argument struct");
+  DCAE_REQUIRE(a->base && e->out, "dcae_op_gemm: null operand/output pointer");
+  DCAE_REQUIRE(a->taps == 1 || a->taps == 9, "dcae_op_gemm: taps must be 1 or 9 (got %d)", a->taps);
+  DCAE_REQUIRE(a->k0 > 0 && a->k0 % 32 == 0 && a->k1 >= 0 && a->k1 % 32 == 0 && a->col0 % 4 == 0 && a->col1 % 4 == 0,
+               "dcae_op_gemm: operand segments must be multiples of 32 columns (k0=%d k1=%d)", a->k0, a->k1);
+  DCAE_REQUIRE(w->K == a->taps * (a->k0 + a->k1), "dcae_op_gemm: weight K=%d != taps*(k0+k1)=%d", w->K, a->taps * (a->k0 + a->k1));
+  DCAE_REQUIRE(w->N > 0 && w->N % 16 == 0, "dcae_op_gemm: N=%d must be a positive multiple of 16", w->N);
+  DCAE_REQUIRE(a->B >= 0 && a->h >= 0 && a->w >= 0 && (int64_t)a->B * a->h * a->w < (1ll << 31), "dcae_op_gemm: bad token grid");
+  DCAE_REQUIRE(a->ld % 4 == 0 && e->out_ld % 4 == 0 && aligned16(a->base) && aligned16(e->out), "dcae_op_gemm: operand/output must be 16-byte aligned, ld %% 4 == 0");
+  DCAE_REQUIRE(a->col0 + a->k0 <= a->ld && (a->k1 == 0 || a->col1 + a->k1 <= a->ld), "dcae_op_gemm: operand columns exceed ld");
+  DCAE_REQUIRE(e->act >= DCAE_ACT_NONE && e->act <= DCAE_ACT_HALF_TANH, "dcae_op_gemm: bad activation %d", e->act);
+  DCAE_REQUIRE(e->act_cols % 4 == 0, "dcae_op_gemm: act_cols must be a multiple of 4");
+  DCAE_REQUIRE((!e->addend || (aligned16(e->addend) && e->addend_ld % 4 == 0)) && (!e->residual || (aligned16(e->residual) && e->residual_ld % 4 == 0)) &&
+                   aligned16(e->bias) && aligned16(e->res_scale),
+               "dcae_op_gemm: epilogue tensors must be 16-byte aligned");
+  return DCAE_OK;
+}
+
+extern "C" int dcae_op_gemm(const dcae_operand* a, const dcae_weight* w, const dcae_epilogue* e, int math, void* stream) {
+  DCAE_TRY(check_gemm_args(a, w, e));
+  ProfileScope prof(DCAE_PROF_GEMM, 2.0 * a->B * a->h * a->w * (double)w->N * (double)w->K, stream);
+  switch (math) {
+    case DCAE_MATH_FP32_SIMT: return gemm_simt(a, w, e, (cudaStream_t)stream);
+    case DCAE_MATH_TF32X3: return gemm_tcgen05(a, w, e, 3, (cudaStream_t)stream);
+    case DCAE_MATH_TF32: return gemm_tcgen05(a, w, e, 1, (cudaStream_t)stream);
+  }
+  set_error("dcae_op_gemm: unknown math mode %d", math);
+  return DCAE_E_INVALID;
+}
+
+extern "C" int dcae_op_dict_attention(const float* q, int64_t q_ld, const float* Kh, const float* Vh,
+                                      const float* head_scale, int64_t T, float* out, int64_t out_ld, int math, void* stream) {
+  DCAE_REQUIRE(q && Kh && Vh && head_scale && out, "dcae_op_dict_attention: null pointer");
+  DCAE_REQUIRE(aligned16(q) && aligned16(out) && aligned16(Kh) && aligned16(Vh) && q_ld % 4 == 0 && out_ld % 4 == 0 && q_ld >= 640 && out_ld >= 640,
+               "dcae_op_dict_attention: 16-byte alignment and ld >= 640 required");
+  (void)math;  // the tcgen05 attention core plugs in here; SIMT is the strict-fp32 mode
+  ProfileScope prof(DCAE_PROF_ATTN, 327680.0 * (double)T, stream);
+  return dict_attention_simt(q, q_ld, Kh, Vh, head_scale, T, out, out_ld, (cudaStream_t)stream);
+}
+
+// =============================================================================================
+// Slice-loop plan
+// =============================================================================================
+namespace {
+
+constexpr int NS = 5, M = 320, SL = 64, D = 640;
+constexpr int SUP_LD = 1344;   // [dict_info 320 | latent_scales 320 | latent_means 320 | y_hat 5x64 | y_hat_pre 64]
+constexpr int SUP_DICT = 0, SUP_LS = 320, SUP_LM = 640, SUP_YHAT = 960, SUP_PRE = 1280;
+constexpr int GC_PARTIALS_MAX = 148 * 8;
+
+struct Buf {
+  float* p = nullptr;
+  int cols = 0;
+};
+
+}  // namespace
+
+struct dcae_slice_loop {
+  int B, h, w, math;
+  int64_t T, HW;
+  dcae_slice_weights wt[NS];
+  const float* scale_table;
+  // token-major workspace
+  Buf sup, y, means, scales, lik, x0, x1, x2, x3, ln, q, ao, so, dc, ga, t1, t2, f, g, h1, h2, l1, l2, stats, part, stage;
+  int32_t *sym, *idx, *istage;
+  int64_t n_part;   // partial sums per slice
+};
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static size_t carve(dcae_slice_loop* p, char* base) {
+  // Returns total bytes; assigns pointers when base != nullptr.
+  size_t off = 0;
+  const size_t T = (size_t)p->T;
+  auto take = [&](Buf& b, int cols) {
+    b.cols = cols;
+    b.p = base ? reinterpret_cast<float*>(base + off) : nullptr;
+    off = align_up(off + T * cols * sizeof(float), 256);
+  };
+  take(p->sup, SUP_LD); take(p->y, M); take(p->means, M); take(p->scales, M); take(p->lik, M);
+  take(p->x0, D); take(p->x1, D); take(p->x2, D); take(p->x3, D); take(p->ln, D); take(p->q, D);
+  take(p->ao, D); take(p->so, D); take(p->dc, 4 * D); take(p->ga, D); take(p->t1, D); take(p->t2, D);
+  take(p->f, 4 * D); take(p->g, 2 * D); take(p->h1, 672); take(p->h2, 256); take(p->l1, 224); take(p->l2, 128);
+  take(p->stats, 4); take(p->stage, SL);
+  p->sym = base ? reinterpret_cast<int32_t*>(base + off) : nullptr; off = align_up(off + T * M * 4, 256);
+  p->idx = base ? reinterpret_cast<int32_t*>(base + off) : nullptr; off = align_up(off + T * M * 4, 256);
+  p->istage = base ? reinterpret_cast<int32_t*>(base + off) : nullptr; off = align_up(off + T * SL * 4, 256);
+  p->part.cols = 0;
+  p->part.p = base ? reinterpret_cast<float*>(base + off) : nullptr;
+  off = align_up(off + (size_t)NS * GC_PARTIALS_MAX * sizeof(float), 256);
+  return off;
+}
+
+extern "C" size_t dcae_slice_loop_workspace_bytes(int32_t B, int32_t h, int32_t w) {
+  if (B < 0 || h < 0 || w < 0) return 0;
+  dcae_slice_loop tmp;
+  memset(&tmp, 0, sizeof(tmp));
+  tmp.T = (int64_t)B * h * w;
+  return carve(&tmp, nullptr) + 256;
+}
+
+extern "C" int dcae_slice_loop_create(dcae_slice_loop** out, int32_t B, int32_t h, int32_t w,
+                                      const dcae_slice_weights* weights, const float* scale_table, void* workspace,
+                                      size_t workspace_bytes, int math) {
+  DCAE_REQUIRE(out && weights && workspace, "dcae_slice_loop_create: null argument");
+  DCAE_REQUIRE(B > 0 && h > 0 && w > 0 && (int64_t)B * h * w < (1ll << 31) / 4, "dcae_slice_loop_create: bad shape B=%d h=%d w=%d", B, h, w);
+  DCAE_REQUIRE(math >= DCAE_MATH_FP32_SIMT && math <= DCAE_MATH_TF32, "dcae_slice_loop_create: bad math mode %d", math);
+  DCAE_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, "dcae_slice_loop_create: workspace must be 256-byte aligned");
+  DCAE_TRY(dcae_device_check());
+  dcae_slice_loop* p = new (std::nothrow) dcae_slice_loop;
+  DCAE_REQUIRE(p != nullptr, "dcae_slice_loop_create: out of host memory");
+  memset(p, 0, sizeof(*p));
+  p->B = B; p->h = h; p->w = w; p->math = math;
+  p->HW = (int64_t)h * w;
+  p->T = (int64_t)B * h * w;
+  const size_t need = carve(p, nullptr);
+  if (need > workspace_bytes) {
+    set_error("dcae_slice_loop_create: workspace too small (%zu < %zu)", workspace_bytes, need);
+    delete p;
+    return DCAE_E_WORKSPACE;
+  }
+  carve(p, static_cast<char*>(workspace));
+  memcpy(p->wt, weights, sizeof(dcae_slice_weights) * NS);
+  p->scale_table = scale_table;
+  p->n_part = dcae_gc_num_partials(p->T, SL);
+  *out = p;
+  return DCAE_OK;
+}
+
+extern "C" void dcae_slice_loop_destroy(dcae_slice_loop* p) { delete p; }
+
+// ---- small builders --------------------------------------------------------------------------
+static dcae_operand opnd(const dcae_slice_loop* p, const float* base, int64_t ld, int col0, int k0, int taps, int col1 = 0, int k1 = 0) {
+  dcae_operand a;
+  a.base = base; a.ld = ld; a.col0 = col0; a.k0 = k0; a.col1 = col1; a.k1 = k1; a.taps = taps;
+  a.B = p->B; a.h = p->h; a.w = p->w;
+  return a;
+}
+static dcae_epilogue epi(const float* bias, float* out, int64_t out_ld, int act = DCAE_ACT_NONE) {
+  dcae_epilogue e;
+  memset(&e, 0, sizeof(e));
+  e.bias = bias; e.out = out; e.out_ld = out_ld; e.act = act;
+  return e;
+}
+static int gemm(const dcae_slice_loop* p, const dcae_operand& a, const dcae_weight& w, const dcae_epilogue& e, void* s) {
+  return dcae_op_gemm(&a, &w, &e, p->math, s);
+}
+
+extern "C" int dcae_slice_loop_load(dcae_slice_loop* p, const float* y, const float* latent_scales,
+                                    const float* latent_means, void* stream) {
+  DCAE_REQUIRE(p && latent_scales && latent_means, "dcae_slice_loop_load: null argument");
+  g_launches = 0;
+  if (y) DCAE_TRY(dcae_op_nchw_to_tokens(y, p->B, M, p->HW, p->y.p, M, stream));
+  DCAE_TRY(dcae_op_nchw_to_tokens(latent_scales, p->B, M, p->HW, p->sup.p + SUP_LS, SUP_LD, stream));
+  DCAE_TRY(dcae_op_nchw_to_tokens(latent_means, p->B, M, p->HW, p->sup.p + SUP_LM, SUP_LD, stream));
+  return DCAE_OK;
+}
+
+// dictionary cross-attention module of slice i (dcae.py:479-509) -> SUP[:, 0:320]
+static int run_dca(dcae_slice_loop* p, int i, void* s) {
+  const dcae_slice_weights& W = p->wt[i];
+  const int64_t T = p->T;
+  const int cq = 2 * M + SL * i;
+  // x = x_trans(query)                                                       dcae.py:481-482
+  DCAE_TRY(gemm(p, opnd(p, p->sup.p, SUP_LD, SUP_LS, cq, 1), W.x_trans, epi(W.x_trans_b, p->x0.p, D), s));
+  // msa(ln_scale(x))                                                         dcae.py:484, 435-448
+  DCAE_TRY(dcae_op_layernorm(p->x0.p, D, W.ln_scale_g, W.ln_scale_b, D, T, p->ln.p, D, s));
+  DCAE_TRY(gemm(p, opnd(p, p->ln.p, D, 0, D, 1), W.msa_s, epi(W.msa_s_b, p->dc.p, 4 * D), s));
+  for (int j = 0; j < 3; ++j) {                                            // DenseBlock dcae.py:416-433
+    DCAE_TRY(dcae_op_gelu(p->dc.p + D * j, 4 * D, D, T, p->ga.p, D, s));
+    DCAE_TRY(gemm(p, opnd(p, p->ga.p, D, 0, D, 1), W.dense_in[j], epi(W.dense_in_b[j], p->t1.p, D, DCAE_ACT_GELU), s));
+    DCAE_TRY(dcae_op_dwconv3x3(p->t1.p, D, W.dense_dw[j], W.dense_dw_b[j], D, p->B, p->h, p->w, DCAE_ACT_GELU, nullptr, 0, p->t2.p, D, s));
+    DCAE_TRY(gemm(p, opnd(p, p->t2.p, D, 0, D, 1), W.dense_out[j], epi(W.dense_out_b[j], p->dc.p + D * (j + 1), 4 * D), s));
+  }
+  DCAE_TRY(gemm(p, opnd(p, p->dc.p, 4 * D, 0, 4 * D, 1), W.dense_proj, epi(W.dense_proj_b, p->so.p, D), s));
+  // x = s_out * spatial_atte(s_out) + res_scale_1(x)                         dcae.py:446, 484
+  DCAE_TRY(dcae_op_spatial_gate(p->so.p, D, p->x0.p, D, W.res_scale_1, W.spatial_w7, D, p->B, p->h, p->w, p->stats.p, p->x1.p, D, s));
+  // q = q_trans(lnx(x)); attention against the dictionary                    dcae.py:486-501
+  DCAE_TRY(dcae_op_layernorm(p->x1.p, D, W.lnx_g, W.lnx_b, D, T, p->ln.p, D, s));
+  DCAE_TRY(gemm(p, opnd(p, p->ln.p, D, 0, D, 1), W.q_trans, epi(W.q_trans_b, p->q.p, D), s));
+  DCAE_TRY(dcae_op_dict_attention(p->q.p, D, W.Kh, W.Vh, W.head_scale, T, p->ao.p, D, p->math, s));
+  // output = linear(output) + res_scale_2(shortcut)                          dcae.py:503
+  {
+    dcae_epilogue e = epi(W.linear_b, p->x2.p, D);
+    e.residual = p->x1.p; e.residual_ld = D; e.res_scale = W.res_scale_2;
+    DCAE_TRY(gemm(p, opnd(p, p->ao.p, D, 0, D, 1), W.linear, e, s));
+  }
+  // output = mlp(ln_mlp(output)) + res_scale_3(output)                       dcae.py:505, 312-328
+  DCAE_TRY(dcae_op_layernorm(p->x2.p, D, W.ln_mlp_g, W.ln_mlp_b, D, T, p->ln.p, D, s));
+  DCAE_TRY(gemm(p, opnd(p, p->ln.p, D, 0, D, 1), W.fc1, epi(W.fc1_b, p->f.p, 4 * D), s));
+  DCAE_TRY(dcae_op_dwconv3x3(p->f.p, 4 * D, W.mlp_dw, W.mlp_dw_b, 2 * D, p->B, p->h, p->w, DCAE_ACT_GELU, p->f.p + 2 * D, 4 * D, p->g.p, 2 * D, s));
+  {
+    dcae_epilogue e = epi(W.fc2_b, p->x3.p, D);
+    e.residual = p->x2.p; e.residual_ld = D; e.res_scale = W.res_scale_3;
+    DCAE_TRY(gemm(p, opnd(p, p->g.p, 2 * D, 0, 2 * D, 1), W.fc2, e, s));
+  }
+  // dict_info = output_trans(output)                                         dcae.py:507
+  DCAE_TRY(gemm(p, opnd(p, p->x3.p, D, 0, D, 1), W.output_trans, epi(W.output_trans_b, p->sup.p + SUP_DICT, SUP_LD), s));
+  return DCAE_OK;
+}
+
+extern "C" int dcae_slice_loop_params(dcae_slice_loop* p, int32_t i, void* s) {
+  DCAE_REQUIRE(p && i >= 0 && i < NS, "dcae_slice_loop_params: bad slice index");
+  const dcae_slice_weights& W = p->wt[i];
+  DCAE_TRY(run_dca(p, i, s));
+  const int cs = 3 * M + SL * i;   // support channels of slice i (dcae.py:647)
+  // layer 1 of cc_mean | cc_scale | lrp(support part) share the A operand: N = 672       dcae.py:649-655, 661-662
+  {
+    dcae_epilogue e = epi(W.cc1_b, p->h1.p, 672, DCAE_ACT_GELU);
+    e.act_cols = 448;
+    DCAE_TRY(gemm(p, opnd(p, p->sup.p, SUP_LD, 0, cs, 9), W.cc1, e, s));
+  }
+  DCAE_TRY(gemm(p, opnd(p, p->h1.p, 672, 0, 224, 9), W.mean2, epi(W.mean2_b, p->h2.p, 256, DCAE_ACT_GELU), s));
+  DCAE_TRY(gemm(p, opnd(p, p->h1.p, 672, 224, 224, 9), W.scale2, epi(W.scale2_b, p->h2.p + 128, 256, DCAE_ACT_GELU), s));
+  DCAE_TRY(gemm(p, opnd(p, p->h2.p, 256, 0, 128, 9), W.mean3, epi(W.mean3_b, p->means.p + SL * i, M), s));
+  DCAE_TRY(gemm(p, opnd(p, p->h2.p, 256, 128, 128, 9), W.scale3, epi(W.scale3_b, p->scales.p + SL * i, M), s));
+  return DCAE_OK;
+}
+
+// LRP of slice i (dcae.py:661-664): y_hat_i = y_hat_pre + 0.5 tanh(lrp(cat(support, y_hat_pre)))
+static int run_lrp(dcae_slice_loop* p, int i, void* s) {
+  const dcae_slice_weights& W = p->wt[i];
+  {
+    dcae_epilogue e = epi(W.lrp1_b, p->l1.p, 224, DCAE_ACT_GELU);
+    e.addend = p->h1.p + 448; e.addend_ld = 672;     // support part of lrp layer 1, accumulated with cc1
+    DCAE_TRY(gemm(p, opnd(p, p->sup.p, SUP_LD, SUP_PRE, SL, 9), W.lrp1y, e, s));
+  }
+  DCAE_TRY(gemm(p, opnd(p, p->l1.p, 224, 0, 224, 9), W.lrp2, epi(W.lrp2_b, p->l2.p, 128, DCAE_ACT_GELU), s));
+  {
+    dcae_epilogue e = epi(W.lrp3_b, p->sup.p + SUP_YHAT + SL * i, SUP_LD, DCAE_ACT_HALF_TANH);
+    e.residual = p->sup.p + SUP_PRE; e.residual_ld = SUP_LD;
+    DCAE_TRY(gemm(p, opnd(p, p->l2.p, 128, 0, 128, 9), W.lrp3, e, s));
+  }
+  return DCAE_OK;
+}
+
+static dcae_gc_args gc_base(dcae_slice_loop* p, int i) {
+  dcae_gc_args a;
+  memset(&a, 0, sizeof(a));
+  a.mu = p->means.p + SL * i; a.mu_ld = M;
+  a.scale = p->scales.p + SL * i; a.scale_ld = M;
+  a.scale_table = p->scale_table; a.n_table = 64;
+  a.scale_bound = 0.11f; a.lik_bound = 1e-9f;
+  a.rows = p->T; a.inner = SL;
+  return a;
+}
+
+extern "C" int dcae_slice_loop_encode(dcae_slice_loop* p, int32_t i, int32_t gc_mode, const float* noise, void* s) {
+  DCAE_REQUIRE(p && i >= 0 && i < NS, "dcae_slice_loop_encode: bad slice index");
+  DCAE_REQUIRE(gc_mode == DCAE_GC_EVAL || (gc_mode == DCAE_GC_NOISE && noise), "dcae_slice_loop_encode: bad mode / missing noise");
+  dcae_gc_args a = gc_base(p, i);
+  a.mode = gc_mode;
+  a.y = p->y.p + SL * i; a.y_ld = M;
+  if (gc_mode == DCAE_GC_NOISE) {
+    DCAE_TRY(dcae_op_nchw_to_tokens(noise, p->B, SL, p->HW, p->stage.p, SL, s));
+    a.noise = p->stage.p; a.noise_ld = SL;
+  }
+  a.y_hat = p->sup.p + SUP_PRE; a.y_hat_ld = SUP_LD;
+  a.lik = p->lik.p + SL * i; a.lik_ld = M;
+  a.sym = p->sym + SL * i; a.sym_ld = M;
+  if (p->scale_table) { a.idx = p->idx + SL * i; a.idx_ld = M; }
+  a.log2_partials = p->part.p + (int64_t)i * p->n_part;
+  DCAE_TRY(dcae_gc_fused(&a, s));
+  return run_lrp(p, i, s);
+}
+
+extern "C" int dcae_slice_loop_indexes(dcae_slice_loop* p, int32_t i, int32_t* indexes_nchw, void* s) {
+  DCAE_REQUIRE(p && i >= 0 && i < NS && indexes_nchw, "dcae_slice_loop_indexes: bad arguments");
+  DCAE_REQUIRE(p->scale_table, "dcae_slice_loop_indexes: no scale table (update_scale_table not called)");
+  dcae_gc_args a = gc_base(p, i);
+  a.mode = DCAE_GC_EVAL;
+  a.idx = p->idx + SL * i; a.idx_ld = M;
+  DCAE_TRY(dcae_gc_fused(&a, s));
+  return dcae_op_tokens_to_nchw_i32(p->idx + SL * i, M, p->B, SL, p->HW, indexes_nchw, s);
+}
+
+extern "C" int dcae_slice_loop_decode(dcae_slice_loop* p, int32_t i, const int32_t* symbols_nchw, void* s) {
+  DCAE_REQUIRE(p && i >= 0 && i < NS && symbols_nchw, "dcae_slice_loop_decode: bad arguments");
+  DCAE_TRY(dcae_op_nchw_to_tokens_i32(symbols_nchw, p->B, SL, p->HW, p->istage, SL, s));
+  dcae_gc_args a = gc_base(p, i);
+  a.mode = DCAE_GC_DECODE;
+  a.scale = nullptr;
+  a.sym_in = p->istage; a.sym_in_ld = SL;
+  a.y_hat = p->sup.p + SUP_PRE; a.y_hat_ld = SUP_LD;
+  DCAE_TRY(dcae_gc_fused(&a, s));
+  return run_lrp(p, i, s);
+}
+
+extern "C" int dcae_slice_loop_store(dcae_slice_loop* p, float* y_hat, float* means, float* scales, float* lik,
+                                     int32_t* symbols, int32_t* indexes, float* log2_lik_sum, void* s) {
+  DCAE_REQUIRE(p, "dcae_slice_loop_store: null plan");
+  if (y_hat) DCAE_TRY(dcae_op_tokens_to_nchw(p->sup.p + SUP_YHAT, SUP_LD, p->B, M, p->HW, y_hat, s));
+  if (means) DCAE_TRY(dcae_op_tokens_to_nchw(p->means.p, M, p->B, M, p->HW, means, s));
+  if (scales) DCAE_TRY(dcae_op_tokens_to_nchw(p->scales.p, M, p->B, M, p->HW, scales, s));
+  if (lik) DCAE_TRY(dcae_op_tokens_to_nchw(p->lik.p, M, p->B, M, p->HW, lik, s));
+  const int64_t per_slice = (int64_t)p->B * SL * p->HW;
+  for (int i = 0; i < NS; ++i) {
+    if (symbols) DCAE_TRY(dcae_op_tokens_to_nchw_i32(p->sym + SL * i, M, p->B, SL, p->HW, symbols + i * per_slice, s));
+    if (indexes) {
+      DCAE_REQUIRE(p->scale_table, "dcae_slice_loop_store: indexes requested but no scale table");
+      DCAE_TRY(dcae_op_tokens_to_nchw_i32(p->idx + SL * i, M, p->B, SL, p->HW, indexes + i * per_slice, s));
+    }
+  }
+  if (log2_lik_sum) DCAE_TRY(dcae_reduce_partials(p->part.p, NS * p->n_part, log2_lik_sum, s));
+  return DCAE_OK;
+}
+
+extern "C" int dcae_slice_loop_forward(dcae_slice_loop* p, const float* y, const float* latent_scales,
+                                       const float* latent_means, float* y_hat, float* means, float* scales, float* lik,
+                                       int32_t* symbols, int32_t* indexes, float* log2_lik_sum, void* s) {
+  DCAE_REQUIRE(p && y, "dcae_slice_loop_forward: null argument");
+  DCAE_TRY(dcae_slice_loop_load(p, y, latent_scales, latent_means, s));
+  for (int i = 0; i < NS; ++i) {
+    DCAE_TRY(dcae_slice_loop_params(p, i, s));
+    DCAE_TRY(dcae_slice_loop_encode(p, i, DCAE_GC_EVAL, nullptr, s));
+  }
+  return dcae_slice_loop_store(p, y_hat, means, scales, lik, symbols, indexes, log2_lik_sum, s);
+}
+
+extern "C" int dcae_slice_loop_tap(dcae_slice_loop* p, const char* name, const float** ptr, int32_t* cols, int64_t* ld) {
+  DCAE_REQUIRE(p && name && ptr && cols && ld, "dcae_slice_loop_tap: null argument");
+  struct { const char* n; Buf* b; } tbl[] = {
+      {"support", &p->sup}, {"y", &p->y}, {"means", &p->means}, {"scales", &p->scales}, {"lik", &p->lik},
+      {"x0", &p->x0}, {"x1", &p->x1}, {"x2", &p->x2}, {"x3", &p->x3}, {"q", &p->q}, {"attn", &p->ao},
+      {"s_out", &p->so}, {"dense", &p->dc}, {"fc1", &p->f}, {"glu", &p->g}, {"h1", &p->h1}, {"h2", &p->h2},
+      {"l1", &p->l1}, {"l2", &p->l2}};
+  for (auto& t : tbl)
+    if (strcmp(t.n, name) == 0) {
+      *ptr = t.b->p; *cols = t.b->cols; *ld = t.b->cols;
+      return DCAE_OK;
+    }
+  set_error("dcae_slice_loop_tap: unknown buffer '%s'", name);
+  return DCAE_E_INVALID;
+}

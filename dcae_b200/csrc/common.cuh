@@ -1,0 +1,95 @@
+// Shared host/device helpers for libdcae_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/dcae_b200.h"
+
+namespace dcae {
+
+// thread-local error string behind dcae_last_error()
+void set_error(const char* fmt, ...);
+// every kernel launch goes through this counter (bench `gpu_launches`)
+extern thread_local int64_t g_launches;
+inline void count_launch(int n = 1) { g_launches += n; }
+
+#define DCAE_REQUIRE(cond, ...)                     \
+  do {                                              \
+    if (!(cond)) {                                  \
+      ::dcae::set_error(__VA_ARGS__);               \
+      return DCAE_E_INVALID;                        \
+    }                                               \
+  } while (0)
+
+#define DCAE_CUDA(call)                                                                    \
+  do {                                                                                     \
+    cudaError_t e__ = (call);                                                              \
+    if (e__ != cudaSuccess) {                                                              \
+      ::dcae::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, \
+                        __LINE__);                                                         \
+      return DCAE_E_CUDA;                                                                  \
+    }                                                                                      \
+  } while (0)
+
+#define DCAE_LAUNCH_CHECK()                                                                      \
+  do {                                                                                           \
+    ::dcae::count_launch();                                                                      \
+    cudaError_t e__ = cudaPeekAtLastError();                                                     \
+    if (e__ != cudaSuccess) {                                                                    \
+      ::dcae::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__,   \
+                        __LINE__);                                                               \
+      return DCAE_E_CUDA;                                                                        \
+    }                                                                                            \
+  } while (0)
+
+#define DCAE_TRY(call)          \
+  do {                          \
+    int rc__ = (call);          \
+    if (rc__ != DCAE_OK) return rc__; \
+  } while (0)
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+inline int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+// exact (erf-form) GELU as torch.nn.GELU() computes it in fp32: 0.5 x (1 + erf(x / sqrt 2))
+__device__ __forceinline__ float gelu_erf(float x) {
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// RAII event pair around one public op when profiling is on (dcae_profile_start/stop)
+struct ProfileScope {
+  ProfileScope(int family, double work, void* stream);
+  ~ProfileScope();
+  int slot;
+  void* stream;
+};
+
+// internal cross-file entry points
+int gemm_simt(const dcae_operand* a, const dcae_weight* w, const dcae_epilogue* e, cudaStream_t s);
+int gemm_tcgen05(const dcae_operand* a, const dcae_weight* w, const dcae_epilogue* e, int passes, cudaStream_t s);
+int dict_attention_simt(const float* q, int64_t q_ld, const float* Kh, const float* Vh, const float* head_scale,
+                        int64_t T, float* out, int64_t out_ld, cudaStream_t s);
+
+}  // namespace dcae

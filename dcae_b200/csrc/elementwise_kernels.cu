@@ -1,0 +1,343 @@
+// Token-major fp32 helper kernels of the dictionary cross-attention module
+// (/root/reference/models/dcae.py:300-336, 386-448, 479-509): LayerNorm, GELU, depthwise 3x3,
+// spatial-attention gate, NCHW <-> token-major transposes.  All HBM-bound: float4 accesses,
+// channel-contiguous thread mapping, no atomics.
+#include "common.cuh"
+
+namespace dcae {
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm: one warp per token, C % 128 == 0, C <= 1024.  Two-pass (mean, then centred variance).
+// ---------------------------------------------------------------------------------------------
+template <int V>  // V = C / 128 float4 per lane
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, int64_t x_ld,
+                                                        const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, int64_t T,
+                                                        float* __restrict__ out, int64_t out_ld) {
+  const int lane = threadIdx.x & 31;
+  const int64_t t = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (t >= T) return;
+  constexpr int C = V * 128;
+  const float4* xr = reinterpret_cast<const float4*>(x + t * x_ld);
+  float4 v[V];
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < V; ++k) {
+    v[k] = __ldg(xr + lane + 32 * k);
+    s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+  }
+  const float mean = warp_sum(s) * (1.0f / C);
+  float q = 0.f;
+#pragma unroll
+  for (int k = 0; k < V; ++k) {
+    float a = v[k].x - mean, b = v[k].y - mean, c = v[k].z - mean, d = v[k].w - mean;
+    q += (a * a + b * b) + (c * c + d * d);
+  }
+  const float rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / C) + 1e-5f);
+  float4* orow = reinterpret_cast<float4*>(out + t * out_ld);
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(beta);
+#pragma unroll
+  for (int k = 0; k < V; ++k) {
+    const float4 g = __ldg(g4 + lane + 32 * k), b = __ldg(b4 + lane + 32 * k);
+    float4 o;
+    o.x = (v[k].x - mean) * rstd * g.x + b.x;
+    o.y = (v[k].y - mean) * rstd * g.y + b.y;
+    o.z = (v[k].z - mean) * rstd * g.z + b.z;
+    o.w = (v[k].w - mean) * rstd * g.w + b.w;
+    orow[lane + 32 * k] = o;
+  }
+}
+
+__global__ void __launch_bounds__(256) gelu_kernel(const float* __restrict__ x, int64_t x_ld, int C4, int64_t n4,
+                                                   float* __restrict__ out, int64_t out_ld) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t t = i / C4;
+    const int c = (int)(i - t * C4) * 4;
+    float4 v = __ldg(reinterpret_cast<const float4*>(x + t * x_ld + c));
+    v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w);
+    *reinterpret_cast<float4*>(out + t * out_ld + c) = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Depthwise 3x3 (stride 1, zero pad 1) on the token grid; weights tap-major [9, C].
+// out = act(dw(x) + bias) * gate
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dwconv3x3_kernel(const float* __restrict__ x, int64_t x_ld,
+                                                        const float* __restrict__ wt, const float* __restrict__ bias,
+                                                        int C4, int B, int h, int w, int act,
+                                                        const float* __restrict__ gate, int64_t gate_ld,
+                                                        float* __restrict__ out, int64_t out_ld) {
+  const int64_t n4 = (int64_t)B * h * w * C4;
+  const int C = C4 * 4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t t = i / C4;
+    const int c = (int)(i - t * C4) * 4;
+    const int xx = (int)(t % w);
+    const int yy = (int)((t / w) % h);
+    float4 acc = __ldg(reinterpret_cast<const float4*>(bias + c));
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy) {
+#pragma unroll
+      for (int dx = -1; dx <= 1; ++dx) {
+        if ((unsigned)(yy + dy) < (unsigned)h && (unsigned)(xx + dx) < (unsigned)w) {
+          const float4 v = __ldg(reinterpret_cast<const float4*>(x + (t + dy * w + dx) * x_ld + c));
+          const float4 k = __ldg(reinterpret_cast<const float4*>(wt + ((dy + 1) * 3 + (dx + 1)) * C + c));
+          acc.x = fmaf(v.x, k.x, acc.x); acc.y = fmaf(v.y, k.y, acc.y);
+          acc.z = fmaf(v.z, k.z, acc.z); acc.w = fmaf(v.w, k.w, acc.w);
+        }
+      }
+    }
+    if (act == DCAE_ACT_GELU) { acc.x = gelu_erf(acc.x); acc.y = gelu_erf(acc.y); acc.z = gelu_erf(acc.z); acc.w = gelu_erf(acc.w); }
+    if (gate != nullptr) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gate + t * gate_ld + c));
+      acc.x *= g.x; acc.y *= g.y; acc.z *= g.z; acc.w *= g.w;
+    }
+    *reinterpret_cast<float4*>(out + t * out_ld + c) = acc;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Spatial attention gate.  Pass 1: per-token channel mean and max.  Pass 2: 7x7 conv over the
+// 2-channel stats map, sigmoid, out = s_out * gate + res_scale * x0.
+// ---------------------------------------------------------------------------------------------
+template <int V>
+__global__ void __launch_bounds__(256) channel_stats_kernel(const float* __restrict__ x, int64_t x_ld, int64_t T,
+                                                            float* __restrict__ stats) {
+  const int lane = threadIdx.x & 31;
+  const int64_t t = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (t >= T) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + t * x_ld);
+  float s = 0.f, m = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < V; ++k) {
+    const float4 v = __ldg(xr + lane + 32 * k);
+    s += (v.x + v.y) + (v.z + v.w);
+    m = fmaxf(fmaxf(m, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+  }
+  s = warp_sum(s);
+  m = warp_max(m);
+  if (lane == 0) {
+    stats[2 * t] = s * (1.0f / (V * 128));
+    stats[2 * t + 1] = m;
+  }
+}
+
+template <int V>
+__global__ void __launch_bounds__(256) spatial_gate_kernel(const float* __restrict__ s_out, int64_t s_ld,
+                                                           const float* __restrict__ x0, int64_t x0_ld,
+                                                           const float* __restrict__ res_scale,
+                                                           const float* __restrict__ w7,
+                                                           const float* __restrict__ stats, int B, int h, int w,
+                                                           float* __restrict__ out, int64_t out_ld) {
+  const int lane = threadIdx.x & 31;
+  const int64_t T = (int64_t)B * h * w;
+  const int64_t t = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (t >= T) return;
+  const int xx = (int)(t % w);
+  const int yy = (int)((t / w) % h);
+  float acc = 0.f;
+  for (int k = lane; k < 98; k += 32) {
+    const int ch = k / 49, r = k - ch * 49;
+    const int dy = r / 7 - 3, dx = r % 7 - 3;
+    if ((unsigned)(yy + dy) < (unsigned)h && (unsigned)(xx + dx) < (unsigned)w)
+      acc = fmaf(__ldg(w7 + k), __ldg(stats + 2 * (t + dy * w + dx) + ch), acc);
+  }
+  acc = warp_sum(acc);
+  const float gate = 1.0f / (1.0f + expf(-acc));
+  const float4* sr = reinterpret_cast<const float4*>(s_out + t * s_ld);
+  const float4* xr = reinterpret_cast<const float4*>(x0 + t * x0_ld);
+  const float4* rs = reinterpret_cast<const float4*>(res_scale);
+  float4* orow = reinterpret_cast<float4*>(out + t * out_ld);
+#pragma unroll
+  for (int k = 0; k < V; ++k) {
+    const float4 a = __ldg(sr + lane + 32 * k), b = __ldg(xr + lane + 32 * k), r = __ldg(rs + lane + 32 * k);
+    float4 o;
+    o.x = a.x * gate + b.x * r.x; o.y = a.y * gate + b.y * r.y;
+    o.z = a.z * gate + b.z * r.z; o.w = a.w * gate + b.w * r.w;
+    orow[lane + 32 * k] = o;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// [B, C, HW] <-> [B*HW, ld] transposes through a 32x33 shared tile.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) nchw_to_tokens_kernel(const T* __restrict__ src, int C, int64_t HW,
+                                                             T* __restrict__ dst, int64_t dst_ld) {
+  __shared__ T tile[32][33];
+  const int b = blockIdx.z;
+  const int64_t p0 = (int64_t)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int r = ty; r < 32; r += 8) {
+    const int c = c0 + r;
+    const int64_t p = p0 + tx;
+    tile[r][tx] = (c < C && p < HW) ? src[((int64_t)b * C + c) * HW + p] : T(0);
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int64_t p = p0 + r;
+    const int c = c0 + tx;
+    if (c < C && p < HW) dst[((int64_t)b * HW + p) * dst_ld + c] = tile[tx][r];
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) tokens_to_nchw_kernel(const T* __restrict__ src, int64_t src_ld, int C,
+                                                             int64_t HW, T* __restrict__ dst) {
+  __shared__ T tile[32][33];
+  const int b = blockIdx.z;
+  const int64_t p0 = (int64_t)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8) {
+    const int64_t p = p0 + r;
+    const int c = c0 + tx;
+    tile[r][tx] = (c < C && p < HW) ? src[((int64_t)b * HW + p) * src_ld + c] : T(0);
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int c = c0 + r;
+    const int64_t p = p0 + tx;
+    if (c < C && p < HW) dst[((int64_t)b * C + c) * HW + p] = tile[tx][r];
+  }
+}
+
+__global__ void split_tf32_kernel(const float* __restrict__ w, float* __restrict__ hi, float* __restrict__ lo, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = w[i];
+    uint32_t h;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
+    const float hf = __uint_as_float(h);
+    uint32_t l;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(v - hf));
+    hi[i] = hf;
+    lo[i] = __uint_as_float(l);
+  }
+}
+
+static inline unsigned grid_for(int64_t n, int threads) {
+  int64_t b = (n + threads - 1) / threads;
+  const int64_t cap = (int64_t)num_sms() * 16;
+  return (unsigned)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace dcae
+
+using namespace dcae;
+
+extern "C" int dcae_op_layernorm(const float* x, int64_t x_ld, const float* gamma, const float* beta, int32_t C,
+                                 int64_t T, float* out, int64_t out_ld, void* stream) {
+  ProfileScope prof(DCAE_PROF_OTHER, 0.0, stream);
+  DCAE_REQUIRE(x && gamma && beta && out, "dcae_op_layernorm: null pointer");
+  DCAE_REQUIRE(C % 128 == 0 && C >= 128 && C <= 1024, "dcae_op_layernorm: C=%d must be a multiple of 128 in [128,1024]", C);
+  DCAE_REQUIRE(aligned16(x) && aligned16(out) && aligned16(gamma) && aligned16(beta) && x_ld % 4 == 0 && out_ld % 4 == 0,
+               "dcae_op_layernorm: 16-byte alignment required");
+  if (T == 0) return DCAE_OK;
+  const unsigned blocks = (unsigned)((T + 7) / 8);
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (C / 128) {
+#define LN_CASE(V) case V: layernorm_kernel<V><<<blocks, 256, 0, s>>>(x, x_ld, gamma, beta, T, out, out_ld); break;
+    LN_CASE(1) LN_CASE(2) LN_CASE(3) LN_CASE(4) LN_CASE(5) LN_CASE(6) LN_CASE(7) LN_CASE(8)
+#undef LN_CASE
+  }
+  DCAE_LAUNCH_CHECK();
+  return DCAE_OK;
+}
+
+extern "C" int dcae_op_gelu(const float* x, int64_t x_ld, int32_t C, int64_t T, float* out, int64_t out_ld, void* stream) {
+  ProfileScope prof(DCAE_PROF_OTHER, 0.0, stream);
+  DCAE_REQUIRE(x && out && C % 4 == 0 && x_ld % 4 == 0 && out_ld % 4 == 0 && aligned16(x) && aligned16(out), "dcae_op_gelu: bad arguments");
+  if (T == 0) return DCAE_OK;
+  const int64_t n4 = T * (C / 4);
+  gelu_kernel<<<grid_for(n4, 256), 256, 0, (cudaStream_t)stream>>>(x, x_ld, C / 4, n4, out, out_ld);
+  DCAE_LAUNCH_CHECK();
+  return DCAE_OK;
+}
+
+extern "C" int dcae_op_dwconv3x3(const float* x, int64_t x_ld, const float* wt, const float* bias, int32_t C, int32_t B,
+                                 int32_t h, int32_t w, int32_t act, const float* gate, int64_t gate_ld, float* out,
+                                 int64_t out_ld, void* stream) {
+  ProfileScope prof(DCAE_PROF_OTHER, 0.0, stream);
+  DCAE_REQUIRE(x && wt && bias && out, "dcae_op_dwconv3x3: null pointer");
+  DCAE_REQUIRE(C % 4 == 0 && x_ld % 4 == 0 && out_ld % 4 == 0 && (gate == nullptr || gate_ld % 4 == 0), "dcae_op_dwconv3x3: C and lds must be multiples of 4");
+  DCAE_REQUIRE(aligned16(x) && aligned16(wt) && aligned16(bias) && aligned16(out) && aligned16(gate), "dcae_op_dwconv3x3: 16-byte alignment required");
+  DCAE_REQUIRE(act == DCAE_ACT_NONE || act == DCAE_ACT_GELU, "dcae_op_dwconv3x3: act must be NONE or GELU");
+  const int64_t n4 = (int64_t)B * h * w * (C / 4);
+  if (n4 == 0) return DCAE_OK;
+  dwconv3x3_kernel<<<grid_for(n4, 256), 256, 0, (cudaStream_t)stream>>>(x, x_ld, wt, bias, C / 4, B, h, w, act, gate, gate_ld, out, out_ld);
+  DCAE_LAUNCH_CHECK();
+  return DCAE_OK;
+}
+
+extern "C" int dcae_op_spatial_gate(const float* s_out, int64_t s_ld, const float* x0, int64_t x0_ld,
+                                    const float* res_scale, const float* w7, int32_t C, int32_t B, int32_t h, int32_t w,
+                                    float* stats, float* out, int64_t out_ld, void* stream) {
+  ProfileScope prof(DCAE_PROF_OTHER, 0.0, stream);
+  DCAE_REQUIRE(s_out && x0 && res_scale && w7 && stats && out, "dcae_op_spatial_gate: null pointer");
+  DCAE_REQUIRE(C % 128 == 0 && C >= 128 && C <= 1024, "dcae_op_spatial_gate: C=%d must be a multiple of 128 in [128,1024]", C);
+  DCAE_REQUIRE(aligned16(s_out) && aligned16(x0) && aligned16(res_scale) && aligned16(out) && s_ld % 4 == 0 && x0_ld % 4 == 0 && out_ld % 4 == 0,
+               "dcae_op_spatial_gate: 16-byte alignment required");
+  const int64_t T = (int64_t)B * h * w;
+  if (T == 0) return DCAE_OK;
+  const unsigned blocks = (unsigned)((T + 7) / 8);
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (C / 128) {
+#define SG_CASE(V)                                                                                               \
+  case V:                                                                                                        \
+    channel_stats_kernel<V><<<blocks, 256, 0, s>>>(s_out, s_ld, T, stats);                                       \
+    count_launch();                                                                                              \
+    spatial_gate_kernel<V><<<blocks, 256, 0, s>>>(s_out, s_ld, x0, x0_ld, res_scale, w7, stats, B, h, w, out, out_ld); \
+    break;
+    SG_CASE(1) SG_CASE(2) SG_CASE(3) SG_CASE(4) SG_CASE(5) SG_CASE(6) SG_CASE(7) SG_CASE(8)
+#undef SG_CASE
+  }
+  DCAE_LAUNCH_CHECK();
+  return DCAE_OK;
+}
+
+template <typename T>
+static int transpose_in(const T* src, int32_t B, int32_t C, int64_t HW, T* dst, int64_t dst_ld, void* stream) {
+  ProfileScope prof(DCAE_PROF_OTHER, 0.0, stream);
+  DCAE_REQUIRE(src && dst && B >= 0 && C >= 0 && HW >= 0 && dst_ld >= C, "nchw_to_tokens: bad arguments");
+  if (B == 0 || C == 0 || HW == 0) return DCAE_OK;
+  DCAE_REQUIRE(B <= 65535 && (C + 31) / 32 <= 65535, "nchw_to_tokens: B or C too large");
+  dim3 grid((unsigned)((HW + 31) / 32), (unsigned)((C + 31) / 32), (unsigned)B);
+  nchw_to_tokens_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(src, C, HW, dst, dst_ld);
+  DCAE_LAUNCH_CHECK();
+  return DCAE_OK;
+}
+template <typename T>
+static int transpose_out(const T* src, int64_t src_ld, int32_t B, int32_t C, int64_t HW, T* dst, void* stream) {
+  ProfileScope prof(DCAE_PROF_OTHER, 0.0, stream);
+  DCAE_REQUIRE(src && dst && B >= 0 && C >= 0 && HW >= 0 && src_ld >= C, "tokens_to_nchw: bad arguments");
+  if (B == 0 || C == 0 || HW == 0) return DCAE_OK;
+  DCAE_REQUIRE(B <= 65535 && (C + 31) / 32 <= 65535, "tokens_to_nchw: B or C too large");
+  dim3 grid((unsigned)((HW + 31) / 32), (unsigned)((C + 31) / 32), (unsigned)B);
+  tokens_to_nchw_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(src, src_ld, C, HW, dst);
+  DCAE_LAUNCH_CHECK();
+  return DCAE_OK;
+}
+
+extern "C" int dcae_op_nchw_to_tokens(const float* src, int32_t B, int32_t C, int64_t HW, float* dst, int64_t dst_ld, void* stream) {
+  return transpose_in<float>(src, B, C, HW, dst, dst_ld, stream);
+}
+extern "C" int dcae_op_tokens_to_nchw(const float* src, int64_t src_ld, int32_t B, int32_t C, int64_t HW, float* dst, void* stream) {
+  return transpose_out<float>(src, src_ld, B, C, HW, dst, stream);
+}
+extern "C" int dcae_op_tokens_to_nchw_i32(const int32_t* src, int64_t src_ld, int32_t B, int32_t C, int64_t HW, int32_t* dst, void* stream) {
+  return transpose_out<int32_t>(src, src_ld, B, C, HW, dst, stream);
+}
+extern "C" int dcae_op_nchw_to_tokens_i32(const int32_t* src, int32_t B, int32_t C, int64_t HW, int32_t* dst, int64_t dst_ld, void* stream) {
+  return transpose_in<int32_t>(src, B, C, HW, dst, dst_ld, stream);
+}
+
+extern "C" int dcae_split_tf32(const float* w, float* w_hi, float* w_lo, int64_t n, void* stream) {
+  DCAE_REQUIRE(w && w_hi && w_lo && n >= 0, "dcae_split_tf32: bad arguments");
+  if (n == 0) return DCAE_OK;
+  split_tf32_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(w, w_hi, w_lo, n);
+  DCAE_LAUNCH_CHECK();
+  return DCAE_OK;
+}

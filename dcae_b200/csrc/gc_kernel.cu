@@ -1,0 +1,191 @@
+// Kernel 3: GaussianConditional quantise + likelihood + CDF index in one HBM pass.
+// Replaces compressai GaussianConditional.forward/quantize/build_indexes/dequantize at
+// /root/reference/models/dcae.py:657-659, :738-740, :891-896 (math: dcae.py:839-857, :57-58).
+//
+// HBM-bound elementwise kernel: every thread owns float4 groups (16-byte coalesced loads and
+// stores), the 64-entry scale table lives in shared memory, and the table search is a log-domain
+// guess corrected against the real table entries (exact for ANY sorted table).  Arithmetic follows
+// the reference's op order with explicit round-to-nearest intrinsics so that no FMA contraction
+// can change a symbol, an index or a likelihood bit.
+#include "common.cuh"
+
+namespace dcae {
+
+constexpr int GC_THREADS = 256;
+constexpr int GC_MAX_BLOCKS = 148 * 8;
+constexpr int GC_MAX_TABLE = 256;
+
+struct GcParams {
+  dcae_gc_args a;
+  int64_t groups;   // rows * inner/4
+  uint32_t inner4;
+};
+
+__device__ __forceinline__ float nan_max(float x, float bound) {
+  // torch.max(x, bound): NaN propagates
+  return (x != x) ? x : fmaxf(x, bound);
+}
+
+__device__ __forceinline__ float gaussian_likelihood(float out, float mu, float s, float lik_bound) {
+  const float c = -0.70710678118654752440f;  // float(-(2 ** -0.5)), dcae.py:855
+  float v = fabsf(__fsub_rn(out, mu));
+  float up = __fmul_rn(0.5f, erfcf(__fmul_rn(c, __fdiv_rn(__fsub_rn(0.5f, v), s))));
+  float lo = __fmul_rn(0.5f, erfcf(__fmul_rn(c, __fdiv_rn(__fsub_rn(-0.5f, v), s))));
+  return nan_max(__fsub_rn(up, lo), lik_bound);
+}
+
+__device__ __forceinline__ int table_index(float s, const float* tbl, int n, float log_t0, float inv_step) {
+  // idx = (n-1) - sum_{j<n-1} [s <= tbl[j]]  ==  #{ j < n-1 : tbl[j] < s }   (NaN -> n-1)
+  if (s != s) return n - 1;
+  float g = (__logf(s) - log_t0) * inv_step;
+  int j = (int)fminf(fmaxf(g, 0.0f), (float)(n - 1));
+  while (j < n - 1 && tbl[j] < s) ++j;
+  while (j > 0 && !(tbl[j - 1] < s)) --j;
+  return j;
+}
+
+__global__ void __launch_bounds__(GC_THREADS) gc_fused_kernel(const GcParams p) {
+  __shared__ float tbl[GC_MAX_TABLE];
+  __shared__ float red[GC_THREADS / 32];
+  const dcae_gc_args& a = p.a;
+  const int n = a.n_table;
+  for (int i = threadIdx.x; i < n; i += GC_THREADS) tbl[i] = a.scale_table ? a.scale_table[i] : 0.0f;
+  __syncthreads();
+  float log_t0 = 0.f, inv_step = 0.f;
+  if (a.idx != nullptr && n > 1) {
+    log_t0 = __logf(tbl[0]);
+    inv_step = (float)(n - 1) / (__logf(tbl[n - 1]) - log_t0);
+  }
+  const bool want_lik = (a.lik != nullptr || a.log2_partials != nullptr) && a.mode != DCAE_GC_DECODE && a.y != nullptr;
+  float log2_acc = 0.f;
+
+  for (int64_t g = (int64_t)blockIdx.x * GC_THREADS + threadIdx.x; g < p.groups;
+       g += (int64_t)gridDim.x * GC_THREADS) {
+    int64_t row, col;
+    if (p.groups <= 0xffffffffll) {   // 32-bit divide on the common path
+      const uint32_t r32 = (uint32_t)g / p.inner4;
+      row = r32;
+      col = (int64_t)((uint32_t)g - r32 * p.inner4) * 4;
+    } else {
+      row = g / p.inner4;
+      col = (g - row * p.inner4) * 4;
+    }
+    const float4 mu4 = __ldg(reinterpret_cast<const float4*>(a.mu + row * a.mu_ld + col));
+    float4 y4 = make_float4(0.f, 0.f, 0.f, 0.f), sc4 = y4, nz4 = y4;
+    int4 si4 = make_int4(0, 0, 0, 0);
+    if (a.mode != DCAE_GC_DECODE && a.y != nullptr) y4 = __ldg(reinterpret_cast<const float4*>(a.y + row * a.y_ld + col));
+    if (a.scale != nullptr) sc4 = __ldg(reinterpret_cast<const float4*>(a.scale + row * a.scale_ld + col));
+    if (a.mode == DCAE_GC_NOISE) nz4 = __ldg(reinterpret_cast<const float4*>(a.noise + row * a.noise_ld + col));
+    if (a.mode == DCAE_GC_DECODE) si4 = __ldg(reinterpret_cast<const int4*>(a.sym_in + row * a.sym_in_ld + col));
+
+    const float mu[4] = {mu4.x, mu4.y, mu4.z, mu4.w};
+    const float y[4] = {y4.x, y4.y, y4.z, y4.w};
+    const float sc[4] = {sc4.x, sc4.y, sc4.z, sc4.w};
+    const float nz[4] = {nz4.x, nz4.y, nz4.z, nz4.w};
+    const int si[4] = {si4.x, si4.y, si4.z, si4.w};
+    float yh[4], lk[4];
+    int sy[4], ix[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float r, out;
+      if (a.mode == DCAE_GC_DECODE) {
+        r = (float)si[k];                       // dequantize: inputs.type_as(means) + means
+        out = __fadd_rn(r, mu[k]);
+        yh[k] = out;
+      } else {
+        r = rintf(__fsub_rn(y[k], mu[k]));      // torch.round: half to even
+        yh[k] = __fadd_rn(r, mu[k]);            // ste_round(y - mu) + mu == r + mu (exactly)
+        out = (a.mode == DCAE_GC_NOISE) ? __fadd_rn(y[k], nz[k]) : yh[k];
+      }
+      sy[k] = (int)r;
+      const float s = nan_max(sc[k], a.scale_bound);
+      lk[k] = want_lik ? gaussian_likelihood(out, mu[k], s, a.lik_bound) : 1.0f;
+      ix[k] = (a.idx != nullptr) ? table_index(s, tbl, n, log_t0, inv_step) : 0;
+      if (a.log2_partials != nullptr) log2_acc += log2f(lk[k]);
+    }
+    if (a.y_hat) *reinterpret_cast<float4*>(a.y_hat + row * a.y_hat_ld + col) = make_float4(yh[0], yh[1], yh[2], yh[3]);
+    if (a.lik && want_lik) *reinterpret_cast<float4*>(a.lik + row * a.lik_ld + col) = make_float4(lk[0], lk[1], lk[2], lk[3]);
+    if (a.sym) *reinterpret_cast<int4*>(a.sym + row * a.sym_ld + col) = make_int4(sy[0], sy[1], sy[2], sy[3]);
+    if (a.idx) *reinterpret_cast<int4*>(a.idx + row * a.idx_ld + col) = make_int4(ix[0], ix[1], ix[2], ix[3]);
+  }
+
+  if (a.log2_partials != nullptr) {
+    // fixed-order block reduction: lanes by xor-shuffle, warps in index order
+    log2_acc = warp_sum(log2_acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = log2_acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+      for (int w = 0; w < GC_THREADS / 32; ++w) t += red[w];
+      a.log2_partials[blockIdx.x] = t;
+    }
+  }
+}
+
+__global__ void reduce_partials_kernel(const float* __restrict__ p, int64_t n, float* __restrict__ out) {
+  // one block, 256 threads; each thread sums a strided subsequence in index order, then a fixed tree
+  __shared__ float sh[256];
+  float t = 0.f;
+  for (int64_t i = threadIdx.x; i < n; i += 256) t += p[i];
+  sh[threadIdx.x] = t;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = sh[0];
+}
+
+static int64_t gc_blocks(int64_t rows, int64_t inner) {
+  int64_t groups = rows * (inner / 4);
+  int64_t b = (groups + GC_THREADS - 1) / GC_THREADS;
+  if (b > GC_MAX_BLOCKS) b = GC_MAX_BLOCKS;
+  if (b < 1) b = 1;
+  return b;
+}
+
+}  // namespace dcae
+
+extern "C" int64_t dcae_gc_num_partials(int64_t rows, int64_t inner) { return dcae::gc_blocks(rows, inner); }
+
+extern "C" int dcae_gc_fused(const dcae_gc_args* a, void* stream) {
+  using namespace dcae;
+  DCAE_REQUIRE(a != nullptr, "dcae_gc_fused: null args");
+  DCAE_REQUIRE(a->mode >= DCAE_GC_EVAL && a->mode <= DCAE_GC_DECODE, "dcae_gc_fused: bad mode %d", a->mode);
+  DCAE_REQUIRE(a->rows >= 0 && a->inner >= 0 && a->inner % 4 == 0, "dcae_gc_fused: inner (%lld) must be a multiple of 4",
+               (long long)a->inner);
+  DCAE_REQUIRE(a->mu != nullptr, "dcae_gc_fused: mu is required");
+  const bool need_y = a->mode != DCAE_GC_DECODE && (a->y_hat || a->lik || a->sym || a->log2_partials);
+  DCAE_REQUIRE(a->mode == DCAE_GC_DECODE ? a->sym_in != nullptr : (!need_y || a->y != nullptr), "dcae_gc_fused: missing input for mode %d", a->mode);
+  DCAE_REQUIRE(a->mode != DCAE_GC_NOISE || a->noise != nullptr, "dcae_gc_fused: NOISE mode needs a noise tensor");
+  const bool need_scale = a->idx != nullptr || ((a->lik != nullptr || a->log2_partials != nullptr) && a->mode != DCAE_GC_DECODE);
+  DCAE_REQUIRE(!need_scale || a->scale != nullptr, "dcae_gc_fused: scale is required for lik/idx");
+  DCAE_REQUIRE(a->idx == nullptr || (a->scale_table != nullptr && a->n_table >= 2 && a->n_table <= GC_MAX_TABLE),
+               "dcae_gc_fused: idx needs a scale_table of 2..%d entries (update_scale_table not called?)", GC_MAX_TABLE);
+#define GC_CHECK_PTR(ptr, ld)                                                                        \
+  DCAE_REQUIRE((ptr) == nullptr || (aligned16(ptr) && (ld) % 4 == 0), "dcae_gc_fused: " #ptr " must be 16-byte aligned with ld %% 4 == 0")
+  GC_CHECK_PTR(a->y, a->y_ld); GC_CHECK_PTR(a->mu, a->mu_ld); GC_CHECK_PTR(a->scale, a->scale_ld);
+  GC_CHECK_PTR(a->noise, a->noise_ld); GC_CHECK_PTR(a->sym_in, a->sym_in_ld); GC_CHECK_PTR(a->y_hat, a->y_hat_ld);
+  GC_CHECK_PTR(a->lik, a->lik_ld); GC_CHECK_PTR(a->sym, a->sym_ld); GC_CHECK_PTR(a->idx, a->idx_ld);
+#undef GC_CHECK_PTR
+  if (a->rows == 0 || a->inner == 0) return DCAE_OK;   // empty input: nothing to do
+  GcParams p;
+  p.a = *a;
+  p.inner4 = (uint32_t)(a->inner / 4);
+  p.groups = a->rows * (a->inner / 4);
+  const int64_t blocks = gc_blocks(a->rows, a->inner);
+  const int n_tensors = (a->y && a->mode != DCAE_GC_DECODE) + 1 + (a->scale != nullptr) + (a->mode == DCAE_GC_NOISE) +
+                        (a->mode == DCAE_GC_DECODE) + (a->y_hat != nullptr) + (a->lik != nullptr) + (a->sym != nullptr) + (a->idx != nullptr);
+  ProfileScope prof(DCAE_PROF_GC, 4.0 * n_tensors * (double)a->rows * (double)a->inner, stream);
+  gc_fused_kernel<<<(unsigned)blocks, GC_THREADS, 0, (cudaStream_t)stream>>>(p);
+  DCAE_LAUNCH_CHECK();
+  return DCAE_OK;
+}
+
+extern "C" int dcae_reduce_partials(const float* partials, int64_t n, float* out, void* stream) {
+  using namespace dcae;
+  DCAE_REQUIRE(partials != nullptr && out != nullptr && n >= 0, "dcae_reduce_partials: bad arguments");
+  reduce_partials_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(partials, n, out);
+  DCAE_LAUNCH_CHECK();
+  return DCAE_OK;
+}

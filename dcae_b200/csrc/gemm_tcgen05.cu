@@ -1,0 +1,422 @@
+// tcgen05 / TMEM / TMA GEMM for the dense layers of the entropy model (Linear, 1x1 conv and 3x3
+// conv as implicit GEMM; /root/reference/models/dcae.py:482-507, :584-611).
+//
+//   acc[128 tokens, BN] (fp32, TMEM)  +=  A[128, 32] (smem, K-major, SWIZZLE_128B) * W[BN, 32]^T
+//
+// * A tile = one TMA 4-D box {32 ch, TW, TH, 1} of the token-major activation viewed as
+//   [B][h][w][ld]; the 3x3 taps are the same box shifted by (dy, dx) with hardware zero fill
+//   outside the image -- the convolution padding costs nothing and no im2col buffer exists.
+// * kind::tf32 MMA, M = 128, N = BN (<= 256), K = 8 per instruction, fp32 accumulate in TMEM.
+// * PASSES == 3 (DCAE_MATH_TF32X3): fp32-level accuracy on the TF32 pipe.  Four "split" warps
+//   rewrite each landed A tile in place as a_hi = tf32(a) and store a_lo = tf32(a - a_hi) next to
+//   it; weights are pre-split (w_hi, w_lo) once per weight load.  Per k-step the MMA warp issues
+//   a_lo*w_hi + a_hi*w_lo + a_hi*w_hi.  The dropped a_lo*w_lo term is O(2^-22).
+// * PASSES == 1 (DCAE_MATH_TF32): operands go TMA -> MMA untouched (hardware truncates to TF32).
+// * warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2..5 = split warps, then the
+//   epilogue (tcgen05.ld 32x32b -> bias / addend / GELU / 0.5 tanh / scaled residual -> st.global).
+//
+// Every mbarrier wait is bounded: a protocol bug traps instead of hanging the GPU.
+#include <cuda.h>
+
+#include <mutex>
+
+#include "common.cuh"
+
+namespace dcae {
+
+namespace {
+
+constexpr int BM = 128;        // tokens per tile (TMEM lanes)
+constexpr int BK = 32;         // fp32 per k-block = 128 B = one swizzle row
+constexpr int UMMA_K = 8;      // tf32
+constexpr int MAX_STAGES = 4;
+constexpr int A_BYTES = BM * BK * 4;   // 16 KB
+constexpr int NTHREADS = 192;
+constexpr uint32_t SMEM_LIMIT = 227 * 1024;
+
+struct TcParams {
+  dcae_epilogue e;
+  int N, KB;                 // KB = K / 32 k-blocks
+  int cblk_per_tap;          // (k0 + k1) / 32
+  int col0, k0, col1;
+  int taps;
+  int B, h, w, TH, TW, tiles_x, tiles_y;
+  int BN, stages, tmem_cols;
+  uint32_t stage_bytes, b_bytes;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0, spins = 0;
+  uint64_t t0 = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    if ((++spins & 1023u) == 0) {          // never hang the GPU on a protocol bug: trap after 2 s
+      uint64_t now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 2000000000ull) __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr) {
+  // K-major, SWIZZLE_128B: rows of 128 B, 8-row atoms 1024 B apart (SBO), LBO unused (=1), version 1
+  uint64_t d = 0;
+  d |= (uint64_t)((addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float tf32_rna(float v) {
+  uint32_t o;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(o) : "f"(v));
+  return __uint_as_float(o);
+}
+__device__ __forceinline__ float act_apply(float v, int act) {
+  if (act == DCAE_ACT_GELU) return gelu_erf(v);
+  if (act == DCAE_ACT_HALF_TANH) return 0.5f * tanhf(v);
+  return v;
+}
+
+template <int PASSES>
+__global__ void __launch_bounds__(NTHREADS, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bh,
+                    const __grid_constant__ CUtensorMap map_bl, const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[MAX_STAGES], ready_bar[MAX_STAGES], empty_bar[MAX_STAGES], accum_bar;
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B atoms need 1024-B alignment
+
+  // tile coordinates
+  const int n0 = blockIdx.x * p.BN;
+  int mt = blockIdx.y;
+  const int tile_x = mt % p.tiles_x; mt /= p.tiles_x;
+  const int tile_y = mt % p.tiles_y;
+  const int b = mt / p.tiles_y;
+  const int x0 = tile_x * p.TW, y0 = tile_y * p.TH;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&ready_bar[s]), 128);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    mbar_init(smem_u32(&accum_bar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_bh) : "memory");
+    if (PASSES == 3) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_bl) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_acc = tmem_base_slot;
+
+  // per-stage smem carve-up: [A | A_lo (x3) | B_hi | B_lo (x3)]
+  const uint32_t off_al = A_BYTES;
+  const uint32_t off_bh = (PASSES == 3) ? 2 * A_BYTES : A_BYTES;
+  const uint32_t off_bl = off_bh + p.b_bytes;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < p.KB; ++kb) {
+        mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+        const uint32_t sbase = smem0 + stage * p.stage_bytes;
+        const uint32_t fb = smem_u32(&full_bar[stage]);
+        mbar_expect_tx(fb, A_BYTES + (PASSES == 3 ? 2 : 1) * p.b_bytes);
+        const int tap = kb / p.cblk_per_tap;
+        const int c = (kb - tap * p.cblk_per_tap) * BK;
+        const int col = (c < p.k0) ? (p.col0 + c) : (p.col1 + (c - p.k0));
+        int dy = 0, dx = 0;
+        if (p.taps == 9) { dy = tap / 3 - 1; dx = tap % 3 - 1; }
+        tma_load_4d(sbase, &map_a, fb, col, x0 + dx, y0 + dy, b);
+        tma_load_2d(sbase + off_bh, &map_bh, fb, kb * BK, n0);
+        if (PASSES == 3) tma_load_2d(sbase + off_bl, &map_bl, fb, kb * BK, n0);
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < p.KB; ++kb) {
+        mbar_wait(smem_u32(PASSES == 3 ? &ready_bar[stage] : &full_bar[stage]), phase);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t sbase = smem0 + stage * p.stage_bytes;
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k) {
+          const uint32_t koff = k * UMMA_K * 4;
+          const uint64_t a_hi = make_smem_desc(sbase + koff);
+          const uint64_t b_hi = make_smem_desc(sbase + off_bh + koff);
+          if (PASSES == 3) {
+            const uint64_t a_lo = make_smem_desc(sbase + off_al + koff);
+            const uint64_t b_lo = make_smem_desc(sbase + off_bl + koff);
+            mma_tf32(tmem_acc, a_lo, b_hi, idesc, (kb | k) != 0);
+            mma_tf32(tmem_acc, a_hi, b_lo, idesc, 1);
+            mma_tf32(tmem_acc, a_hi, b_hi, idesc, 1);
+          } else {
+            mma_tf32(tmem_acc, a_hi, b_hi, idesc, (kb | k) != 0);
+          }
+        }
+        mma_commit(smem_u32(&empty_bar[stage]));       // frees the smem slot once these MMAs retire
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+      mma_commit(smem_u32(&accum_bar));                // accumulator complete
+    }
+  } else {
+    // ===================== split warps (x3), then epilogue =====================
+    const int st = threadIdx.x - 64;   // 0..127
+    if (PASSES == 3) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < p.KB; ++kb) {
+        mbar_wait(smem_u32(&full_bar[stage]), phase);
+        const uint32_t sbase = smem0 + stage * p.stage_bytes;
+#pragma unroll
+        for (int i = 0; i < A_BYTES / 16 / 128; ++i) {
+          const uint32_t off = (uint32_t)(st + i * 128) * 16;
+          float4 v;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(sbase + off));
+          float4 hi, lo;
+          hi.x = tf32_rna(v.x); hi.y = tf32_rna(v.y); hi.z = tf32_rna(v.z); hi.w = tf32_rna(v.w);
+          lo.x = tf32_rna(v.x - hi.x); lo.y = tf32_rna(v.y - hi.y); lo.z = tf32_rna(v.z - hi.z); lo.w = tf32_rna(v.w - hi.w);
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sbase + off), "f"(hi.x), "f"(hi.y), "f"(hi.z), "f"(hi.w) : "memory");
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sbase + off_al + off), "f"(lo.x), "f"(lo.y), "f"(lo.z), "f"(lo.w) : "memory");
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA (async proxy)
+        mbar_arrive(smem_u32(&ready_bar[stage]));
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+    // ---- epilogue: TMEM lane quarter of this warp = warp % 4 ----
+    mbar_wait(smem_u32(&accum_bar), 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;             // tile row = TMEM lane
+    const int ty = r / p.TW, tx = r - ty * p.TW;
+    const int yy = y0 + ty, xx = x0 + tx;
+    const bool row_ok = (yy < p.h) && (xx < p.w);
+    const int64_t token = ((int64_t)b * p.h + yy) * p.w + xx;
+    const dcae_epilogue& e = p.e;
+    const int act_cols = (e.act_cols <= 0 || e.act_cols > p.N) ? p.N : e.act_cols;
+    for (int c = 0; c < p.BN; c += 32) {
+      uint32_t raw[32];
+      tmem_ld32(tmem_acc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c, raw);   // warp-collective
+      if (!row_ok) continue;
+      const int n = n0 + c;
+      float* orow = e.out + token * e.out_ld + n;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        float4 v = make_float4(__uint_as_float(raw[j]), __uint_as_float(raw[j + 1]), __uint_as_float(raw[j + 2]), __uint_as_float(raw[j + 3]));
+        if (e.bias) {
+          const float4 bv = __ldg(reinterpret_cast<const float4*>(e.bias + n + j));
+          v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+        }
+        if (e.addend) {
+          const float4 ad = __ldg(reinterpret_cast<const float4*>(e.addend + token * e.addend_ld + n + j));
+          v.x += ad.x; v.y += ad.y; v.z += ad.z; v.w += ad.w;
+        }
+        const int act = (n + j < act_cols) ? e.act : DCAE_ACT_NONE;
+        v.x = act_apply(v.x, act); v.y = act_apply(v.y, act); v.z = act_apply(v.z, act); v.w = act_apply(v.w, act);
+        if (e.residual) {
+          const float4 rv = __ldg(reinterpret_cast<const float4*>(e.residual + token * e.residual_ld + n + j));
+          float4 rs = make_float4(1.f, 1.f, 1.f, 1.f);
+          if (e.res_scale) rs = __ldg(reinterpret_cast<const float4*>(e.res_scale + n + j));
+          v.x = fmaf(rv.x, rs.x, v.x); v.y = fmaf(rv.y, rs.y, v.y); v.z = fmaf(rv.z, rs.z, v.z); v.w = fmaf(rv.w, rs.w, v.w);
+        }
+        *reinterpret_cast<float4*>(orow + j) = v;
+      }
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(p.tmem_cols) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  });
+  return fn;
+}
+
+int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+               const cuuint32_t* box) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return DCAE_E_CUDA;
+  }
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d, dims %llu %llu, box %u %u)", (int)r, rank,
+              (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1]);
+    return DCAE_E_CUDA;
+  }
+  return DCAE_OK;
+}
+
+void pick_tile(int h, int w, int* TH, int* TW) {
+  // 128 tokens per tile as a TH x TW box inside one image; minimise the number of tiles
+  int best = 1 << 30;
+  for (int tw = 128; tw >= 1; tw >>= 1) {
+    const int th = 128 / tw;
+    const int tiles = ((h + th - 1) / th) * ((w + tw - 1) / tw);
+    // prefer wide-ish boxes (tw = 16) on ties: longer contiguous rows per TMA line group
+    if (tiles < best || (tiles == best && tw == 16)) { best = tiles; *TH = th; *TW = tw; }
+  }
+}
+
+int pick_bn(int N) {
+  for (int bn = 256; bn >= 32; bn -= 32)
+    if (N % bn == 0) return bn;
+  return 0;
+}
+
+}  // namespace
+
+int gemm_tcgen05(const dcae_operand* a, const dcae_weight* w, const dcae_epilogue* e, int passes, cudaStream_t s) {
+  DCAE_REQUIRE(w->w_hi != nullptr && (passes == 1 || w->w_lo != nullptr), "gemm(tcgen05): weight has no TF32 split (w_hi/w_lo)");
+  DCAE_REQUIRE(aligned16(w->w_hi) && aligned16(w->w_lo), "gemm(tcgen05): split weights must be 16-byte aligned");
+  const int64_t T = (int64_t)a->B * a->h * a->w;
+  if (T == 0) return DCAE_OK;
+  TcParams p;
+  p.e = *e;
+  p.N = w->N;
+  p.KB = w->K / BK;
+  p.cblk_per_tap = (a->k0 + a->k1) / BK;
+  p.col0 = a->col0; p.k0 = a->k0; p.col1 = a->col1;
+  p.taps = a->taps;
+  p.B = a->B; p.h = a->h; p.w = a->w;
+  pick_tile(a->h, a->w, &p.TH, &p.TW);
+  p.tiles_x = (a->w + p.TW - 1) / p.TW;
+  p.tiles_y = (a->h + p.TH - 1) / p.TH;
+  p.BN = pick_bn(w->N);
+  DCAE_REQUIRE(p.BN > 0, "gemm(tcgen05): N=%d must be a multiple of 32", w->N);
+  p.tmem_cols = p.BN <= 32 ? 32 : p.BN <= 64 ? 64 : p.BN <= 128 ? 128 : 256;
+  p.b_bytes = (uint32_t)p.BN * BK * 4;
+  p.stage_bytes = (passes == 3) ? (2 * A_BYTES + 2 * p.b_bytes) : (A_BYTES + p.b_bytes);
+  p.stages = (int)((SMEM_LIMIT - 2048) / p.stage_bytes);
+  if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
+  if (p.stages > p.KB) p.stages = p.KB;
+  DCAE_REQUIRE(p.stages >= 1, "gemm(tcgen05): tile does not fit in shared memory");
+  const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
+
+  CUtensorMap map_a, map_bh, map_bl;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)a->ld, (cuuint64_t)a->w, (cuuint64_t)a->h, (cuuint64_t)a->B};
+    cuuint64_t str[3] = {(cuuint64_t)a->ld * 4, (cuuint64_t)a->ld * 4 * a->w, (cuuint64_t)a->ld * 4 * a->w * a->h};
+    cuuint32_t box[4] = {BK, (cuuint32_t)p.TW, (cuuint32_t)p.TH, 1};
+    DCAE_TRY(encode_map(&map_a, a->base, 4, dims, str, box));
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)w->K, (cuuint64_t)w->N};
+    cuuint64_t str[1] = {(cuuint64_t)w->K * 4};
+    cuuint32_t box[2] = {BK, (cuuint32_t)p.BN};
+    DCAE_TRY(encode_map(&map_bh, w->w_hi, 2, dims, str, box));
+    if (passes == 3) DCAE_TRY(encode_map(&map_bl, w->w_lo, 2, dims, str, box));
+    else map_bl = map_bh;
+  }
+  static std::once_flag attr_once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(attr_once, [] {
+    attr_err = cudaFuncSetAttribute(gemm_tcgen05_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT - 1024);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(gemm_tcgen05_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT - 1024);
+  });
+  DCAE_CUDA(attr_err);
+  dim3 grid((unsigned)(w->N / p.BN), (unsigned)(p.tiles_x * p.tiles_y * a->B));
+  DCAE_REQUIRE(grid.y <= 65535u, "gemm(tcgen05): too many token tiles (%u)", grid.y);
+  if (passes == 3) gemm_tcgen05_kernel<3><<<grid, NTHREADS, smem, s>>>(map_a, map_bh, map_bl, p);
+  else gemm_tcgen05_kernel<1><<<grid, NTHREADS, smem, s>>>(map_a, map_bh, map_bl, p);
+  DCAE_LAUNCH_CHECK();
+  return DCAE_OK;
+}
+
+}  // namespace dcae

@@ -1,0 +1,183 @@
+"""Host-side mirror of the reference's channel-slice loop, running on libdcae_b200.so.
+
+`EntropySliceLoop` is what `DCAE.forward` (dcae.py:638-670), `DCAE.compress` (:713-753) and
+`DCAE.decompress` (:878-906) do between `(y, latent_scales, latent_means)` and
+`(y_hat, means, scales, likelihoods)` / `(symbols, indexes)`.  Inputs and outputs are the
+reference's NCHW fp32 CUDA tensors; everything in between is token-major inside the library.
+There is no torch math on this path and no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math as _math
+from typing import Callable, Dict, Optional
+
+import torch
+
+from . import _lib
+from .params import M_LATENT, NUM_SLICES, SLICE_CH
+from .weights import PackedWeights
+
+SCALES_MIN, SCALES_MAX, SCALES_LEVELS = 0.11, 256, 64
+
+
+def get_scale_table(min=SCALES_MIN, max=SCALES_MAX, levels=SCALES_LEVELS) -> torch.Tensor:
+    """dcae.py:54-55 (host-side constant table; the kernels always take the buffer, never recompute it)."""
+    return torch.exp(torch.linspace(_math.log(min), _math.log(max), levels))
+
+
+class _Plan:
+    """One dcae_slice_loop plan + its workspace for a fixed (B, h, w)."""
+
+    def __init__(self, eng: "EntropySliceLoop", B: int, h: int, w: int):
+        lib = eng.lib
+        nbytes = lib.dcae_slice_loop_workspace_bytes(B, h, w)
+        self.workspace = torch.empty(nbytes + 256, dtype=torch.uint8, device=eng.device)
+        base = (self.workspace.data_ptr() + 255) // 256 * 256
+        self.handle = C.c_void_p()
+        table = eng.scale_table.data_ptr() if eng.scale_table is not None else None
+        _lib.check(lib.dcae_slice_loop_create(C.byref(self.handle), B, h, w, eng.weights.array, table, base,
+                                              nbytes, _lib.MATH[eng.math]), "dcae_slice_loop_create")
+        self.lib = lib
+
+    def __del__(self):
+        try:
+            if self.handle:
+                self.lib.dcae_slice_loop_destroy(self.handle)
+        except Exception:
+            pass
+
+
+class EntropySliceLoop:
+    """params: reference state dict (hot-path keys).  math: 'fp32' | 'tf32x3' | 'tf32'."""
+
+    def __init__(self, params: Dict[str, torch.Tensor], device="cuda:0", math: str = "tf32x3",
+                 scale_table: Optional[torch.Tensor] = None):
+        if math not in _lib.MATH:
+            raise ValueError(f"math must be one of {list(_lib.MATH)}")
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.DcaeError("dcae_b200 runs on CUDA devices only (no CPU fallback)")
+        self.lib = _lib.load()
+        self.math = math
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.dcae_device_check(), "dcae_device_check")
+        self.weights = PackedWeights(params, self.device, split_tf32=True)
+        if scale_table is None:
+            scale_table = get_scale_table()
+        self.scale_table = scale_table.to(self.device, torch.float32).contiguous()
+        self._plans: Dict[tuple, _Plan] = {}
+        self.last_launches = 0
+
+    # ---- plumbing -------------------------------------------------------------------------------
+    def _plan(self, B, h, w) -> _Plan:
+        key = (B, h, w)
+        if key not in self._plans:
+            self._plans[key] = _Plan(self, B, h, w)
+        return self._plans[key]
+
+    def _check_in(self, name, t, B=None, C_=M_LATENT):
+        if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float32 and t.dim() == 4):
+            raise ValueError(f"{name}: expected a 4-D float32 CUDA tensor")
+        if t.device != self.device:
+            raise ValueError(f"{name}: tensor is on {t.device}, engine on {self.device}")
+        if t.shape[1] != C_:
+            raise ValueError(f"{name}: expected {C_} channels, got {t.shape[1]}")
+        return t.contiguous()
+
+    def _stream(self):
+        return _lib.current_stream(self.device)
+
+    # ---- DCAE.forward slice loop (eval mode or training noise) ----------------------------------
+    def forward(self, y, latent_scales, latent_means, noise: Optional[torch.Tensor] = None,
+                want_symbols: bool = False):
+        """-> dict(y_hat, means, scales, likelihoods [B,320,h,w], log2_lik_sum [1])
+        (+ symbols, indexes int32 [5,B,64,h,w] if want_symbols)."""
+        y = self._check_in("y", y)
+        ls = self._check_in("latent_scales", latent_scales)
+        lm = self._check_in("latent_means", latent_means)
+        B, _, h, w = y.shape
+        if ls.shape != y.shape or lm.shape != y.shape:
+            raise ValueError("y, latent_scales and latent_means must have the same shape")
+        if noise is not None:
+            noise = self._check_in("noise", noise)
+        plan, lib, s = self._plan(B, h, w), self.lib, self._stream()
+        out = {k: torch.empty_like(y) for k in ("y_hat", "means", "scales", "likelihoods")}
+        out["log2_lik_sum"] = torch.empty(1, device=self.device)
+        sym = idx = None
+        if want_symbols:
+            sym = torch.empty(NUM_SLICES, B, SLICE_CH, h, w, dtype=torch.int32, device=self.device)
+            idx = torch.empty_like(sym)
+            out["symbols"], out["indexes"] = sym, idx
+        if B == 0 or h == 0 or w == 0:
+            return out
+        with torch.cuda.device(self.device):
+            if noise is None:
+                _lib.check(lib.dcae_slice_loop_forward(plan.handle, y.data_ptr(), ls.data_ptr(), lm.data_ptr(),
+                                                       out["y_hat"].data_ptr(), out["means"].data_ptr(),
+                                                       out["scales"].data_ptr(), out["likelihoods"].data_ptr(),
+                                                       _lib.ptr(sym), _lib.ptr(idx), out["log2_lik_sum"].data_ptr(), s),
+                           "dcae_slice_loop_forward")
+            else:
+                _lib.check(lib.dcae_slice_loop_load(plan.handle, y.data_ptr(), ls.data_ptr(), lm.data_ptr(), s), "load")
+                for i, nz in enumerate(noise.chunk(NUM_SLICES, 1)):
+                    nz = nz.contiguous()
+                    _lib.check(lib.dcae_slice_loop_params(plan.handle, i, s), "params")
+                    _lib.check(lib.dcae_slice_loop_encode(plan.handle, i, _lib.GC_NOISE, nz.data_ptr(), s), "encode")
+                _lib.check(lib.dcae_slice_loop_store(plan.handle, out["y_hat"].data_ptr(), out["means"].data_ptr(),
+                                                     out["scales"].data_ptr(), out["likelihoods"].data_ptr(),
+                                                     _lib.ptr(sym), _lib.ptr(idx), out["log2_lik_sum"].data_ptr(), s), "store")
+        self.last_launches = int(lib.dcae_launch_count())
+        return out
+
+    # ---- DCAE.compress slice loop ---------------------------------------------------------------
+    def compress(self, y, latent_scales, latent_means, with_likelihoods: bool = False):
+        """-> dict(symbols, indexes int32 [5,B,64,h,w] in the reference's coder order (dcae.py:742-743),
+        y_hat, means, scales [, likelihoods])."""
+        out = self.forward(y, latent_scales, latent_means, want_symbols=True)
+        if not with_likelihoods:
+            out.pop("likelihoods", None)
+        return out
+
+    # ---- DCAE.decompress slice loop -------------------------------------------------------------
+    def decompress(self, latent_scales, latent_means,
+                   decode_slice: Callable[[int, torch.Tensor], torch.Tensor]):
+        """decode_slice(i, indexes int32 [B,64,h,w] on device) -> symbols (int tensor, same shape) plays
+        the rANS decoder of dcae.py:893.  -> dict(y_hat, indexes [5,B,64,h,w])."""
+        ls = self._check_in("latent_scales", latent_scales)
+        lm = self._check_in("latent_means", latent_means)
+        B, _, h, w = ls.shape
+        plan, lib, s = self._plan(B, h, w), self.lib, self._stream()
+        y_hat = torch.empty_like(ls)
+        idx_all = torch.empty(NUM_SLICES, B, SLICE_CH, h, w, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(lib.dcae_slice_loop_load(plan.handle, None, ls.data_ptr(), lm.data_ptr(), s), "load")
+            launches = 0
+            for i in range(NUM_SLICES):
+                _lib.check(lib.dcae_slice_loop_params(plan.handle, i, s), "params")
+                _lib.check(lib.dcae_slice_loop_indexes(plan.handle, i, idx_all[i].data_ptr(), s), "indexes")
+                sym = decode_slice(i, idx_all[i])
+                sym = torch.as_tensor(sym).to(self.device, torch.int32).reshape(B, SLICE_CH, h, w).contiguous()
+                _lib.check(lib.dcae_slice_loop_decode(plan.handle, i, sym.data_ptr(), s), "decode")
+            _lib.check(lib.dcae_slice_loop_store(plan.handle, y_hat.data_ptr(), None, None, None, None, None, None, s), "store")
+        self.last_launches = int(lib.dcae_launch_count())
+        return {"y_hat": y_hat, "indexes": idx_all}
+
+    # ---- debugging / stage-wise parity (the reference's debug_save pattern, dcae_5_fixed.py:29-34) ---
+    def tap(self, name: str, B: int, h: int, w: int) -> torch.Tensor:
+        """Copy of a named token-major intermediate [T, cols] of the most recent call."""
+        plan = self._plan(B, h, w)
+        p, cols, ld = C.c_void_p(), C.c_int32(), C.c_int64()
+        _lib.check(self.lib.dcae_slice_loop_tap(plan.handle, name.encode(), C.byref(p), C.byref(cols), C.byref(ld)), "tap")
+        T = B * h * w
+        base = (plan.workspace.data_ptr() + 255) // 256 * 256
+        off = (p.value - base) // 4
+        o = base - plan.workspace.data_ptr()
+        n = (plan.workspace.numel() - o) // 4 * 4
+        flat = plan.workspace[o: o + n].view(torch.float32)
+        return flat[off: off + T * ld.value].view(T, ld.value)[:, : cols.value].clone()
+
+
+def bits_per_pixel(log2_lik_sum: torch.Tensor, num_pixels: int) -> torch.Tensor:
+    """train.py:82-85 with the log2 sum the slice loop already reduced: bpp = -sum(log2 lik) / num_pixels."""
+    return -log2_lik_sum / float(num_pixels)

@@ -1,0 +1,258 @@
+/*
+ * dcae_b200.h -- C ABI of libdcae_b200.so: the B200 (sm_100a) implementation of the DCAE
+ * entropy-model hot path.
+ *
+ * Drop-in boundary.  The reference has no native code; its "FFI" for this
+ * path is the Python operator interface of `/root/reference/models/dcae.py` plus compressai's
+ * `GaussianConditional`.  Every entry point below names the reference call it replaces.
+ *
+ * Conventions
+ *   - plain C types only; all pointers are DEVICE pointers unless named `*_host`;
+ *   - the caller owns every buffer (inputs, outputs, workspace); nothing is allocated here except
+ *     the small host-side plan object returned by dcae_slice_loop_create();
+ *   - work is enqueued on the given CUDA stream (a `cudaStream_t`, passed as void*) and the call
+ *     returns immediately; no host synchronisation inside;
+ *   - return 0 on success, a negative DCAE_E_* code otherwise; dcae_last_error() returns a
+ *     thread-local message;
+ *   - results are deterministic (no atomics, fixed reduction order) and independent of B.
+ *
+ * Activations inside the library are TOKEN-MAJOR fp32: a matrix [T, C] with T = B*h*w tokens in
+ * (b, y, x) order and an explicit leading dimension `ld` (elements).  NCHW tensors only appear at
+ * the slice-loop entry/exit (dcae_slice_loop_*), where the reference's callers hold them.
+ */
+#ifndef DCAE_B200_H_
+#define DCAE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DCAE_B200_VERSION 100 /* 0.1.0 */
+
+enum {
+  DCAE_OK = 0,
+  DCAE_E_INVALID = -1,   /* bad argument (null pointer, misaligned, unsupported shape) */
+  DCAE_E_CUDA = -2,      /* a CUDA runtime / driver call failed */
+  DCAE_E_WORKSPACE = -3, /* workspace too small */
+  DCAE_E_DEVICE = -4     /* not running on an sm_100 device */
+};
+
+/* GEMM arithmetic selection for the dense layers (A1-A3 of SURVEY section 8a). */
+enum {
+  DCAE_MATH_FP32_SIMT = 0, /* FFMA reference path: fp32 in, fp32 accumulate */
+  DCAE_MATH_TF32X3 = 1,    /* tcgen05 kind::tf32, error-compensated 3-pass split: fp32-level accuracy */
+  DCAE_MATH_TF32 = 2       /* tcgen05 kind::tf32 single pass (like torch allow_tf32=True) */
+};
+
+int dcae_version(void);
+const char* dcae_last_error(void);
+/* 0 if the current device is compute capability 10.x, DCAE_E_DEVICE otherwise. */
+int dcae_device_check(void);
+
+/* --------------------------------------------------------------------------------------------
+ * Kernel 3: GaussianConditional in one HBM pass.
+ * Replaces compressai GaussianConditional.forward / quantize / build_indexes / dequantize as
+ * called at dcae.py:657-659 (forward), :738-740 (compress), :891-896 (decompress); math of
+ * dcae.py:839-857 and dcae.py:57-58.
+ *
+ * The tensors are viewed as `rows` rows of `inner` contiguous fp32 (inner % 4 == 0, 16-byte aligned
+ * rows), each tensor with its own row stride, so both NCHW slices (rows = B, inner = 64*h*w,
+ * y row stride 320*h*w) and token-major slices (rows = T, inner = 64) are expressible.
+ *
+ * mode DCAE_GC_EVAL   : out = rint(y - mu) + mu
+ * mode DCAE_GC_NOISE  : out = y + noise            (training; noise supplied by the caller)
+ * mode DCAE_GC_DECODE : out = float(symbols_in) + mu   (y unused; lik not produced)
+ * y_hat  <- rint(y - mu) + mu (EVAL/NOISE: the straight-through value of dcae.py:659) or out (DECODE)
+ * lik    <- max(0.5 erfc(c (0.5-v)/s) - 0.5 erfc(c (-0.5-v)/s), lik_bound), v = |out - mu|,
+ *           s = max(scale, scale_bound), c = -(2^-0.5)
+ * sym    <- int32(rint(y - mu));   idx <- #{ j < n_table-1 : table[j] < s }
+ * Any output pointer may be NULL.  log2_partials (nullable, >= dcae_gc_num_partials() floats)
+ * receives per-block sums of log2(lik) in a fixed order (bpp numerator, train.py:82-85).
+ * ------------------------------------------------------------------------------------------*/
+enum { DCAE_GC_EVAL = 0, DCAE_GC_NOISE = 1, DCAE_GC_DECODE = 2 };
+
+typedef struct {
+  const float* y;          int64_t y_ld;
+  const float* mu;         int64_t mu_ld;
+  const float* scale;      int64_t scale_ld;
+  const float* noise;      int64_t noise_ld;      /* NOISE mode only */
+  const int32_t* sym_in;   int64_t sym_in_ld;     /* DECODE mode only */
+  const float* scale_table; int32_t n_table;      /* the module's scale_table buffer (64 entries) */
+  float scale_bound;                              /* 0.11 */
+  float lik_bound;                                /* 1e-9 */
+  int32_t mode;
+  int64_t rows; int64_t inner;
+  float* y_hat;   int64_t y_hat_ld;
+  float* lik;     int64_t lik_ld;
+  int32_t* sym;   int64_t sym_ld;
+  int32_t* idx;   int64_t idx_ld;
+  float* log2_partials;
+} dcae_gc_args;
+
+int dcae_gc_fused(const dcae_gc_args* a, void* stream);
+/* number of per-block partial sums dcae_gc_fused writes for this problem size */
+int64_t dcae_gc_num_partials(int64_t rows, int64_t inner);
+/* out[0] = sum(partials[0..n)) in index order, one block (deterministic). */
+int dcae_reduce_partials(const float* partials, int64_t n, float* out, void* stream);
+
+/* --------------------------------------------------------------------------------------------
+ * Elementary token-major operators (each replaces one torch dispatch chain of dcae.py:300-509).
+ * ------------------------------------------------------------------------------------------*/
+
+/* A-operand of a GEMM: columns [col0, col0+k0) then [col1, col1+k1) of a token-major buffer,
+ * optionally gathered over the 9 taps of a 3x3 / stride 1 / pad 1 window (taps = 9), in which case
+ * K = 9*(k0+k1) ordered tap-major (tap = 3*(dy+1) + (dx+1)).  k0, k1 multiples of 32. */
+typedef struct {
+  const float* base; int64_t ld;
+  int32_t col0, k0, col1, k1;
+  int32_t taps;            /* 1 or 9 */
+  int32_t B, h, w;         /* token grid */
+} dcae_operand;
+
+enum { DCAE_ACT_NONE = 0, DCAE_ACT_GELU = 1, DCAE_ACT_HALF_TANH = 2 };
+
+/* out[t, n] = act_n( acc[t, n] + bias[n] + addend[t, n] ) + residual[t, n] * res_scale[n]
+ * act applies to columns n < act_cols (all columns if act_cols <= 0 or >= N).
+ * bias, addend, residual, res_scale nullable (res_scale NULL means 1). */
+typedef struct {
+  const float* bias;
+  const float* addend;   int64_t addend_ld;
+  const float* residual; int64_t residual_ld;
+  const float* res_scale;
+  int32_t act; int32_t act_cols;
+  float* out; int64_t out_ld;
+} dcae_epilogue;
+
+/* Dense weight [N, K] row-major (K contiguous; nn.Linear layout).  `w` is the fp32 weight;
+ * w_hi / w_lo are its TF32 split (w_hi = tf32(w), w_lo = tf32(w - w_hi)) made by dcae_split_tf32,
+ * required by the tcgen05 paths. */
+typedef struct {
+  const float* w; const float* w_hi; const float* w_lo;
+  int32_t N; int32_t K;
+} dcae_weight;
+
+/* nn.Linear / 1x1 conv / 3x3 conv as one GEMM: acc[T, N] = A[T, K] * W[N, K]^T.
+ * Replaces F.linear / F.conv2d dispatches of dcae.py:482-507 and :584-611. */
+int dcae_op_gemm(const dcae_operand* a, const dcae_weight* w, const dcae_epilogue* e, int math, void* stream);
+int dcae_split_tf32(const float* w, float* w_hi, float* w_lo, int64_t n, void* stream);
+
+/* LayerNorm over C channels per token, eps 1e-5 (dcae.py:461,465,467,471). */
+int dcae_op_layernorm(const float* x, int64_t x_ld, const float* gamma, const float* beta, int32_t C,
+                      int64_t T, float* out, int64_t out_ld, void* stream);
+/* out = gelu(x) (exact erf form), [T, C] (dcae.py:421-423 prologue GELU of the dense block). */
+int dcae_op_gelu(const float* x, int64_t x_ld, int32_t C, int64_t T, float* out, int64_t out_ld, void* stream);
+/* Depthwise 3x3, stride 1, pad 1 on a token grid (dcae.py:303,404): wt is [9, C] tap-major.
+ * out = act(dw(x) + bias) * gate   (gate nullable: ConvolutionalGLU, dcae.py:325-326). */
+int dcae_op_dwconv3x3(const float* x, int64_t x_ld, const float* wt, const float* bias, int32_t C,
+                      int32_t B, int32_t h, int32_t w, int32_t act, const float* gate, int64_t gate_ld,
+                      float* out, int64_t out_ld, void* stream);
+/* SpatialAttentionModule + residual (dcae.py:386-397, 446, 484):
+ * out = s_out * sigmoid(conv7x7([mean_c s_out, max_c s_out])) + res_scale * x0.
+ * stats: scratch [T, 2].  w7: [2, 7, 7]. */
+int dcae_op_spatial_gate(const float* s_out, int64_t s_ld, const float* x0, int64_t x0_ld,
+                         const float* res_scale, const float* w7, int32_t C, int32_t B, int32_t h, int32_t w,
+                         float* stats, float* out, int64_t out_ld, void* stream);
+/* Dictionary attention core (dcae.py:489-501): per head e (20 heads of 32):
+ * out[t, e, :] = softmax_j( q[t, e, :] . K[e, j, :] * head_scale[e] ) V[e, j, :], j < 128.
+ * Kh, Vh: [20, 128, 32].  */
+int dcae_op_dict_attention(const float* q, int64_t q_ld, const float* Kh, const float* Vh,
+                           const float* head_scale, int64_t T, float* out, int64_t out_ld, int math, void* stream);
+/* 'b c h w -> (b h w) c' and back, for a channel window of the token-major buffer. */
+int dcae_op_nchw_to_tokens(const float* src, int32_t B, int32_t C, int64_t HW, float* dst, int64_t dst_ld, void* stream);
+int dcae_op_tokens_to_nchw(const float* src, int64_t src_ld, int32_t B, int32_t C, int64_t HW, float* dst, void* stream);
+int dcae_op_tokens_to_nchw_i32(const int32_t* src, int64_t src_ld, int32_t B, int32_t C, int64_t HW, int32_t* dst, void* stream);
+int dcae_op_nchw_to_tokens_i32(const int32_t* src, int32_t B, int32_t C, int64_t HW, int32_t* dst, int64_t dst_ld, void* stream);
+
+/* --------------------------------------------------------------------------------------------
+ * The channel-slice loop (dcae.py:638-670 forward, :713-753 compress, :878-906 decompress).
+ * Packed weights of one slice i.  Dense weights are dcae_weight (row-major [N, K]); packing rules
+ * (done by dcae_b200/weights.py from a reference state dict):
+ *   - 3x3 conv weights [N, C, 3, 3] -> [N, 9, C'] (tap-major K), with the input channels permuted
+ *     from the reference's `support = [latent_scales, latent_means, y_hat_0.., dict_info]` order to
+ *     this library's support-buffer order `[dict_info, latent_scales, latent_means, y_hat_0..]`;
+ *   - cc1 = rows [cc_mean.0 (224) | cc_scale.0 (224) | lrp.0 restricted to the support channels (224)];
+ *     lrp1y = lrp.0 restricted to its last 64 input channels (the current y_hat slice);
+ *   - depthwise weights [C, 1, 3, 3] -> [9, C];
+ *   - Kh = per-head split of k(LN_dict(dt)), Vh = per-head split of LN_dict(dt)   [20, 128, 32]
+ *     (batch invariant, dcae.py:492-495; computed once per weight load).
+ * ------------------------------------------------------------------------------------------*/
+typedef struct {
+  dcae_weight x_trans;  const float* x_trans_b;
+  const float* ln_scale_g; const float* ln_scale_b;
+  dcae_weight msa_s;    const float* msa_s_b;
+  dcae_weight dense_in[3];  const float* dense_in_b[3];
+  const float* dense_dw[3]; const float* dense_dw_b[3];
+  dcae_weight dense_out[3]; const float* dense_out_b[3];
+  dcae_weight dense_proj;   const float* dense_proj_b;
+  const float* spatial_w7;
+  const float* res_scale_1; const float* res_scale_2; const float* res_scale_3;
+  const float* lnx_g; const float* lnx_b;
+  dcae_weight q_trans;  const float* q_trans_b;
+  const float* Kh; const float* Vh; const float* head_scale;
+  dcae_weight linear;   const float* linear_b;
+  const float* ln_mlp_g; const float* ln_mlp_b;
+  dcae_weight fc1;      const float* fc1_b;
+  const float* mlp_dw;  const float* mlp_dw_b;
+  dcae_weight fc2;      const float* fc2_b;
+  dcae_weight output_trans; const float* output_trans_b;
+  dcae_weight cc1;      const float* cc1_b;          /* N = 672, bias = [mean.0.b | scale.0.b | 0] */
+  dcae_weight mean2;    const float* mean2_b;        /* [128, 9*224] */
+  dcae_weight scale2;   const float* scale2_b;
+  dcae_weight mean3;    const float* mean3_b;        /* [64, 9*128] */
+  dcae_weight scale3;   const float* scale3_b;
+  dcae_weight lrp1y;    const float* lrp1_b;         /* [224, 9*64], bias of lrp.0 */
+  dcae_weight lrp2;     const float* lrp2_b;
+  dcae_weight lrp3;     const float* lrp3_b;
+} dcae_slice_weights;
+
+typedef struct dcae_slice_loop dcae_slice_loop;
+
+size_t dcae_slice_loop_workspace_bytes(int32_t B, int32_t h, int32_t w);
+/* weights: array of 5; scale_table: device [64]; workspace: device, 256-byte aligned. */
+int dcae_slice_loop_create(dcae_slice_loop** out, int32_t B, int32_t h, int32_t w,
+                           const dcae_slice_weights* weights, const float* scale_table,
+                           void* workspace, size_t workspace_bytes, int math);
+void dcae_slice_loop_destroy(dcae_slice_loop* p);
+
+/* NCHW fp32 [B,320,h,w] -> token-major workspace.  y may be NULL (decompress). */
+int dcae_slice_loop_load(dcae_slice_loop* p, const float* y, const float* latent_scales,
+                         const float* latent_means, void* stream);
+/* slice i: dict_info, mu, scale (dcae.py:644-655); idx if `want_indexes`. */
+int dcae_slice_loop_params(dcae_slice_loop* p, int32_t i, void* stream);
+/* slice i: quantise + likelihood + indexes (kernel 3) then LRP (dcae.py:657-664 / :738-750).
+ * gc_mode DCAE_GC_EVAL or DCAE_GC_NOISE (noise: NCHW [B,64,h,w] for this slice, or NULL). */
+int dcae_slice_loop_encode(dcae_slice_loop* p, int32_t i, int32_t gc_mode, const float* noise, void* stream);
+/* slice i of decompress: indexes for the coder are available after _params (dcae_slice_loop_indexes);
+ * then y_hat = symbols + mu and LRP (dcae.py:891-904).  symbols: NCHW int32 [B,64,h,w]. */
+int dcae_slice_loop_indexes(dcae_slice_loop* p, int32_t i, int32_t* indexes_nchw, void* stream);
+int dcae_slice_loop_decode(dcae_slice_loop* p, int32_t i, const int32_t* symbols_nchw, void* stream);
+/* Token-major workspace -> the caller's NCHW tensors; any pointer may be NULL.
+ * y_hat/means/scales/lik: fp32 [B,320,h,w]; symbols/indexes: int32 [5,B,64,h,w] (the reference's
+ * coder order, dcae.py:742-743).  log2_lik_sum: 1 float = sum log2(lik) (deterministic). */
+int dcae_slice_loop_store(dcae_slice_loop* p, float* y_hat, float* means, float* scales, float* lik,
+                          int32_t* symbols, int32_t* indexes, float* log2_lik_sum, void* stream);
+/* load + 5 x (params, encode) + store. */
+int dcae_slice_loop_forward(dcae_slice_loop* p, const float* y, const float* latent_scales,
+                            const float* latent_means, float* y_hat, float* means, float* scales,
+                            float* lik, int32_t* symbols, int32_t* indexes, float* log2_lik_sum, void* stream);
+/* Debug/test access to a named token-major intermediate of the last call ("x0","x1","q","attn","x2",
+ * "x3","support","h1"...): returns pointer, columns and ld; 0 on success. */
+int dcae_slice_loop_tap(dcae_slice_loop* p, const char* name, const float** ptr, int32_t* cols, int64_t* ld);
+/* Number of kernels the last dcae_slice_loop_* call enqueued (bench `gpu_launches`). */
+int64_t dcae_launch_count(void);
+
+/* Optional per-kernel-family timing with CUDA events on the launching stream (bench.py roofline).
+ * Families: 0 = dense GEMM (work = 2*T*N*K flop), 1 = dictionary attention core (work = 327680 flop per
+ * token), 2 = kernel 3 (work = algorithmic bytes: 4 B per tensor touched per element), 3 = other
+ * elementwise kernels (work = 0).  dcae_profile_stop synchronises the device and fills 4-entry arrays. */
+enum { DCAE_PROF_GEMM = 0, DCAE_PROF_ATTN = 1, DCAE_PROF_GC = 2, DCAE_PROF_OTHER = 3, DCAE_PROF_FAMILIES = 4 };
+int dcae_profile_start(void);
+int dcae_profile_stop(double* ms, double* work, int64_t* launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DCAE_B200_H_ */

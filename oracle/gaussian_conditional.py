@@ -128,11 +128,12 @@ def _standardized_quantile(q: float) -> float:
 def pmf_to_quantized_cdf(pmf, precision: int = 16):
     """Restatement of compressai's C++ `pmf_to_quantized_cdf` (rans interface)."""
     cdf = [0] * (len(pmf) + 1)
-    total = float(sum(pmf))
     for i, p in enumerate(pmf):
-        cdf[i + 1] = int(round(p / total * (1 << precision)))
+        cdf[i + 1] = int(round(float(p) * (1 << precision)))      # std::round(p * 2^precision)
+    total = sum(cdf)
+    cdf = [((1 << precision) * c) // total for c in cdf]          # integer renormalisation (floor)
     for i in range(1, len(cdf)):
-        cdf[i] += cdf[i - 1]
+        cdf[i] += cdf[i - 1]                                       # std::partial_sum
     cdf[-1] = 1 << precision
     for i in range(len(cdf) - 1):
         if cdf[i] == cdf[i + 1]:

@@ -1,0 +1,102 @@
+"""Thin test-side wrappers that call the C ABI ops with torch CUDA tensors."""
+import torch
+
+from dcae_b200 import _lib
+
+
+def _s(dev):
+    return _lib.current_stream(dev)
+
+
+def split_weight(w2d: torch.Tensor):
+    lib = _lib.load()
+    w = w2d.contiguous()
+    hi, lo = torch.empty_like(w), torch.empty_like(w)
+    _lib.check(lib.dcae_split_tf32(w.data_ptr(), hi.data_ptr(), lo.data_ptr(), w.numel(), _s(w.device)))
+    return hi, lo
+
+
+def gemm(buf, B, h, w, col0, k0, weight2d, math="fp32", taps=1, col1=0, k1=0, bias=None, addend=None,
+         residual=None, res_scale=None, act=0, act_cols=0, out=None, out_col=0):
+    """buf: token-major [T, ld] CUDA fp32.  weight2d: [N, K].  Returns out [T, N] (or writes into `out`)."""
+    lib = _lib.load()
+    T, ld = buf.shape
+    N, K = weight2d.shape
+    wt = weight2d.contiguous()
+    hi, lo = split_weight(wt)
+    a = _lib.Operand(buf.data_ptr(), ld, col0, k0, col1, k1, taps, B, h, w)
+    W = _lib.Weight(wt.data_ptr(), hi.data_ptr(), lo.data_ptr(), N, K)
+    if out is None:
+        out = torch.zeros(T, N, device=buf.device)
+    e = _lib.Epilogue()
+    e.bias = _lib.ptr(bias)
+    if addend is not None:
+        e.addend, e.addend_ld = addend.data_ptr(), addend.stride(0)
+    if residual is not None:
+        e.residual, e.residual_ld = residual.data_ptr(), residual.stride(0)
+    e.res_scale = _lib.ptr(res_scale)
+    e.act, e.act_cols = act, act_cols
+    e.out, e.out_ld = out.data_ptr() + 4 * out_col, out.stride(0)
+    _lib.check(lib.dcae_op_gemm(a, W, e, _lib.MATH[math], _s(buf.device)), "dcae_op_gemm")
+    return out
+
+
+def layernorm(x, g, b):
+    lib = _lib.load()
+    out = torch.empty_like(x)
+    _lib.check(lib.dcae_op_layernorm(x.data_ptr(), x.stride(0), g.data_ptr(), b.data_ptr(), x.shape[1], x.shape[0],
+                                     out.data_ptr(), out.stride(0), _s(x.device)))
+    return out
+
+
+def gelu(x):
+    lib = _lib.load()
+    out = torch.empty_like(x)
+    _lib.check(lib.dcae_op_gelu(x.data_ptr(), x.stride(0), x.shape[1], x.shape[0], out.data_ptr(), out.stride(0), _s(x.device)))
+    return out
+
+
+def dwconv3x3(x, wt9c, bias, B, h, w, act=0, gate=None):
+    lib = _lib.load()
+    C = wt9c.shape[1]
+    out = torch.empty(x.shape[0], C, device=x.device)
+    _lib.check(lib.dcae_op_dwconv3x3(x.data_ptr(), x.stride(0), wt9c.data_ptr(), bias.data_ptr(), C, B, h, w, act,
+                                     _lib.ptr(gate), gate.stride(0) if gate is not None else 0,
+                                     out.data_ptr(), out.stride(0), _s(x.device)))
+    return out
+
+
+def spatial_gate(s_out, x0, res_scale, w7, B, h, w):
+    lib = _lib.load()
+    out = torch.empty_like(s_out)
+    stats = torch.empty(s_out.shape[0], 2, device=s_out.device)
+    _lib.check(lib.dcae_op_spatial_gate(s_out.data_ptr(), s_out.stride(0), x0.data_ptr(), x0.stride(0), res_scale.data_ptr(),
+                                        w7.data_ptr(), s_out.shape[1], B, h, w, stats.data_ptr(), out.data_ptr(),
+                                        out.stride(0), _s(s_out.device)))
+    return out
+
+
+def dict_attention(q, Kh, Vh, head_scale, math="fp32"):
+    lib = _lib.load()
+    out = torch.empty_like(q)
+    _lib.check(lib.dcae_op_dict_attention(q.data_ptr(), q.stride(0), Kh.data_ptr(), Vh.data_ptr(), head_scale.data_ptr(),
+                                          q.shape[0], out.data_ptr(), out.stride(0), _lib.MATH[math], _s(q.device)))
+    return out
+
+
+def nchw_to_tokens(x):
+    lib = _lib.load()
+    B, C, H, W = x.shape
+    out = torch.empty(B * H * W, C, device=x.device, dtype=x.dtype)
+    fn = lib.dcae_op_nchw_to_tokens if x.dtype == torch.float32 else lib.dcae_op_nchw_to_tokens_i32
+    _lib.check(fn(x.contiguous().data_ptr(), B, C, H * W, out.data_ptr(), C, _s(x.device)))
+    return out
+
+
+def tokens_to_nchw(t, B, H, W):
+    lib = _lib.load()
+    C = t.shape[1]
+    out = torch.empty(B, C, H, W, device=t.device, dtype=t.dtype)
+    fn = lib.dcae_op_tokens_to_nchw if t.dtype == torch.float32 else lib.dcae_op_tokens_to_nchw_i32
+    _lib.check(fn(t.data_ptr(), t.stride(0), B, C, H * W, out.data_ptr(), _s(t.device)))
+    return out

@@ -1,0 +1,169 @@
+"""GPU parity of kernel 3 (dcae_gc_fused via the C ABI) against the CPU oracle restatement of
+compressai's GaussianConditional.  Bar: symbols and indexes bit-exact; likelihood within 1e-5
+relative (after the 1e-9 floor), tolerance written below."""
+import pytest
+import torch
+
+from oracle import gaussian_conditional as orc
+
+pytestmark = pytest.mark.gpu
+
+LIK_RTOL = 1e-5     # north-star tolerance for likelihoods
+LIK_ATOL = 2e-10    # the floor is 1e-9; differences below a fifth of the floor are erfc ulp noise
+
+
+def _gc():
+    from dcae_b200.gaussian_conditional import GaussianConditional
+    g = GaussianConditional(None).cuda()
+    g.update_scale_table(orc.get_scale_table())
+    return g
+
+
+def _direct_inputs(shape, seed=4321):
+    """SURVEY §8d direct inputs: y = 4 randn, mu = 2 randn, scale log-uniform over [0.05, 300]."""
+    g = torch.Generator().manual_seed(seed)
+    y = 4 * torch.randn(shape, generator=g)
+    mu = 2 * torch.randn(shape, generator=g)
+    scale = torch.exp(torch.empty(shape).uniform_(-3.0, 5.7, generator=g))
+    return y, mu, scale
+
+
+def _assert_lik_close(got, want):
+    err = (got.double() - want.double()).abs()
+    tol = LIK_RTOL * want.double().abs() + LIK_ATOL
+    assert bool((err <= tol).all()), f"max rel err {float((err / want.double().abs()).max()):.3e}"
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 16, 16), (1, 64, 7, 9), (3, 64, 32, 48)])
+def test_eval_forward_symbols_indexes_likelihood(shape):
+    gc = _gc()
+    y, mu, scale = _direct_inputs(shape)
+    sym, idx, y_hat, lik = gc.fused(y.cuda(), scale.cuda(), mu.cuda())
+    assert torch.equal(sym.cpu(), orc.quantize(y, "symbols", mu))
+    assert torch.equal(idx.cpu(), orc.build_indexes(scale, orc.get_scale_table()))
+    assert torch.equal(y_hat.cpu(), orc.quantize(y, "dequantize", mu))
+    want = orc.lower_bound(orc.likelihood(orc.quantize(y, "dequantize", mu), scale, mu), 1e-9)
+    _assert_lik_close(lik.cpu(), want)
+    # the reference's surface, one call each
+    out, lik2 = gc(y.cuda(), scale.cuda(), mu.cuda(), training=False)
+    assert torch.equal(out, y_hat) and torch.equal(lik2, lik)
+    assert torch.equal(gc.quantize(y.cuda(), "symbols", mu.cuda()), sym)
+    assert torch.equal(gc.build_indexes(scale.cuda()), idx)
+    assert torch.equal(gc.dequantize(sym, mu.cuda()), y_hat)
+    assert torch.equal(gc.dequantize(sym.float(), mu.cuda()), y_hat)   # decoder hands floats (dcae.py:894)
+
+
+def test_strided_nchw_slice_view_like_the_reference_call_site():
+    """dcae.py:638,657: y_slice is a chunk(5, 1) view -> batch stride 320*h*w, no copy."""
+    gc = _gc()
+    g = torch.Generator().manual_seed(3)
+    y = (4 * torch.randn(2, 320, 8, 12, generator=g)).cuda()
+    _, mu, scale = _direct_inputs((2, 64, 8, 12), seed=9)
+    for i, ys in enumerate(y.chunk(5, 1)):
+        sym, idx, y_hat, lik = gc.fused(ys, scale.cuda(), mu.cuda())
+        assert torch.equal(sym.cpu(), orc.quantize(ys.cpu(), "symbols", mu))
+
+
+def test_round_half_to_even_and_scale_edges():
+    gc = _gc()
+    table = orc.get_scale_table()
+    d = torch.tensor([0.5, -0.5, 1.5, -1.5, 2.5, -2.5, 3.5, 0.49999997, -0.49999997, 1e6 + 0.5, 0.0, -0.0])
+    mu = torch.tensor([0.25] * 12)
+    y = d + mu
+    edge = torch.cat([torch.tensor([-1.0, 0.0, 0.11, 1e4, float("inf"), 255.99, 256.0, 257.0, 0.1099999, 0.1100001]),
+                      table, torch.nextafter(table, torch.tensor(0.0)), torch.nextafter(table, torch.tensor(1e9))])
+    n = (max(len(d), len(edge)) + 3) // 4 * 4
+    yv = torch.zeros(1, n); yv[0, :len(y)] = y
+    mv = torch.zeros(1, n); mv[0, :len(mu)] = mu
+    sv = torch.ones(1, n); sv[0, :len(edge)] = edge
+    sym, idx, y_hat, lik = gc.fused(yv.cuda(), sv.cuda(), mv.cuda())
+    assert torch.equal(sym.cpu(), orc.quantize(yv, "symbols", mv))
+    assert torch.equal(idx.cpu(), orc.build_indexes(sv, table))
+    want = orc.lower_bound(orc.likelihood(orc.quantize(yv, "dequantize", mv), sv, mv), 1e-9)
+    _assert_lik_close(lik.cpu(), want)
+    assert int(idx.min()) == 0 and int(idx.max()) == 63
+
+
+def test_nan_propagation_matches_torch():
+    gc = _gc()
+    y = torch.tensor([[1.0, float("nan"), 2.0, 3.0]])
+    mu = torch.tensor([[0.0, 0.0, float("nan"), 0.0]])
+    sc = torch.tensor([[1.0, 1.0, 1.0, float("nan")]])
+    sym, idx, y_hat, lik = gc.fused(y.cuda(), sc.cuda(), mu.cuda())
+    want_idx = orc.build_indexes(sc, orc.get_scale_table())
+    assert torch.equal(idx.cpu(), want_idx)           # NaN scale -> index 63 (no threshold compares true)
+    want = orc.lower_bound(orc.likelihood(orc.quantize(y, "dequantize", mu), sc, mu), 1e-9)
+    assert torch.equal(torch.isnan(lik.cpu()), torch.isnan(want))
+
+
+def test_likelihood_floor_and_far_tail():
+    gc = _gc()
+    y = torch.tensor([[0.0, 40.0, 400.0, -1e6]])
+    mu = torch.zeros(1, 4)
+    sc = torch.tensor([[0.11, 1.0, 1.0, 0.5]])
+    _, _, _, lik = gc.fused(y.cuda(), sc.cuda(), mu.cuda())
+    want = orc.lower_bound(orc.likelihood(orc.quantize(y, "dequantize", mu), sc, mu), 1e-9)
+    _assert_lik_close(lik.cpu(), want)
+    assert float(lik.min()) == pytest.approx(1e-9)
+
+
+def test_training_noise_mode():
+    gc = _gc()
+    y, mu, scale = _direct_inputs((2, 64, 8, 8), seed=5)
+    noise = torch.empty_like(y).uniform_(-0.5, 0.5, generator=torch.Generator().manual_seed(1))
+    out, lik = gc(y.cuda(), scale.cuda(), mu.cuda(), training=True, noise=noise.cuda())
+    want_out, want_lik = orc.GaussianConditionalOracle()(y, scale, mu, training=True, noise=noise)
+    assert torch.equal(out.cpu(), want_out)
+    _assert_lik_close(lik.cpu(), want_lik)
+
+
+def test_empty_ragged_and_missing_table():
+    from dcae_b200 import _lib
+    from dcae_b200.gaussian_conditional import GaussianConditional
+    gc = _gc()
+    e = torch.empty(0, 64, 4, 4).cuda()
+    sym, idx, y_hat, lik = gc.fused(e, e, e)
+    assert sym.shape == e.shape and idx.numel() == 0
+    # ragged: 1-D tensor whose length is not a multiple of 4
+    y, mu, scale = _direct_inputs((37,), seed=2)
+    sym, idx, y_hat, lik = gc.fused(y.cuda(), scale.cuda(), mu.cuda())
+    assert torch.equal(sym.cpu(), orc.quantize(y, "symbols", mu))
+    assert torch.equal(idx.cpu(), orc.build_indexes(scale, orc.get_scale_table()))
+    # build_indexes before update_scale_table is an error, as in compressai (empty table)
+    with pytest.raises(_lib.DcaeError):
+        GaussianConditional(None).cuda().build_indexes(scale.cuda())
+    # CPU tensors are refused: there is no CPU fallback
+    with pytest.raises(_lib.DcaeError):
+        gc.build_indexes(scale)
+
+
+def test_cdf_tables_cover_emitted_symbols():
+    """sym - offset[idx] must fall inside cdf_length[idx] - 2 except in the tails."""
+    gc = _gc()
+    y, mu, scale = _direct_inputs((2, 64, 16, 16))
+    y = mu + (y - mu).clamp(-3, 3) * scale.clamp(0.11, 256) * 0.5   # within +-1.5 sigma
+    sym, idx, _, _ = gc.fused(y.cuda(), scale.cuda(), mu.cuda())
+    off = gc.offset[idx.long()]
+    ln = gc.cdf_length[idx.long()]
+    v = sym - off
+    assert bool(((v >= 0) & (v < ln - 2)).all())
+    assert tuple(gc.quantized_cdf.shape) == (64, 3133) and int(gc.cdf_length.max()) == 3133
+
+
+def test_large_input_properties_and_log2_sum():
+    """Config-2 size (16 x 64 x 32 x 48 per slice): size-independent properties."""
+    gc = _gc()
+    y, mu, scale = _direct_inputs((16, 64, 32, 48), seed=77)
+    yc, mc, sc = y.cuda(), mu.cuda(), scale.cuda()
+    sym, idx, y_hat, lik = gc.fused(yc, sc, mc)
+    # quantise -> dequantise round trip is the identity on y_hat; re-quantising y_hat is idempotent
+    assert torch.equal(gc.dequantize(sym, mc), y_hat)
+    assert torch.equal(gc.quantize(y_hat, "symbols", mc), sym)
+    assert bool(((y_hat - yc).abs() <= 0.5 + 1e-5 * yc.abs()).all())
+    # indexes are monotone in scale
+    order = torch.argsort(sc.flatten())
+    assert bool((idx.flatten()[order].diff() >= 0).all())
+    assert bool(((lik >= 1e-9) & (lik <= 1.0)).all())
+    # run-to-run determinism
+    sym2, idx2, y_hat2, lik2 = gc.fused(yc, sc, mc)
+    assert torch.equal(lik, lik2) and torch.equal(sym, sym2) and torch.equal(idx, idx2)
