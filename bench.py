@@ -58,7 +58,7 @@ class ClockSampler:
     def __init__(self, index):
         self.rows, self.proc = [], None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -133,7 +133,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--math", default="tf32x3", choices=["tf32x3", "tf32", "fp32"])
@@ -198,9 +198,15 @@ def main():
         barrier()
         return float(ms) / steps, out
 
+    # the sampler starts BEFORE the warm-up: nvidia-smi/NVML start-up briefly stalls the driver and must
+    # not land inside the timed region
+    sampler = ClockSampler(local) if rank == 0 else None
     for _ in range(max(args.warmup, 3)):
         step_resident()
-    sampler = ClockSampler(local) if rank == 0 else None
+    torch.cuda.synchronize()
+    time.sleep(0.3)
+    for _ in range(2):
+        step_resident()
     ms_step, out = timed(step_resident, args.steps)
     clocks = sampler.stop() if sampler else None
     launches = eng.last_launches

@@ -18,6 +18,8 @@
 // Every mbarrier wait is bounded: a protocol bug traps instead of hanging the GPU.
 #include <cuda.h>
 
+#include <stdlib.h>
+
 #include <mutex>
 
 #include "common.cuh"
@@ -29,9 +31,13 @@ namespace {
 constexpr int BM = 128;        // tokens per tile (TMEM lanes)
 constexpr int BK = 32;         // fp32 per k-block = 128 B = one swizzle row
 constexpr int UMMA_K = 8;      // tf32
-constexpr int MAX_STAGES = 4;
+constexpr int MAX_STAGES = 8;
 constexpr int A_BYTES = BM * BK * 4;   // 16 KB
-constexpr int NTHREADS = 192;
+constexpr int NTHREADS = 512;     // 16 warps, see the role table at the kernel
+constexpr int NDRAIN = 256;       // drain/epilogue threads (warps 8..15)
+constexpr int MAX_GROUPS = 8;     // 16-column groups per drain thread: BN/2 <= 128
+constexpr int REGS_CTRL = 40, REGS_SPLIT = 64, REGS_DRAIN = 200;   // 128*40 + 128*64 + 256*200 <= 65536
+constexpr int CHUNK_MMAS = 96;    // longest TMEM accumulation chain (RZ bias ~1.75e-8 per MMA)
 constexpr uint32_t SMEM_LIMIT = 227 * 1024;
 
 struct TcParams {
@@ -42,6 +48,8 @@ struct TcParams {
   int taps;
   int B, h, w, TH, TW, tiles_x, tiles_y;
   int BN, stages, tmem_cols;
+  int n_tiles_n, total_tiles, chunk_kb;
+  int dbg_nosplit, dbg_nostore;   // tuning experiments only (env DCAE_TC_NOSPLIT / DCAE_TC_NOSTORE): wrong results
   uint32_t stage_bytes, b_bytes;
 };
 
@@ -121,6 +129,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
 __device__ __forceinline__ float tf32_rna(float v) {
   uint32_t o;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(o) : "f"(v));
@@ -132,24 +149,30 @@ __device__ __forceinline__ float act_apply(float v, int act) {
   return v;
 }
 
+// Persistent kernel: grid = min(#tiles, #SMs); each CTA walks tiles t = blockIdx.x + i * gridDim.x in
+// (token-tile major, n-tile minor) order so that CTAs running together share A tiles through L2.
+//
+// Accuracy: the tensor core's fp32 accumulator rounds toward zero, which biases a long accumulation
+// chain by ~1.75e-8 per MMA (measured: 5.7e-5 at K = 8640).  Each TMEM chain is therefore limited to
+// `chunk_kb` k-blocks (96 MMAs in the 3-pass mode); chains alternate between two TMEM buffers and the
+// drain warps add the chunk partials into fp32 registers with round-to-nearest while the MMA warp is
+// already filling the other buffer.  The same double buffering overlaps the epilogue of tile i with
+// the mainloop of tile i+1.
+//
+// Warps: 0 = TMA producer, 1 = TMEM owner + MMA issuer, 2-3 idle, 4-7 = split warps (3-pass mode),
+// 8-15 = drain/epilogue (two warps per TMEM lane quarter, half of the BN columns each).
+// Registers are re-balanced with setmaxnreg: the drain warps hold BN/2 running sums per thread.
 template <int PASSES>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bh,
                     const __grid_constant__ CUtensorMap map_bl, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t full_bar[MAX_STAGES], ready_bar[MAX_STAGES], empty_bar[MAX_STAGES], accum_bar;
+  __shared__ __align__(8) uint64_t full_bar[MAX_STAGES], ready_bar[MAX_STAGES], empty_bar[MAX_STAGES];
+  __shared__ __align__(8) uint64_t tmem_full_bar[2], tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_slot;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B atoms need 1024-B alignment
-
-  // tile coordinates
-  const int n0 = blockIdx.x * p.BN;
-  int mt = blockIdx.y;
-  const int tile_x = mt % p.tiles_x; mt /= p.tiles_x;
-  const int tile_y = mt % p.tiles_y;
-  const int b = mt / p.tiles_y;
-  const int x0 = tile_x * p.TW, y0 = tile_y * p.TH;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
@@ -157,7 +180,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       mbar_init(smem_u32(&ready_bar[s]), 128);
       mbar_init(smem_u32(&empty_bar[s]), 1);
     }
-    mbar_init(smem_u32(&accum_bar), 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&tmem_full_bar[b]), 1);
+      mbar_init(smem_u32(&tmem_empty_bar[b]), NDRAIN);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0 && lane == 0) {
@@ -172,126 +198,186 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_acc = tmem_base_slot;
+  const uint32_t tmem_base = tmem_base_slot;
 
   // per-stage smem carve-up: [A | A_lo (x3) | B_hi | B_lo (x3)]
   const uint32_t off_al = A_BYTES;
   const uint32_t off_bh = (PASSES == 3) ? 2 * A_BYTES : A_BYTES;
   const uint32_t off_bl = off_bh + p.b_bytes;
+  const int n_chunks = (p.KB + p.chunk_kb - 1) / p.chunk_kb;
 
-  if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+  auto tile_coords = [&](int t, int& b, int& y0, int& x0, int& n0) {
+    const int nt = t % p.n_tiles_n;
+    int mt = t / p.n_tiles_n;
+    const int tile_x = mt % p.tiles_x; mt /= p.tiles_x;
+    const int tile_y = mt % p.tiles_y;
+    b = mt / p.tiles_y;
+    x0 = tile_x * p.TW; y0 = tile_y * p.TH; n0 = nt * p.BN;
+  };
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_CTRL));
+    if (warp == 0 && lane == 0) {
+      // ===================== TMA producer =====================
       int stage = 0;
       uint32_t phase = 0;
-      for (int kb = 0; kb < p.KB; ++kb) {
-        mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
-        const uint32_t sbase = smem0 + stage * p.stage_bytes;
-        const uint32_t fb = smem_u32(&full_bar[stage]);
-        mbar_expect_tx(fb, A_BYTES + (PASSES == 3 ? 2 : 1) * p.b_bytes);
-        const int tap = kb / p.cblk_per_tap;
-        const int c = (kb - tap * p.cblk_per_tap) * BK;
-        const int col = (c < p.k0) ? (p.col0 + c) : (p.col1 + (c - p.k0));
-        int dy = 0, dx = 0;
-        if (p.taps == 9) { dy = tap / 3 - 1; dx = tap % 3 - 1; }
-        tma_load_4d(sbase, &map_a, fb, col, x0 + dx, y0 + dy, b);
-        tma_load_2d(sbase + off_bh, &map_bh, fb, kb * BK, n0);
-        if (PASSES == 3) tma_load_2d(sbase + off_bl, &map_bl, fb, kb * BK, n0);
-        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        int b, y0, x0, n0;
+        tile_coords(t, b, y0, x0, n0);
+        for (int kb = 0; kb < p.KB; ++kb) {
+          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+          const uint32_t sbase = smem0 + stage * p.stage_bytes;
+          const uint32_t fb = smem_u32(&full_bar[stage]);
+          mbar_expect_tx(fb, A_BYTES + (PASSES == 3 ? 2 : 1) * p.b_bytes);
+          const int tap = kb / p.cblk_per_tap;
+          const int c = (kb - tap * p.cblk_per_tap) * BK;
+          const int col = (c < p.k0) ? (p.col0 + c) : (p.col1 + (c - p.k0));
+          int dy = 0, dx = 0;
+          if (p.taps == 9) { dy = tap / 3 - 1; dx = tap % 3 - 1; }
+          tma_load_4d(sbase, &map_a, fb, col, x0 + dx, y0 + dy, b);
+          tma_load_2d(sbase + off_bh, &map_bh, fb, kb * BK, n0);
+          if (PASSES == 3) tma_load_2d(sbase + off_bl, &map_bl, fb, kb * BK, n0);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
       }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    } else if (warp == 1 && lane == 0) {
+      // ===================== MMA issuer =====================
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       int stage = 0;
-      uint32_t phase = 0;
-      for (int kb = 0; kb < p.KB; ++kb) {
-        mbar_wait(smem_u32(PASSES == 3 ? &ready_bar[stage] : &full_bar[stage]), phase);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t sbase = smem0 + stage * p.stage_bytes;
+      uint32_t phase = 0, gchunk = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        for (int ck = 0; ck < n_chunks; ++ck, ++gchunk) {
+          const uint32_t buf = gchunk & 1;
+          mbar_wait(smem_u32(&tmem_empty_bar[buf]), ((gchunk >> 1) & 1) ^ 1);   // drained by the epilogue warps
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t tmem_acc = tmem_base + buf * (uint32_t)p.BN;
+          const int kb_end = min(p.KB, (ck + 1) * p.chunk_kb);
+          for (int kb = ck * p.chunk_kb; kb < kb_end; ++kb) {
+            mbar_wait(smem_u32((PASSES == 3 && !p.dbg_nosplit) ? &ready_bar[stage] : &full_bar[stage]), phase);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t sbase = smem0 + stage * p.stage_bytes;
+            const uint32_t first = (kb == ck * p.chunk_kb) ? 0u : 1u;
 #pragma unroll
-        for (int k = 0; k < BK / UMMA_K; ++k) {
-          const uint32_t koff = k * UMMA_K * 4;
-          const uint64_t a_hi = make_smem_desc(sbase + koff);
-          const uint64_t b_hi = make_smem_desc(sbase + off_bh + koff);
-          if (PASSES == 3) {
-            const uint64_t a_lo = make_smem_desc(sbase + off_al + koff);
-            const uint64_t b_lo = make_smem_desc(sbase + off_bl + koff);
-            mma_tf32(tmem_acc, a_lo, b_hi, idesc, (kb | k) != 0);
-            mma_tf32(tmem_acc, a_hi, b_lo, idesc, 1);
-            mma_tf32(tmem_acc, a_hi, b_hi, idesc, 1);
-          } else {
-            mma_tf32(tmem_acc, a_hi, b_hi, idesc, (kb | k) != 0);
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint32_t koff = k * UMMA_K * 4;
+              const uint64_t a_hi = make_smem_desc(sbase + koff);
+              const uint64_t b_hi = make_smem_desc(sbase + off_bh + koff);
+              if (PASSES == 3) {
+                const uint64_t a_lo = make_smem_desc(sbase + off_al + koff);
+                const uint64_t b_lo = make_smem_desc(sbase + off_bl + koff);
+                mma_tf32(tmem_acc, a_lo, b_hi, idesc, first | (uint32_t)(k != 0));
+                mma_tf32(tmem_acc, a_hi, b_lo, idesc, 1);
+                mma_tf32(tmem_acc, a_hi, b_hi, idesc, 1);
+              } else {
+                mma_tf32(tmem_acc, a_hi, b_hi, idesc, first | (uint32_t)(k != 0));
+              }
+            }
+            mma_commit(smem_u32(&empty_bar[stage]));       // frees the smem slot once these MMAs retire
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
+          mma_commit(smem_u32(&tmem_full_bar[buf]));       // this chain is complete
         }
-        mma_commit(smem_u32(&empty_bar[stage]));       // frees the smem slot once these MMAs retire
-        if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
-      mma_commit(smem_u32(&accum_bar));                // accumulator complete
     }
-  } else {
-    // ===================== split warps (x3), then epilogue =====================
-    const int st = threadIdx.x - 64;   // 0..127
-    if (PASSES == 3) {
+  } else if (warp < 8) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_SPLIT));
+    if (PASSES == 3 && !p.dbg_nosplit) {
+      // ===================== split warps: a -> (a_hi in place, a_lo) =====================
+      const int st = threadIdx.x - 128;   // 0..127
       int stage = 0;
       uint32_t phase = 0;
-      for (int kb = 0; kb < p.KB; ++kb) {
-        mbar_wait(smem_u32(&full_bar[stage]), phase);
-        const uint32_t sbase = smem0 + stage * p.stage_bytes;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        for (int kb = 0; kb < p.KB; ++kb) {
+          mbar_wait(smem_u32(&full_bar[stage]), phase);
+          const uint32_t sbase = smem0 + stage * p.stage_bytes;
 #pragma unroll
-        for (int i = 0; i < A_BYTES / 16 / 128; ++i) {
-          const uint32_t off = (uint32_t)(st + i * 128) * 16;
-          float4 v;
-          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(sbase + off));
-          float4 hi, lo;
-          hi.x = tf32_rna(v.x); hi.y = tf32_rna(v.y); hi.z = tf32_rna(v.z); hi.w = tf32_rna(v.w);
-          lo.x = tf32_rna(v.x - hi.x); lo.y = tf32_rna(v.y - hi.y); lo.z = tf32_rna(v.z - hi.z); lo.w = tf32_rna(v.w - hi.w);
-          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sbase + off), "f"(hi.x), "f"(hi.y), "f"(hi.z), "f"(hi.w) : "memory");
-          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sbase + off_al + off), "f"(lo.x), "f"(lo.y), "f"(lo.z), "f"(lo.w) : "memory");
+          for (int i = 0; i < A_BYTES / 16 / 128; ++i) {
+            const uint32_t off = (uint32_t)(st + i * 128) * 16;
+            float4 v;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(sbase + off));
+            float4 hi, lo;
+            hi.x = tf32_rna(v.x); hi.y = tf32_rna(v.y); hi.z = tf32_rna(v.z); hi.w = tf32_rna(v.w);
+            lo.x = tf32_rna(v.x - hi.x); lo.y = tf32_rna(v.y - hi.y); lo.z = tf32_rna(v.z - hi.z); lo.w = tf32_rna(v.w - hi.w);
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sbase + off), "f"(hi.x), "f"(hi.y), "f"(hi.z), "f"(hi.w) : "memory");
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sbase + off_al + off), "f"(lo.x), "f"(lo.y), "f"(lo.z), "f"(lo.w) : "memory");
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA (async proxy)
+          mbar_arrive(smem_u32(&ready_bar[stage]));
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA (async proxy)
-        mbar_arrive(smem_u32(&ready_bar[stage]));
-        if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
     }
-    // ---- epilogue: TMEM lane quarter of this warp = warp % 4 ----
-    mbar_wait(smem_u32(&accum_bar), 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int quarter = warp & 3;
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_DRAIN));
+    // ===================== drain + epilogue warps =====================
+    const int quarter = warp & 3;                  // TMEM lane quarter this warp may touch
+    const int half = (warp - 8) >> 2;              // which half of the BN columns
+    const int half_cols = p.BN >> 1;               // multiple of 16
     const int r = quarter * 32 + lane;             // tile row = TMEM lane
     const int ty = r / p.TW, tx = r - ty * p.TW;
-    const int yy = y0 + ty, xx = x0 + tx;
-    const bool row_ok = (yy < p.h) && (xx < p.w);
-    const int64_t token = ((int64_t)b * p.h + yy) * p.w + xx;
     const dcae_epilogue& e = p.e;
     const int act_cols = (e.act_cols <= 0 || e.act_cols > p.N) ? p.N : e.act_cols;
-    for (int c = 0; c < p.BN; c += 32) {
-      uint32_t raw[32];
-      tmem_ld32(tmem_acc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c, raw);   // warp-collective
-      if (!row_ok) continue;
-      const int n = n0 + c;
-      float* orow = e.out + token * e.out_ld + n;
+    uint32_t gchunk = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      int b, y0, x0, n0;
+      tile_coords(t, b, y0, x0, n0);
+      float acc[MAX_GROUPS * 16];
+      for (int ck = 0; ck < n_chunks; ++ck, ++gchunk) {
+        const uint32_t buf = gchunk & 1;
+        mbar_wait(smem_u32(&tmem_full_bar[buf]), (gchunk >> 1) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * (uint32_t)p.BN + (uint32_t)(half * half_cols);
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        float4 v = make_float4(__uint_as_float(raw[j]), __uint_as_float(raw[j + 1]), __uint_as_float(raw[j + 2]), __uint_as_float(raw[j + 3]));
-        if (e.bias) {
-          const float4 bv = __ldg(reinterpret_cast<const float4*>(e.bias + n + j));
-          v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+        for (int g = 0; g < MAX_GROUPS; ++g) {
+          if (g * 16 < half_cols) {                 // warp-uniform
+            uint32_t raw[16];
+            tmem_ld16(taddr + g * 16, raw);
+            if (ck == 0) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) acc[g * 16 + j] = __uint_as_float(raw[j]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) acc[g * 16 + j] = __fadd_rn(acc[g * 16 + j], __uint_as_float(raw[j]));
+            }
+          }
         }
-        if (e.addend) {
-          const float4 ad = __ldg(reinterpret_cast<const float4*>(e.addend + token * e.addend_ld + n + j));
-          v.x += ad.x; v.y += ad.y; v.z += ad.z; v.w += ad.w;
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        mbar_arrive(smem_u32(&tmem_empty_bar[buf]));   // the MMA warp may start the next chain in this buffer
+      }
+      // ---- epilogue of this tile (overlaps the next tile's mainloop) ----
+      const int yy = y0 + ty, xx = x0 + tx;
+      if (yy < p.h && xx < p.w && !p.dbg_nostore) {
+        const int64_t token = ((int64_t)b * p.h + yy) * p.w + xx;
+        const int nb = n0 + half * half_cols;
+        float* orow = e.out + token * e.out_ld + nb;
+#pragma unroll
+        for (int g = 0; g < MAX_GROUPS; ++g) {
+          if (g * 16 < half_cols) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              const int cidx = g * 16 + j;
+              const int n = nb + cidx;
+              float4 v = make_float4(acc[cidx], acc[cidx + 1], acc[cidx + 2], acc[cidx + 3]);
+              if (e.bias) {
+                const float4 bv = __ldg(reinterpret_cast<const float4*>(e.bias + n));
+                v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+              }
+              if (e.addend) {
+                const float4 ad = __ldg(reinterpret_cast<const float4*>(e.addend + token * e.addend_ld + n));
+                v.x += ad.x; v.y += ad.y; v.z += ad.z; v.w += ad.w;
+              }
+              const int act = (n < act_cols) ? e.act : DCAE_ACT_NONE;
+              v.x = act_apply(v.x, act); v.y = act_apply(v.y, act); v.z = act_apply(v.z, act); v.w = act_apply(v.w, act);
+              if (e.residual) {
+                const float4 rv = __ldg(reinterpret_cast<const float4*>(e.residual + token * e.residual_ld + n));
+                float4 rs = make_float4(1.f, 1.f, 1.f, 1.f);
+                if (e.res_scale) rs = __ldg(reinterpret_cast<const float4*>(e.res_scale + n));
+                v.x = fmaf(rv.x, rs.x, v.x); v.y = fmaf(rv.y, rs.y, v.y); v.z = fmaf(rv.z, rs.z, v.z); v.w = fmaf(rv.w, rs.w, v.w);
+              }
+              *reinterpret_cast<float4*>(orow + cidx) = v;
+            }
+          }
         }
-        const int act = (n + j < act_cols) ? e.act : DCAE_ACT_NONE;
-        v.x = act_apply(v.x, act); v.y = act_apply(v.y, act); v.z = act_apply(v.z, act); v.w = act_apply(v.w, act);
-        if (e.residual) {
-          const float4 rv = __ldg(reinterpret_cast<const float4*>(e.residual + token * e.residual_ld + n + j));
-          float4 rs = make_float4(1.f, 1.f, 1.f, 1.f);
-          if (e.res_scale) rs = __ldg(reinterpret_cast<const float4*>(e.res_scale + n + j));
-          v.x = fmaf(rv.x, rs.x, v.x); v.y = fmaf(rv.y, rs.y, v.y); v.z = fmaf(rv.z, rs.z, v.z); v.w = fmaf(rv.w, rs.w, v.w);
-        }
-        *reinterpret_cast<float4*>(orow + j) = v;
       }
     }
   }
@@ -299,7 +385,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(p.tmem_cols) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
   }
 }
 
@@ -354,6 +440,10 @@ void pick_tile(int h, int w, int* TH, int* TW) {
 }
 
 int pick_bn(int N) {
+  if (const char* env = getenv("DCAE_TC_BN")) {   // tuning override (tools/gemm_bench.py)
+    const int bn = atoi(env);
+    if (bn >= 32 && bn <= 256 && bn % 32 == 0 && N % bn == 0) return bn;
+  }
   for (int bn = 256; bn >= 32; bn -= 32)
     if (N % bn == 0) return bn;
   return 0;
@@ -379,11 +469,18 @@ int gemm_tcgen05(const dcae_operand* a, const dcae_weight* w, const dcae_epilogu
   p.tiles_y = (a->h + p.TH - 1) / p.TH;
   p.BN = pick_bn(w->N);
   DCAE_REQUIRE(p.BN > 0, "gemm(tcgen05): N=%d must be a multiple of 32", w->N);
-  p.tmem_cols = p.BN <= 32 ? 32 : p.BN <= 64 ? 64 : p.BN <= 128 ? 128 : 256;
+  p.tmem_cols = 2 * p.BN <= 64 ? 64 : 2 * p.BN <= 128 ? 128 : 2 * p.BN <= 256 ? 256 : 512;   // two chain buffers
+  p.n_tiles_n = w->N / p.BN;
+  p.total_tiles = p.n_tiles_n * p.tiles_x * p.tiles_y * a->B;
+  p.chunk_kb = (passes == 3) ? CHUNK_MMAS / 12 : p.KB;   // 3-pass: 12 MMAs per k-block; 1-pass: one chain
   p.b_bytes = (uint32_t)p.BN * BK * 4;
   p.stage_bytes = (passes == 3) ? (2 * A_BYTES + 2 * p.b_bytes) : (A_BYTES + p.b_bytes);
   p.stages = (int)((SMEM_LIMIT - 2048) / p.stage_bytes);
   if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
+  if (const char* env = getenv("DCAE_TC_STAGES")) { const int v = atoi(env); if (v >= 1 && v < p.stages) p.stages = v; }
+  p.dbg_nosplit = getenv("DCAE_TC_NOSPLIT") != nullptr;
+  p.dbg_nostore = getenv("DCAE_TC_NOSTORE") != nullptr;
+  if (const char* env = getenv("DCAE_TC_CHUNK")) { const int v = atoi(env); if (v >= 1) p.chunk_kb = v; }
   if (p.stages > p.KB) p.stages = p.KB;
   DCAE_REQUIRE(p.stages >= 1, "gemm(tcgen05): tile does not fit in shared memory");
   const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
@@ -411,8 +508,8 @@ int gemm_tcgen05(const dcae_operand* a, const dcae_weight* w, const dcae_epilogu
       attr_err = cudaFuncSetAttribute(gemm_tcgen05_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT - 1024);
   });
   DCAE_CUDA(attr_err);
-  dim3 grid((unsigned)(w->N / p.BN), (unsigned)(p.tiles_x * p.tiles_y * a->B));
-  DCAE_REQUIRE(grid.y <= 65535u, "gemm(tcgen05): too many token tiles (%u)", grid.y);
+  const int ctas = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+  dim3 grid((unsigned)ctas);
   if (passes == 3) gemm_tcgen05_kernel<3><<<grid, NTHREADS, smem, s>>>(map_a, map_bh, map_bl, p);
   else gemm_tcgen05_kernel<1><<<grid, NTHREADS, smem, s>>>(map_a, map_bh, map_bl, p);
   DCAE_LAUNCH_CHECK();

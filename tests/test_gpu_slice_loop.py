@@ -16,7 +16,8 @@ from oracle.entropy_model import SliceLoopOracle
 pytestmark = pytest.mark.gpu
 
 FP32_TOL = 1e-5
-MODES = {"fp32": (FP32_TOL, 2e-3), "tf32x3": (FP32_TOL, 2e-3), "tf32": (2e-2, 0.15)}   # (rel tol, max sym/idx mismatch rate)
+# (per-slice teacher-forced rel tol, max teacher-forced sym/idx mismatch rate, max free-running mismatch rate)
+MODES = {"fp32": (FP32_TOL, 1e-3, 2e-3), "tf32x3": (FP32_TOL, 1e-3, 5e-2), "tf32": (1e-2, 5e-2, 0.3)}
 
 _engines = {}
 
@@ -30,25 +31,70 @@ def engine(params, math):
 
 @pytest.mark.parametrize("math", ["fp32", "tf32x3", "tf32"])
 @pytest.mark.parametrize("case", GOLDEN_CASES)
-def test_forward_and_compress_vs_reference_golden(case, math, lively_params):
+def test_per_slice_parity_vs_reference_golden(case, math, lively_params):
+    """Stage-wise parity, the only well-defined one: slice i is computed from the REFERENCE's
+    previous slices (its recorded symbols are replayed through the decode path, exactly what
+    DCAE.decompress does, dcae.py:893-896), so one flipped symbol cannot cascade into later slices.
+    Per slice: mu, scale within the fp32 bar; indexes / symbols bit-exact except where the reference
+    value sits within that tolerance of a rounding / table boundary (rate reported and bounded)."""
+    from dcae_b200 import _lib
     g = load_golden(case)
     eng = engine(lively_params, math)
-    tol, mm = MODES[math]
+    tol, mm, _ = MODES[math]
+    y, ls, lm = (g[k].cuda() for k in ("y", "latent_scales", "latent_means"))
+    B, _, h, w = y.shape
+    lib, plan, s = eng.lib, eng._plan(B, h, w), _lib.current_stream(eng.device)
+    _lib.check(lib.dcae_slice_loop_load(plan.handle, y.data_ptr(), ls.data_ptr(), lm.data_ptr(), s))
+    idx = torch.empty(B, 64, h, w, dtype=torch.int32, device="cuda")
+    worst = {"mu": 0.0, "scale": 0.0, "idx": 0.0, "sym": 0.0}
+    tok2img = lambda t: t.reshape(B, h, w, -1).permute(0, 3, 1, 2)
+    for i in range(5):
+        sl = slice(64 * i, 64 * i + 64)
+        _lib.check(lib.dcae_slice_loop_params(plan.handle, i, s))
+        _lib.check(lib.dcae_slice_loop_indexes(plan.handle, i, idx.data_ptr(), s))
+        mu = tok2img(eng.tap("means", B, h, w)[:, sl]).cpu()
+        sc = tok2img(eng.tap("scales", B, h, w)[:, sl]).cpu()
+        worst["mu"] = max(worst["mu"], rel_err(mu, g["means"][:, sl]))
+        worst["scale"] = max(worst["scale"], rel_err(sc, g["scales"][:, sl]))
+        worst["idx"] = max(worst["idx"], mismatch_rate(idx.cpu(), g["indexes"][i]))
+        worst["sym"] = max(worst["sym"], mismatch_rate(ogc.quantize(g["y"][:, sl], "symbols", mu), g["symbols"][i]))
+        # kernel 3 is bit-exact given identical inputs: the device's own scale through the oracle
+        assert torch.equal(idx.cpu(), ogc.build_indexes(sc, ogc.get_scale_table()))
+        sym_ref = g["symbols"][i].cuda().contiguous()
+        _lib.check(lib.dcae_slice_loop_decode(plan.handle, i, sym_ref.data_ptr(), s))
+    y_hat = torch.empty_like(y)
+    _lib.check(lib.dcae_slice_loop_store(plan.handle, y_hat.data_ptr(), None, None, None, None, None, None, s))
+    torch.cuda.synchronize()
+    worst["y_hat"] = rel_err(y_hat.cpu(), g["y_hat"])
+    print(f"\n[{case} {math}] per-slice (teacher-forced) worst: " + ", ".join(f"{k} {v:.2e}" for k, v in worst.items()))
+    assert worst["mu"] < tol and worst["scale"] < tol and worst["y_hat"] < tol
+    assert worst["idx"] <= mm and worst["sym"] <= mm
+
+
+@pytest.mark.parametrize("math", ["fp32", "tf32x3", "tf32"])
+@pytest.mark.parametrize("case", GOLDEN_CASES)
+def test_free_running_forward_and_compress(case, math, lively_params):
+    """DCAE.forward / compress slice loop end to end (no teacher forcing).  A symbol that flips in slice i
+    changes y_hat by 1.0 and every later slice with it, so only the mismatch RATE is meaningful here; it is
+    reported and bounded.  Kernel 3 itself stays bit-exact on the device's own (y, mu, scale)."""
+    g = load_golden(case)
+    eng = engine(lively_params, math)
     y, ls, lm = (g[k].cuda() for k in ("y", "latent_scales", "latent_means"))
     out = eng.compress(y, ls, lm, with_likelihoods=True)
     torch.cuda.synchronize()
-    errs = {k: rel_err(out[k].cpu(), g[r]) for k, r in (("means", "means"), ("scales", "scales"))}
     rates = {k: mismatch_rate(out[k].cpu(), g[k]) for k in ("symbols", "indexes")}
-    print(f"\n[{case} {math}] rel_err {errs}  mismatch vs reference {rates}  launches {eng.last_launches}")
-    assert errs["means"] < tol and errs["scales"] < tol
-    assert rates["symbols"] <= mm and rates["indexes"] <= mm
-    # where the symbols agree, y_hat and the likelihood must agree to fp32 accuracy
-    if math != "tf32":
-        same = (out["symbols"].cpu() == g["symbols"]).permute(1, 0, 2, 3, 4).reshape(g["y_hat"].shape)
-        assert rel_err(torch.where(same, out["y_hat"].cpu(), g["y_hat"]), g["y_hat"]) < 1e-4
-    # kernel 3 is bit-exact given identical inputs: quantise the DEVICE's mu/scale with the oracle
+    errs = {k: rel_err(out[k].cpu(), g[k]) for k in ("means", "scales")}
+    print(f"\n[{case} {math}] free-running: mismatch vs reference {rates}, rel_err {errs}, launches {eng.last_launches}")
+    assert max(rates.values()) <= MODES[math][2]
+    if math == "fp32":
+        # observed: symbols identical to the reference; at most one index in 40 320 differs (a scale within
+        # 2e-6 of a table entry) -- the torch-CPU oracle itself shows 3e-5 against the torch-CPU reference
+        assert rates["symbols"] == 0.0 and rates["indexes"] <= 2e-4
+        assert errs["means"] < FP32_TOL and errs["scales"] < FP32_TOL
+        assert rel_err(out["y_hat"].cpu(), g["y_hat"]) < FP32_TOL
+        lik, want = out["likelihoods"].cpu().double(), g["lik"].double()
+        assert bool(((lik - want).abs() <= 1e-4 * want + 3e-7).all())   # mu/scale differ by 1e-6 -> amplified in the tails
     mu, sc = out["means"].cpu(), out["scales"].cpu()
-    B = y.shape[0]
     for i in range(5):
         sl = slice(64 * i, 64 * i + 64)
         assert torch.equal(out["symbols"][i].cpu(), ogc.quantize(g["y"][:, sl], "symbols", mu[:, sl]))
@@ -149,9 +195,10 @@ def test_kodak_shape_properties(lively_params):
     # symbols are exactly round(y - mu) for the device's own means
     sym = torch.stack([torch.round(y[:, 64 * i:64 * i + 64] - enc["means"][:, 64 * i:64 * i + 64]).int() for i in range(5)])
     assert torch.equal(sym, enc["symbols"])
-    # fp32 SIMT and tf32x3 agree to fp32 accuracy on a full-size problem
+    # fp32 SIMT and tf32x3 agree to fp32 accuracy on a full-size problem (slice 0: nothing has cascaded yet)
     ref = engine(lively_params, "fp32").compress(y, ls, lm)
-    assert rel_err(enc["means"], ref["means"]) < FP32_TOL and rel_err(enc["scales"], ref["scales"]) < FP32_TOL
+    assert rel_err(enc["means"][:, :64], ref["means"][:, :64]) < FP32_TOL
+    assert rel_err(enc["scales"][:, :64], ref["scales"][:, :64]) < FP32_TOL
 
 
 def test_input_validation(lively_params):
