@@ -50,45 +50,59 @@ def synth_latents(B, h, w, seed=1234, pin=False):
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock, power and throttle reasons sampled DURING the timed region through NVML in a thread of this
+    process (nvidia-smi -lms was measured to stall the GPU by tens of ms per query on this box, which is not
+    acceptable inside a 0.6 s timed region; the NVML calls below are the same counters without that cost)."""
 
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-
-    def __init__(self, index):
-        self.rows, self.proc = [], None
+    def __init__(self, index, period_s=0.1):
+        self.rows, self.ok, self._stop = [], False, threading.Event()
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
-                                          "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
+            import pynvml as nv
+            nv.nvmlInit()
+            self.nv, self.h = nv, nv.nvmlDeviceGetHandleByIndex(index)
+            self.max_sm = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:                      # noqa: BLE001
+            self.err = repr(e)
+            return
+        self.period = period_s
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:                   # noqa: BLE001
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.rows.append((sm, pw, rs))
+            except Exception:                       # noqa: BLE001
+                pass
+            self._stop.wait(self.period)
+
+    def mark(self):
+        """Only samples taken after this call count (call right before the timed region)."""
+        self.start = len(self.rows)
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], None, set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[0])); mx = float(r[1])
-            except Exception:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        sm.sort()
-        busy = [v for v in sm if v > 0]
-        return {"sm_mhz": busy[len(busy) // 2] if busy else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        if not self.ok:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: " + getattr(self, "err", "")]}
+        self._stop.set()
+        self.t.join(timeout=2)
+        nv = self.nv
+        rows = self.rows[getattr(self, "start", 0):]
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        reasons = sorted(n for n, bit in names.items() if any(r[2] & bit for r in rows))
+        sm = sorted(r[0] for r in rows)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_sm, "reasons": reasons,
+                "power_w_max": max((r[1] for r in rows), default=None), "samples": len(rows), "source": "nvml"}
 
 
 def cpu_oracle_rate(n_images, steps, warmup, seed=0):
@@ -198,15 +212,13 @@ def main():
         barrier()
         return float(ms) / steps, out
 
-    # the sampler starts BEFORE the warm-up: nvidia-smi/NVML start-up briefly stalls the driver and must
-    # not land inside the timed region
+    # the sampler starts BEFORE the warm-up (NVML start-up must not land inside the timed region)
     sampler = ClockSampler(local) if rank == 0 else None
     for _ in range(max(args.warmup, 3)):
         step_resident()
     torch.cuda.synchronize()
-    time.sleep(0.3)
-    for _ in range(2):
-        step_resident()
+    if sampler:
+        sampler.mark()
     ms_step, out = timed(step_resident, args.steps)
     clocks = sampler.stop() if sampler else None
     launches = eng.last_launches
@@ -215,10 +227,8 @@ def main():
     ms_e2e, _ = timed(step_e2e, args.steps)
 
     # bpp over all ranks: the only data-path reduction -- one scalar all-reduce
-    red = torch.stack([out["log2_lik_sum"].double().squeeze(), torch.tensor(float(B * H_IMG * W_IMG), device=dev, dtype=torch.double)])
-    if world > 1:
-        dist.all_reduce(red)
-    bpp = float(-red[0] / red[1])
+    from dcae_b200.sharding import reduce_bpp
+    bpp = reduce_bpp(out["log2_lik_sum"], B * H_IMG * W_IMG)
 
     # per-kernel-family device time of one instrumented step (CUDA events on the launching stream)
     ms = (C.c_double * 4)(); work = (C.c_double * 4)(); cnt = (C.c_int64 * 4)()

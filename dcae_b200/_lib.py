@@ -52,6 +52,11 @@ class Weight(C.Structure):
     _fields_ = [("w", c_f32p), ("w_hi", c_f32p), ("w_lo", c_f32p), ("N", C.c_int32), ("K", C.c_int32)]
 
 
+class DictKV(C.Structure):
+    _fields_ = [("Kh", c_f32p), ("Vh", c_f32p), ("Kh_hi", c_f32p), ("Kh_lo", c_f32p),
+                ("Vt_hi", c_f32p), ("Vt_lo", c_f32p), ("head_scale", c_f32p)]
+
+
 class SliceWeights(C.Structure):
     _fields_ = [
         ("x_trans", Weight), ("x_trans_b", c_f32p),
@@ -65,7 +70,7 @@ class SliceWeights(C.Structure):
         ("res_scale_1", c_f32p), ("res_scale_2", c_f32p), ("res_scale_3", c_f32p),
         ("lnx_g", c_f32p), ("lnx_b", c_f32p),
         ("q_trans", Weight), ("q_trans_b", c_f32p),
-        ("Kh", c_f32p), ("Vh", c_f32p), ("head_scale", c_f32p),
+        ("kv", DictKV),
         ("linear", Weight), ("linear_b", c_f32p),
         ("ln_mlp_g", c_f32p), ("ln_mlp_b", c_f32p),
         ("fc1", Weight), ("fc1_b", c_f32p),
@@ -101,7 +106,7 @@ SIGNATURES = {
     "dcae_op_gelu": (C.c_int, [_P, _I64, _I32, _I64, _P, _I64, _P]),
     "dcae_op_dwconv3x3": (C.c_int, [_P, _I64, _P, _P, _I32, _I32, _I32, _I32, _I32, _P, _I64, _P, _I64, _P]),
     "dcae_op_spatial_gate": (C.c_int, [_P, _I64, _P, _I64, _P, _P, _I32, _I32, _I32, _I32, _P, _P, _I64, _P]),
-    "dcae_op_dict_attention": (C.c_int, [_P, _I64, _P, _P, _P, _I64, _P, _I64, C.c_int, _P]),
+    "dcae_op_dict_attention": (C.c_int, [_P, _I64, C.POINTER(DictKV), _I64, _P, _I64, C.c_int, _P]),
     "dcae_op_nchw_to_tokens": (C.c_int, [_P, _I32, _I32, _I64, _P, _I64, _P]),
     "dcae_op_tokens_to_nchw": (C.c_int, [_P, _I64, _I32, _I32, _I64, _P, _P]),
     "dcae_op_tokens_to_nchw_i32": (C.c_int, [_P, _I64, _I32, _I32, _I64, _P, _P]),

@@ -122,14 +122,21 @@ extern "C" int dcae_op_gemm(const dcae_operand* a, const dcae_weight* w, const d
   return DCAE_E_INVALID;
 }
 
-extern "C" int dcae_op_dict_attention(const float* q, int64_t q_ld, const float* Kh, const float* Vh,
-                                      const float* head_scale, int64_t T, float* out, int64_t out_ld, int math, void* stream) {
-  DCAE_REQUIRE(q && Kh && Vh && head_scale && out, "dcae_op_dict_attention: null pointer");
-  DCAE_REQUIRE(aligned16(q) && aligned16(out) && aligned16(Kh) && aligned16(Vh) && q_ld % 4 == 0 && out_ld % 4 == 0 && q_ld >= 640 && out_ld >= 640,
+extern "C" int dcae_op_dict_attention(const float* q, int64_t q_ld, const dcae_dict_kv* kv, int64_t T, float* out,
+                                      int64_t out_ld, int math, void* stream) {
+  DCAE_REQUIRE(q && kv && kv->Kh && kv->Vh && kv->head_scale && out, "dcae_op_dict_attention: null pointer");
+  DCAE_REQUIRE(aligned16(q) && aligned16(out) && aligned16(kv->Kh) && aligned16(kv->Vh) && q_ld % 4 == 0 && out_ld % 4 == 0 && q_ld >= 640 && out_ld >= 640,
                "dcae_op_dict_attention: 16-byte alignment and ld >= 640 required");
-  (void)math;  // the tcgen05 attention core plugs in here; SIMT is the strict-fp32 mode
+  DCAE_REQUIRE(T >= 0 && T < (1ll << 31), "dcae_op_dict_attention: bad token count");
   ProfileScope prof(DCAE_PROF_ATTN, 327680.0 * (double)T, stream);
-  return dict_attention_simt(q, q_ld, Kh, Vh, head_scale, T, out, out_ld, (cudaStream_t)stream);
+  switch (math) {
+    case DCAE_MATH_FP32_SIMT:
+      return dict_attention_simt(q, q_ld, kv->Kh, kv->Vh, kv->head_scale, T, out, out_ld, (cudaStream_t)stream);
+    case DCAE_MATH_TF32X3: return dict_attention_tcgen05(q, q_ld, kv, T, out, out_ld, 3, (cudaStream_t)stream);
+    case DCAE_MATH_TF32: return dict_attention_tcgen05(q, q_ld, kv, T, out, out_ld, 1, (cudaStream_t)stream);
+  }
+  set_error("dcae_op_dict_attention: unknown math mode %d", math);
+  return DCAE_E_INVALID;
 }
 
 // =============================================================================================
@@ -272,7 +279,7 @@ static int run_dca(dcae_slice_loop* p, int i, void* s) {
   // q = q_trans(lnx(x)); attention against the dictionary                    dcae.py:486-501
   DCAE_TRY(dcae_op_layernorm(p->x1.p, D, W.lnx_g, W.lnx_b, D, T, p->ln.p, D, s));
   DCAE_TRY(gemm(p, opnd(p, p->ln.p, D, 0, D, 1), W.q_trans, epi(W.q_trans_b, p->q.p, D), s));
-  DCAE_TRY(dcae_op_dict_attention(p->q.p, D, W.Kh, W.Vh, W.head_scale, T, p->ao.p, D, p->math, s));
+  DCAE_TRY(dcae_op_dict_attention(p->q.p, D, &W.kv, T, p->ao.p, D, p->math, s));
   // output = linear(output) + res_scale_2(shortcut)                          dcae.py:503
   {
     dcae_epilogue e = epi(W.linear_b, p->x2.p, D);

@@ -94,8 +94,7 @@ class PackedWeights:
             setattr(W, f"res_scale_{r}", self._vec(g(f"res_scale_{r}.scale")))
         W.lnx_g, W.lnx_b = self._vec(g("lnx.weight")), self._vec(g("lnx.bias"))
         W.q_trans, W.q_trans_b = self._weight(g("q_trans.weight")), self._vec(g("q_trans.bias"))
-        W.head_scale = self._vec(g("scale"))
-        W.Kh, W.Vh = self._dictionary_kv(dt, g)
+        W.kv = self.dictionary_kv(dt, g("dict_ln.weight"), g("dict_ln.bias"), g("k.weight"), g("k.bias"), g("scale"))
         W.linear, W.linear_b = self._weight(g("linear.weight")), self._vec(g("linear.bias"))
         W.ln_mlp_g, W.ln_mlp_b = self._vec(g("ln_mlp.weight")), self._vec(g("ln_mlp.bias"))
         W.fc1, W.fc1_b = self._weight(g("mlp.fc1.weight")), self._vec(g("mlp.fc1.bias"))
@@ -122,16 +121,17 @@ class PackedWeights:
         W.scale3, W.scale3_b = self._weight(self._conv3x3_to_gemm(scale("4.weight"))), self._vec(scale("4.bias"))
         W.lrp3, W.lrp3_b = self._weight(self._conv3x3_to_gemm(lrp("4.weight"))), self._vec(lrp("4.bias"))
 
-    def _dictionary_kv(self, dt: torch.Tensor, g):
+    def dictionary_kv(self, dt, ln_w, ln_b, k_w, k_b, head_scale) -> _lib.DictKV:
         """K = k(dict_ln(dt)), V = dict_ln(dt), per head [20, 128, 32] (dcae.py:492-495); batch invariant,
-        so computed once here with the library's LayerNorm + fp32 GEMM."""
+        so computed once here with the library's LayerNorm + fp32 GEMM; plus the TF32 hi/lo splits of K and of
+        V transposed per head ([20, 32, 128]) that the tcgen05 attention kernel consumes."""
         lib, s = self.lib, _lib.current_stream(self.device)
+        dt = dt.to(self.device, torch.float32).contiguous()
         d = torch.empty(DICT_NUM, DICT_DIM, device=self.device)
-        gam, bet = self._dev(g("dict_ln.weight")), self._dev(g("dict_ln.bias"))
+        gam, bet = self._dev(ln_w), self._dev(ln_b)
         _lib.check(lib.dcae_op_layernorm(dt.data_ptr(), DICT_DIM, gam.data_ptr(), bet.data_ptr(), DICT_DIM, DICT_NUM,
                                          d.data_ptr(), DICT_DIM, s), "dcae_op_layernorm")
-        kw = self._dev(g("k.weight"))
-        kb = self._dev(g("k.bias"))
+        kw, kb = self._dev(k_w), self._dev(k_b)
         k = torch.empty(DICT_NUM, DICT_DIM, device=self.device)
         a = _lib.Operand(d.data_ptr(), DICT_DIM, 0, DICT_DIM, 0, 0, 1, 1, 1, DICT_NUM)
         w = _lib.Weight(kw.data_ptr(), None, None, DICT_DIM, DICT_DIM)
@@ -141,5 +141,14 @@ class PackedWeights:
         # 'n (e c) -> e n c'
         Kh = k.reshape(DICT_NUM, HEAD_NUM, HEAD_DIM).permute(1, 0, 2).contiguous()
         Vh = d.reshape(DICT_NUM, HEAD_NUM, HEAD_DIM).permute(1, 0, 2).contiguous()
-        self._keep += [Kh, Vh]
-        return Kh.data_ptr(), Vh.data_ptr()
+        Vt = Vh.transpose(1, 2).contiguous()          # [20, 32, 128]
+        kv = _lib.DictKV()
+        kv.Kh, kv.Vh, kv.head_scale = Kh.data_ptr(), Vh.data_ptr(), self._vec(head_scale)
+        self._keep += [Kh, Vh, Vt]
+        for src, hi_name, lo_name in ((Kh, "Kh_hi", "Kh_lo"), (Vt, "Vt_hi", "Vt_lo")):
+            hi, lo = torch.empty_like(src), torch.empty_like(src)
+            _lib.check(lib.dcae_split_tf32(src.data_ptr(), hi.data_ptr(), lo.data_ptr(), src.numel(), s), "dcae_split_tf32")
+            self._keep += [hi, lo]
+            setattr(kv, hi_name, hi.data_ptr())
+            setattr(kv, lo_name, lo.data_ptr())
+        return kv

@@ -157,9 +157,19 @@ int dcae_op_spatial_gate(const float* s_out, int64_t s_ld, const float* x0, int6
                          float* stats, float* out, int64_t out_ld, void* stream);
 /* Dictionary attention core (dcae.py:489-501): per head e (20 heads of 32):
  * out[t, e, :] = softmax_j( q[t, e, :] . K[e, j, :] * head_scale[e] ) V[e, j, :], j < 128.
- * Kh, Vh: [20, 128, 32].  */
-int dcae_op_dict_attention(const float* q, int64_t q_ld, const float* Kh, const float* Vh,
-                           const float* head_scale, int64_t T, float* out, int64_t out_ld, int math, void* stream);
+ * The dictionary side is batch invariant (dcae.py:492-495) and prepared once per weight load:
+ *   Kh, Vh            [20, 128, 32] fp32  (K = k(LN(dt)) and V = LN(dt), split per head)
+ *   Kh_hi, Kh_lo      TF32 split of Kh                      (tcgen05 paths)
+ *   Vt_hi, Vt_lo      TF32 split of Vh transposed per head, [20, 32, 128]
+ * math FP32_SIMT = FFMA kernel; TF32X3 / TF32 = kernel 1 (tcgen05 + TMEM, softmax in registers). */
+typedef struct {
+  const float* Kh; const float* Vh;
+  const float* Kh_hi; const float* Kh_lo;
+  const float* Vt_hi; const float* Vt_lo;
+  const float* head_scale;     /* [20] learned per-head scale (dcae.py:457,498) */
+} dcae_dict_kv;
+int dcae_op_dict_attention(const float* q, int64_t q_ld, const dcae_dict_kv* kv, int64_t T, float* out,
+                           int64_t out_ld, int math, void* stream);
 /* 'b c h w -> (b h w) c' and back, for a channel window of the token-major buffer. */
 int dcae_op_nchw_to_tokens(const float* src, int32_t B, int32_t C, int64_t HW, float* dst, int64_t dst_ld, void* stream);
 int dcae_op_tokens_to_nchw(const float* src, int64_t src_ld, int32_t B, int32_t C, int64_t HW, float* dst, void* stream);
@@ -191,7 +201,7 @@ typedef struct {
   const float* res_scale_1; const float* res_scale_2; const float* res_scale_3;
   const float* lnx_g; const float* lnx_b;
   dcae_weight q_trans;  const float* q_trans_b;
-  const float* Kh; const float* Vh; const float* head_scale;
+  dcae_dict_kv kv;
   dcae_weight linear;   const float* linear_b;
   const float* ln_mlp_g; const float* ln_mlp_b;
   dcae_weight fc1;      const float* fc1_b;

@@ -79,8 +79,14 @@ def spatial_gate(s_out, x0, res_scale, w7, B, h, w):
 def dict_attention(q, Kh, Vh, head_scale, math="fp32"):
     lib = _lib.load()
     out = torch.empty_like(q)
-    _lib.check(lib.dcae_op_dict_attention(q.data_ptr(), q.stride(0), Kh.data_ptr(), Vh.data_ptr(), head_scale.data_ptr(),
-                                          q.shape[0], out.data_ptr(), out.stride(0), _lib.MATH[math], _s(q.device)))
+    Kh, Vh = Kh.contiguous(), Vh.contiguous()
+    Vt = Vh.transpose(1, 2).contiguous()
+    khi, klo = split_weight(Kh)
+    vhi, vlo = split_weight(Vt)
+    kv = _lib.DictKV(Kh.data_ptr(), Vh.data_ptr(), khi.data_ptr(), klo.data_ptr(), vhi.data_ptr(), vlo.data_ptr(),
+                     head_scale.data_ptr())
+    _lib.check(lib.dcae_op_dict_attention(q.data_ptr(), q.stride(0), kv, q.shape[0], out.data_ptr(), out.stride(0),
+                                          _lib.MATH[math], _s(q.device)), "dcae_op_dict_attention")
     return out
 
 
