@@ -2,6 +2,7 @@
 
 Public surface (mirrors the reference's operator interface for this path only):
   EntropySliceLoop      -- the channel-slice loop of DCAE.forward/compress/decompress
+  HostPipeline          -- pinned-host-in / pinned-host-out streaming front end (overlapped copies)
   GaussianConditional   -- compressai-compatible quantise / likelihood / build_indexes (kernel 3)
   init_entropy_params   -- deterministic random-init weights with the reference's state-dict keys
 """
@@ -13,6 +14,9 @@ def __getattr__(name):
     if name in ("EntropySliceLoop", "get_scale_table", "bits_per_pixel"):
         from . import entropy_model
         return getattr(entropy_model, name)
+    if name == "HostPipeline":
+        from .pipeline import HostPipeline
+        return HostPipeline
     if name == "GaussianConditional":
         from .gaussian_conditional import GaussianConditional
         return GaussianConditional

@@ -63,38 +63,70 @@ __global__ void __launch_bounds__(256) gelu_kernel(const float* __restrict__ x, 
 // ---------------------------------------------------------------------------------------------
 // Depthwise 3x3 (stride 1, zero pad 1) on the token grid; weights tap-major [9, C].
 // out = act(dw(x) + bias) * gate
+// Each thread owns 4 channels of DW_X horizontally adjacent tokens: a 3 x (DW_X + 2) input patch is read
+// once (3.75 float4 loads per output instead of 9), consecutive threads take consecutive channel
+// groups so every load/store is a coalesced 16-byte access.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) dwconv3x3_kernel(const float* __restrict__ x, int64_t x_ld,
+constexpr int DW_X = 8;
+
+__global__ void __launch_bounds__(128) dwconv3x3_kernel(const float* __restrict__ x, int64_t x_ld,
                                                         const float* __restrict__ wt, const float* __restrict__ bias,
                                                         int C4, int B, int h, int w, int act,
                                                         const float* __restrict__ gate, int64_t gate_ld,
                                                         float* __restrict__ out, int64_t out_ld) {
-  const int64_t n4 = (int64_t)B * h * w * C4;
+  const int xg = (w + DW_X - 1) / DW_X;
+  const int64_t n = (int64_t)B * h * xg * C4;
   const int C = C4 * 4;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t t = i / C4;
-    const int c = (int)(i - t * C4) * 4;
-    const int xx = (int)(t % w);
-    const int yy = (int)((t / w) % h);
-    float4 acc = __ldg(reinterpret_cast<const float4*>(bias + c));
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C4) * 4;
+    int64_t r = i / C4;
+    const int x0 = (int)(r % xg) * DW_X;
+    r /= xg;
+    const int yy = (int)(r % h);
+    const int b = (int)(r / h);
+    float4 k[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) k[t] = __ldg(reinterpret_cast<const float4*>(wt + t * C + c));
+    const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + c));
+    float4 acc[DW_X];
+#pragma unroll
+    for (int j = 0; j < DW_X; ++j) acc[j] = bv;
 #pragma unroll
     for (int dy = -1; dy <= 1; ++dy) {
+      const int y2 = yy + dy;
+      if ((unsigned)y2 >= (unsigned)h) continue;
+      const float* row = x + ((int64_t)(b * h + y2) * w) * x_ld + c;
+      float4 p[DW_X + 2];
 #pragma unroll
-      for (int dx = -1; dx <= 1; ++dx) {
-        if ((unsigned)(yy + dy) < (unsigned)h && (unsigned)(xx + dx) < (unsigned)w) {
-          const float4 v = __ldg(reinterpret_cast<const float4*>(x + (t + dy * w + dx) * x_ld + c));
-          const float4 k = __ldg(reinterpret_cast<const float4*>(wt + ((dy + 1) * 3 + (dx + 1)) * C + c));
-          acc.x = fmaf(v.x, k.x, acc.x); acc.y = fmaf(v.y, k.y, acc.y);
-          acc.z = fmaf(v.z, k.z, acc.z); acc.w = fmaf(v.w, k.w, acc.w);
+      for (int j = 0; j < DW_X + 2; ++j) {
+        const int x2 = x0 - 1 + j;
+        p[j] = ((unsigned)x2 < (unsigned)w) ? __ldg(reinterpret_cast<const float4*>(row + (int64_t)x2 * x_ld))
+                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int j = 0; j < DW_X; ++j) {
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+          const float4 kk = k[(dy + 1) * 3 + dx];
+          const float4 v = p[j + dx];
+          acc[j].x = fmaf(v.x, kk.x, acc[j].x); acc[j].y = fmaf(v.y, kk.y, acc[j].y);
+          acc[j].z = fmaf(v.z, kk.z, acc[j].z); acc[j].w = fmaf(v.w, kk.w, acc[j].w);
         }
       }
     }
-    if (act == DCAE_ACT_GELU) { acc.x = gelu_erf(acc.x); acc.y = gelu_erf(acc.y); acc.z = gelu_erf(acc.z); acc.w = gelu_erf(acc.w); }
-    if (gate != nullptr) {
-      const float4 g = __ldg(reinterpret_cast<const float4*>(gate + t * gate_ld + c));
-      acc.x *= g.x; acc.y *= g.y; acc.z *= g.z; acc.w *= g.w;
+#pragma unroll
+    for (int j = 0; j < DW_X; ++j) {
+      const int x2 = x0 + j;
+      if (x2 >= w) break;
+      const int64_t t = (int64_t)(b * h + yy) * w + x2;
+      float4 a = acc[j];
+      if (act == DCAE_ACT_GELU) { a.x = gelu_erf(a.x); a.y = gelu_erf(a.y); a.z = gelu_erf(a.z); a.w = gelu_erf(a.w); }
+      if (gate != nullptr) {
+        const float4 g = __ldg(reinterpret_cast<const float4*>(gate + t * gate_ld + c));
+        a.x *= g.x; a.y *= g.y; a.z *= g.z; a.w *= g.w;
+      }
+      *reinterpret_cast<float4*>(out + t * out_ld + c) = a;
     }
-    *reinterpret_cast<float4*>(out + t * out_ld + c) = acc;
   }
 }
 
@@ -265,9 +297,9 @@ extern "C" int dcae_op_dwconv3x3(const float* x, int64_t x_ld, const float* wt, 
   DCAE_REQUIRE(C % 4 == 0 && x_ld % 4 == 0 && out_ld % 4 == 0 && (gate == nullptr || gate_ld % 4 == 0), "dcae_op_dwconv3x3: C and lds must be multiples of 4");
   DCAE_REQUIRE(aligned16(x) && aligned16(wt) && aligned16(bias) && aligned16(out) && aligned16(gate), "dcae_op_dwconv3x3: 16-byte alignment required");
   DCAE_REQUIRE(act == DCAE_ACT_NONE || act == DCAE_ACT_GELU, "dcae_op_dwconv3x3: act must be NONE or GELU");
-  const int64_t n4 = (int64_t)B * h * w * (C / 4);
+  const int64_t n4 = (int64_t)B * h * ((w + DW_X - 1) / DW_X) * (C / 4);
   if (n4 == 0) return DCAE_OK;
-  dwconv3x3_kernel<<<grid_for(n4, 256), 256, 0, (cudaStream_t)stream>>>(x, x_ld, wt, bias, C / 4, B, h, w, act, gate, gate_ld, out, out_ld);
+  dwconv3x3_kernel<<<grid_for(n4, 128), 128, 0, (cudaStream_t)stream>>>(x, x_ld, wt, bias, C / 4, B, h, w, act, gate, gate_ld, out, out_ld);
   DCAE_LAUNCH_CHECK();
   return DCAE_OK;
 }

@@ -19,6 +19,7 @@ struct GcParams {
   dcae_gc_args a;
   int64_t groups;   // rows * inner/4
   uint32_t inner4;
+  uint32_t shift;   // log2(inner4) when inner4 is a power of two
 };
 
 __device__ __forceinline__ float nan_max(float x, float bound) {
@@ -37,13 +38,16 @@ __device__ __forceinline__ float gaussian_likelihood(float out, float mu, float 
 __device__ __forceinline__ int table_index(float s, const float* tbl, int n, float log_t0, float inv_step) {
   // idx = (n-1) - sum_{j<n-1} [s <= tbl[j]]  ==  #{ j < n-1 : tbl[j] < s }   (NaN -> n-1)
   if (s != s) return n - 1;
-  float g = (__logf(s) - log_t0) * inv_step;
+  float g = (__log2f(s) - log_t0) * inv_step;
   int j = (int)fminf(fmaxf(g, 0.0f), (float)(n - 1));
   while (j < n - 1 && tbl[j] < s) ++j;
   while (j > 0 && !(tbl[j - 1] < s)) --j;
   return j;
 }
 
+// One float4 group of every tensor lives at row * ld + col; `row, col` come from a shift when inner/4 is a
+// power of two (token-major slices: inner = 64), from a 32-bit divide otherwise.
+template <bool POW2>
 __global__ void __launch_bounds__(GC_THREADS) gc_fused_kernel(const GcParams p) {
   __shared__ float tbl[GC_MAX_TABLE];
   __shared__ float red[GC_THREADS / 32];
@@ -53,16 +57,23 @@ __global__ void __launch_bounds__(GC_THREADS) gc_fused_kernel(const GcParams p) 
   __syncthreads();
   float log_t0 = 0.f, inv_step = 0.f;
   if (a.idx != nullptr && n > 1) {
-    log_t0 = __logf(tbl[0]);
-    inv_step = (float)(n - 1) / (__logf(tbl[n - 1]) - log_t0);
+    log_t0 = __log2f(tbl[0]);
+    inv_step = (float)(n - 1) / (__log2f(tbl[n - 1]) - log_t0);
   }
-  const bool want_lik = (a.lik != nullptr || a.log2_partials != nullptr) && a.mode != DCAE_GC_DECODE && a.y != nullptr;
+  const int mode = a.mode;
+  const bool want_lik = (a.lik != nullptr || a.log2_partials != nullptr) && mode != DCAE_GC_DECODE && a.y != nullptr;
+  const bool want_idx = a.idx != nullptr;
+  const bool want_log2 = a.log2_partials != nullptr;
+  const float scale_bound = a.scale_bound, lik_bound = a.lik_bound;
   float log2_acc = 0.f;
 
   for (int64_t g = (int64_t)blockIdx.x * GC_THREADS + threadIdx.x; g < p.groups;
        g += (int64_t)gridDim.x * GC_THREADS) {
     int64_t row, col;
-    if (p.groups <= 0xffffffffll) {   // 32-bit divide on the common path
+    if (POW2) {
+      row = g >> p.shift;
+      col = (g & (int64_t)(p.inner4 - 1)) << 2;
+    } else if (p.groups <= 0xffffffffll) {   // 32-bit divide on the common path
       const uint32_t r32 = (uint32_t)g / p.inner4;
       row = r32;
       col = (int64_t)((uint32_t)g - r32 * p.inner4) * 4;
@@ -73,10 +84,10 @@ __global__ void __launch_bounds__(GC_THREADS) gc_fused_kernel(const GcParams p) 
     const float4 mu4 = __ldg(reinterpret_cast<const float4*>(a.mu + row * a.mu_ld + col));
     float4 y4 = make_float4(0.f, 0.f, 0.f, 0.f), sc4 = y4, nz4 = y4;
     int4 si4 = make_int4(0, 0, 0, 0);
-    if (a.mode != DCAE_GC_DECODE && a.y != nullptr) y4 = __ldg(reinterpret_cast<const float4*>(a.y + row * a.y_ld + col));
+    if (mode != DCAE_GC_DECODE && a.y != nullptr) y4 = __ldg(reinterpret_cast<const float4*>(a.y + row * a.y_ld + col));
     if (a.scale != nullptr) sc4 = __ldg(reinterpret_cast<const float4*>(a.scale + row * a.scale_ld + col));
-    if (a.mode == DCAE_GC_NOISE) nz4 = __ldg(reinterpret_cast<const float4*>(a.noise + row * a.noise_ld + col));
-    if (a.mode == DCAE_GC_DECODE) si4 = __ldg(reinterpret_cast<const int4*>(a.sym_in + row * a.sym_in_ld + col));
+    if (mode == DCAE_GC_NOISE) nz4 = __ldg(reinterpret_cast<const float4*>(a.noise + row * a.noise_ld + col));
+    if (mode == DCAE_GC_DECODE) si4 = __ldg(reinterpret_cast<const int4*>(a.sym_in + row * a.sym_in_ld + col));
 
     const float mu[4] = {mu4.x, mu4.y, mu4.z, mu4.w};
     const float y[4] = {y4.x, y4.y, y4.z, y4.w};
@@ -88,20 +99,20 @@ __global__ void __launch_bounds__(GC_THREADS) gc_fused_kernel(const GcParams p) 
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       float r, out;
-      if (a.mode == DCAE_GC_DECODE) {
+      if (mode == DCAE_GC_DECODE) {
         r = (float)si[k];                       // dequantize: inputs.type_as(means) + means
         out = __fadd_rn(r, mu[k]);
         yh[k] = out;
       } else {
         r = rintf(__fsub_rn(y[k], mu[k]));      // torch.round: half to even
         yh[k] = __fadd_rn(r, mu[k]);            // ste_round(y - mu) + mu == r + mu (exactly)
-        out = (a.mode == DCAE_GC_NOISE) ? __fadd_rn(y[k], nz[k]) : yh[k];
+        out = (mode == DCAE_GC_NOISE) ? __fadd_rn(y[k], nz[k]) : yh[k];
       }
       sy[k] = (int)r;
-      const float s = nan_max(sc[k], a.scale_bound);
-      lk[k] = want_lik ? gaussian_likelihood(out, mu[k], s, a.lik_bound) : 1.0f;
-      ix[k] = (a.idx != nullptr) ? table_index(s, tbl, n, log_t0, inv_step) : 0;
-      if (a.log2_partials != nullptr) log2_acc += log2f(lk[k]);
+      const float s = nan_max(sc[k], scale_bound);
+      lk[k] = want_lik ? gaussian_likelihood(out, mu[k], s, lik_bound) : 1.0f;
+      ix[k] = want_idx ? table_index(s, tbl, n, log_t0, inv_step) : 0;
+      if (want_log2) log2_acc += __log2f(lk[k]);   // bpp numerator: lik in [1e-9, 1], MUFU.LG2 is ample
     }
     if (a.y_hat) *reinterpret_cast<float4*>(a.y_hat + row * a.y_hat_ld + col) = make_float4(yh[0], yh[1], yh[2], yh[3]);
     if (a.lik && want_lik) *reinterpret_cast<float4*>(a.lik + row * a.lik_ld + col) = make_float4(lk[0], lk[1], lk[2], lk[3]);
@@ -177,7 +188,11 @@ extern "C" int dcae_gc_fused(const dcae_gc_args* a, void* stream) {
   const int n_tensors = (a->y && a->mode != DCAE_GC_DECODE) + 1 + (a->scale != nullptr) + (a->mode == DCAE_GC_NOISE) +
                         (a->mode == DCAE_GC_DECODE) + (a->y_hat != nullptr) + (a->lik != nullptr) + (a->sym != nullptr) + (a->idx != nullptr);
   ProfileScope prof(DCAE_PROF_GC, 4.0 * n_tensors * (double)a->rows * (double)a->inner, stream);
-  gc_fused_kernel<<<(unsigned)blocks, GC_THREADS, 0, (cudaStream_t)stream>>>(p);
+  const bool pow2 = (p.inner4 & (p.inner4 - 1)) == 0;
+  p.shift = 0;
+  while (pow2 && (1u << p.shift) < p.inner4) ++p.shift;
+  if (pow2) gc_fused_kernel<true><<<(unsigned)blocks, GC_THREADS, 0, (cudaStream_t)stream>>>(p);
+  else gc_fused_kernel<false><<<(unsigned)blocks, GC_THREADS, 0, (cudaStream_t)stream>>>(p);
   DCAE_LAUNCH_CHECK();
   return DCAE_OK;
 }

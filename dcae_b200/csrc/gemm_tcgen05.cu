@@ -47,9 +47,9 @@ struct TcParams {
   int cblk_per_tap;          // (k0 + k1) / 32
   int col0, k0, col1;
   int taps;
-  int B, h, w, TH, TW, tiles_x, tiles_y;
+  int B, h, w, TH, TW, tw_shift, tiles_x, tiles_y;
   int BN, stages, tmem_cols;
-  int n_tiles_n, total_tiles, chunk_kb;
+  int n_tiles_n, total_tiles, chunk_kb, dbg_epi;
   int dbg_nosplit, dbg_nostore;   // tuning experiments only (env DCAE_TC_NOSPLIT / DCAE_TC_NOSTORE): wrong results
   uint32_t stage_bytes, b_bytes;
 };
@@ -222,74 +222,23 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_DRAIN));
     // ===================== drain + epilogue warps =====================
     const int quarter = warp & 3;                  // TMEM lane quarter this warp may touch
-    const int half = (warp - 8) >> 2;              // which half of the BN columns
-    const int half_cols = p.BN >> 1;               // multiple of 16
-    const int r = quarter * 32 + lane;             // tile row = TMEM lane
-    const int ty = r / p.TW, tx = r - ty * p.TW;
-    const dcae_epilogue& e = p.e;
-    const int act_cols = (e.act_cols <= 0 || e.act_cols > p.N) ? p.N : e.act_cols;
+    const int half = (warp - 8) >> 2;              // even / odd 32-column blocks
     uint32_t gchunk = 0;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-      int b, y0, x0, n0;
-      tile_coords(t, b, y0, x0, n0);
-      float acc[MAX_GROUPS * 16];
+      EpiTile et;
+      tile_coords(t, et.b, et.y0, et.x0, et.n0);
+      et.B = p.B; et.h = p.h; et.w = p.w; et.tw_shift = p.tw_shift; et.N = p.N; et.BN = p.BN; et.dbg = p.dbg_epi;
+      float acc[EPI_BLOCKS * 32];
       for (int ck = 0; ck < n_chunks; ++ck, ++gchunk) {
         const uint32_t buf = gchunk & 1;
         mbar_wait(smem_u32(&tmem_full_bar[buf]), (gchunk >> 1) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * (uint32_t)p.BN + (uint32_t)(half * half_cols);
-#pragma unroll
-        for (int g = 0; g < MAX_GROUPS; ++g) {
-          if (g * 16 < half_cols) {                 // warp-uniform
-            uint32_t raw[16];
-            tmem_ld16(taddr + g * 16, raw);
-            if (ck == 0) {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) acc[g * 16 + j] = __uint_as_float(raw[j]);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) acc[g * 16 + j] = __fadd_rn(acc[g * 16 + j], __uint_as_float(raw[j]));
-            }
-          }
-        }
+        drain_chunk(acc, tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * (uint32_t)p.BN, half, p.BN, ck == 0);
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         mbar_arrive(smem_u32(&tmem_empty_bar[buf]));   // the MMA warp may start the next chain in this buffer
       }
       // ---- epilogue of this tile (overlaps the next tile's mainloop) ----
-      const int yy = y0 + ty, xx = x0 + tx;
-      if (yy < p.h && xx < p.w && !p.dbg_nostore) {
-        const int64_t token = ((int64_t)b * p.h + yy) * p.w + xx;
-        const int nb = n0 + half * half_cols;
-        float* orow = e.out + token * e.out_ld + nb;
-#pragma unroll
-        for (int g = 0; g < MAX_GROUPS; ++g) {
-          if (g * 16 < half_cols) {
-#pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-              const int cidx = g * 16 + j;
-              const int n = nb + cidx;
-              float4 v = make_float4(acc[cidx], acc[cidx + 1], acc[cidx + 2], acc[cidx + 3]);
-              if (e.bias) {
-                const float4 bv = __ldg(reinterpret_cast<const float4*>(e.bias + n));
-                v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
-              }
-              if (e.addend) {
-                const float4 ad = __ldg(reinterpret_cast<const float4*>(e.addend + token * e.addend_ld + n));
-                v.x += ad.x; v.y += ad.y; v.z += ad.z; v.w += ad.w;
-              }
-              const int act = (n < act_cols) ? e.act : DCAE_ACT_NONE;
-              v.x = act_apply(v.x, act); v.y = act_apply(v.y, act); v.z = act_apply(v.z, act); v.w = act_apply(v.w, act);
-              if (e.residual) {
-                const float4 rv = __ldg(reinterpret_cast<const float4*>(e.residual + token * e.residual_ld + n));
-                float4 rs = make_float4(1.f, 1.f, 1.f, 1.f);
-                if (e.res_scale) rs = __ldg(reinterpret_cast<const float4*>(e.res_scale + n));
-                v.x = fmaf(rv.x, rs.x, v.x); v.y = fmaf(rv.y, rs.y, v.y); v.z = fmaf(rv.z, rs.z, v.z); v.w = fmaf(rv.w, rs.w, v.w);
-              }
-              *reinterpret_cast<float4*>(orow + cidx) = v;
-            }
-          }
-        }
-      }
+      if (!p.dbg_nostore) epilogue_store(acc, p.e, et, quarter, half, lane);
     }
   }
 
@@ -329,8 +278,20 @@ int pick_bn(int N) {
 int gemm_tcgen05(const dcae_operand* a, const dcae_weight* w, const dcae_epilogue* e, int passes, cudaStream_t s) {
   DCAE_REQUIRE(w->w_hi != nullptr && (passes == 1 || w->w_lo != nullptr), "gemm(tcgen05): weight has no TF32 split (w_hi/w_lo)");
   DCAE_REQUIRE(aligned16(w->w_hi) && aligned16(w->w_lo), "gemm(tcgen05): split weights must be 16-byte aligned");
+  DCAE_REQUIRE(e->act_cols <= 0 || e->act_cols >= w->N || e->act_cols % 32 == 0, "gemm(tcgen05): act_cols must be a multiple of 32");
   const int64_t T = (int64_t)a->B * a->h * a->w;
   if (T == 0) return DCAE_OK;
+  {
+    // thread-block-pair kernel (gemm_tcgen05_2cta.cu); DCAE_TC_2CTA=0 forces the single-CTA kernel below
+    // Measured (profiles/r01/gemm_ab_v3.jsonl): the pair kernel wins on long-K 3-pass layers (cc1: K = 8640..10944,
+    // +8 %) and loses on short K, where the extra cross-CTA handshakes are not amortised.  -1 = that heuristic.
+    static const int pair_mode = [] { const char* v = getenv("DCAE_TC_2CTA"); return v ? atoi(v) : -1; }();
+    const bool use_pair = pair_mode == 1 || (pair_mode == -1 && passes == 3 && w->K >= 4096);
+    if (use_pair) {
+      const int rc = gemm_tcgen05_2cta(a, w, e, passes, pick_bn(w->N), s);
+      if (rc != 1) return rc;
+    }
+  }
   TcParams p;
   p.e = *e;
   p.N = w->N;
@@ -340,6 +301,8 @@ int gemm_tcgen05(const dcae_operand* a, const dcae_weight* w, const dcae_epilogu
   p.taps = a->taps;
   p.B = a->B; p.h = a->h; p.w = a->w;
   pick_tile(a->h, a->w, &p.TH, &p.TW);
+  p.tw_shift = 0;
+  while ((1 << p.tw_shift) < p.TW) ++p.tw_shift;
   p.tiles_x = (a->w + p.TW - 1) / p.TW;
   p.tiles_y = (a->h + p.TH - 1) / p.TH;
   p.BN = pick_bn(w->N);
@@ -356,6 +319,7 @@ int gemm_tcgen05(const dcae_operand* a, const dcae_weight* w, const dcae_epilogu
   p.dbg_nosplit = getenv("DCAE_TC_NOSPLIT") != nullptr;
   p.dbg_nostore = getenv("DCAE_TC_NOSTORE") != nullptr;
   if (const char* env = getenv("DCAE_TC_CHUNK")) { const int v = atoi(env); if (v >= 1) p.chunk_kb = v; }
+  p.dbg_epi = getenv("DCAE_TC_EPI") ? atoi(getenv("DCAE_TC_EPI")) : 0;
   if (p.stages > p.KB) p.stages = p.KB;
   DCAE_REQUIRE(p.stages >= 1, "gemm(tcgen05): tile does not fit in shared memory");
   const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;

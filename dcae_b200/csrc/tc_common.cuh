@@ -118,9 +118,159 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
         "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
+// ---- thread-block-pair (cta_group::2) variants ----------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `rank` of this cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t local_bar, uint32_t rank) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_bar), "r"(rank));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;   // clears the CTA-rank bit: the barrier of the pair's leader CTA
+// TMA loads whose completion bytes are credited to the LEADER CTA's mbarrier (both CTAs of the pair issue them)
+__device__ __forceinline__ void tma_load_4d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar & PEER_BIT_MASK), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar & PEER_BIT_MASK), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void mma_tf32_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// commit: one arrival on the barrier at this offset in BOTH CTAs of the pair once all prior MMAs retire
+__device__ __forceinline__ void mma_commit_2sm(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+
 __device__ __forceinline__ uint32_t make_idesc_tf32(int M, int N) {
   // D = F32 (bits 4-5), A = B = TF32 (bits 7-9, 10-12), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---- drain + epilogue shared by the GEMM kernels ---------------------------------------------------
+// Drain thread layout: warp `quarter` (= warp % 4) owns TMEM lanes [32q, 32q+32) = 32 tile rows, one per
+// lane.  The BN accumulator columns are cut into 32-column blocks; the two warps of a quarter take the even
+// / odd blocks (<= 4 each, 128 running sums per thread).
+constexpr int EPI_BLOCKS = 4;
+
+// r[j] of lane i = M[i][j]  ->  r[j] of lane i = M[j][i]   (5 butterfly stages, 80 shuffles)
+__device__ __forceinline__ void warp_transpose32(float* r, int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if ((j & s) == 0) {
+        const float send = up ? r[j] : r[j | s];
+        const float recv = __shfl_xor_sync(0xffffffffu, send, s);
+        if (up) r[j] = recv; else r[j | s] = recv;
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ float epi_act(float v, int act) {
+  if (act == DCAE_ACT_GELU) return gelu_erf(v);
+  if (act == DCAE_ACT_HALF_TANH) return 0.5f * tanhf(v);
+  return v;
+}
+
+// acc (+)= the chain partial sitting in TMEM at taddr (this warp's lane quarter, start of the chain buffer)
+__device__ __forceinline__ void drain_chunk(float* acc, uint32_t taddr, int half, int BN, bool first) {
+#pragma unroll
+  for (int g = 0; g < EPI_BLOCKS; ++g) {
+    const int blk = 2 * g + half;
+    if (blk * 32 < BN) {                      // warp-uniform
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t raw[16];
+        tmem_ld16(taddr + blk * 32 + hh * 16, raw);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int i = g * 32 + hh * 16 + j;
+          acc[i] = first ? __uint_as_float(raw[j]) : __fadd_rn(acc[i], __uint_as_float(raw[j]));
+        }
+      }
+    }
+  }
+}
+
+struct EpiTile {
+  int b, y0, x0, n0;        // image, tile origin on the token grid, first output column
+  int B, h, w, tw_shift, N, BN;
+  int dbg;                  // tuning experiments (env DCAE_TC_EPI): 1 = skip transpose, 2 = skip global stores
+};
+
+// Row-per-lane epilogue of one 32-column block held in r[0..32): bias / addend / activation / scaled
+// residual, eight 16-byte stores per thread.  ACT is a compile-time activation: with a run-time switch the
+// compiler if-converts and evaluates erf AND tanh for every element of every layer (measured: that, not the
+// store pattern, was what made the epilogue slower than the single-pass mainloop).
+template <int ACT>
+__device__ __forceinline__ void epi_block(const float* r, const dcae_epilogue& e, int64_t token, int n0) {
+  float* orow = e.out + token * e.out_ld + n0;
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) {
+    const int n = n0 + j;
+    float4 v = make_float4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+    if (e.bias) {
+      const float4 bv = __ldg(reinterpret_cast<const float4*>(e.bias + n));
+      v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+    }
+    if (e.addend) {
+      const float4 ad = __ldg(reinterpret_cast<const float4*>(e.addend + token * e.addend_ld + n));
+      v.x += ad.x; v.y += ad.y; v.z += ad.z; v.w += ad.w;
+    }
+    if (ACT == DCAE_ACT_GELU) { v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w); }
+    if (ACT == DCAE_ACT_HALF_TANH) { v.x = 0.5f * tanhf(v.x); v.y = 0.5f * tanhf(v.y); v.z = 0.5f * tanhf(v.z); v.w = 0.5f * tanhf(v.w); }
+    if (e.residual) {
+      const float4 rv = __ldg(reinterpret_cast<const float4*>(e.residual + token * e.residual_ld + n));
+      float4 rs = make_float4(1.f, 1.f, 1.f, 1.f);
+      if (e.res_scale) rs = __ldg(reinterpret_cast<const float4*>(e.res_scale + n));
+      v.x = fmaf(rv.x, rs.x, v.x); v.y = fmaf(rv.y, rs.y, v.y); v.z = fmaf(rv.z, rs.z, v.z); v.w = fmaf(rv.w, rs.w, v.w);
+    }
+    *reinterpret_cast<float4*>(orow + j) = v;
+  }
+}
+
+// out = act(acc + bias + addend) + residual * res_scale for this thread's row.  act_cols (columns that get the
+// activation) must be a multiple of 32 when it is smaller than N: a 32-column block is all-or-nothing.
+__device__ __forceinline__ void epilogue_store(float* acc, const dcae_epilogue& e, const EpiTile& t, int quarter, int half, int lane) {
+  const int act_cols = (e.act_cols <= 0 || e.act_cols > t.N) ? t.N : e.act_cols;
+  const int row = quarter * 32 + lane;
+  const int yy = t.y0 + (row >> t.tw_shift), xx = t.x0 + (row & ((1 << t.tw_shift) - 1));
+  if (t.b >= t.B || yy >= t.h || xx >= t.w) return;
+  const int64_t token = ((int64_t)t.b * t.h + yy) * t.w + xx;
+#pragma unroll
+  for (int g = 0; g < EPI_BLOCKS; ++g) {
+    const int blk = 2 * g + half;
+    if (blk * 32 < t.BN) {
+      const int nb0 = t.n0 + blk * 32;
+      const int act = (nb0 < act_cols) ? e.act : DCAE_ACT_NONE;   // uniform over the block
+      if (act == DCAE_ACT_GELU) epi_block<DCAE_ACT_GELU>(acc + g * 32, e, token, nb0);
+      else if (act == DCAE_ACT_HALF_TANH) epi_block<DCAE_ACT_HALF_TANH>(acc + g * 32, e, token, nb0);
+      else epi_block<DCAE_ACT_NONE>(acc + g * 32, e, token, nb0);
+    }
+  }
 }
 
 // ---- host: cuTensorMapEncodeTiled through the runtime's driver entry point (no libcuda link) ----

@@ -90,9 +90,10 @@ class EntropySliceLoop:
 
     # ---- DCAE.forward slice loop (eval mode or training noise) ----------------------------------
     def forward(self, y, latent_scales, latent_means, noise: Optional[torch.Tensor] = None,
-                want_symbols: bool = False):
+                want_symbols: bool = False, out: Optional[dict] = None):
         """-> dict(y_hat, means, scales, likelihoods [B,320,h,w], log2_lik_sum [1])
-        (+ symbols, indexes int32 [5,B,64,h,w] if want_symbols)."""
+        (+ symbols, indexes int32 [5,B,64,h,w] if want_symbols).  `out`: a dict returned by an earlier call
+        with the same shapes, to be overwritten in place (no allocation on the hot path)."""
         y = self._check_in("y", y)
         ls = self._check_in("latent_scales", latent_scales)
         lm = self._check_in("latent_means", latent_means)
@@ -102,13 +103,17 @@ class EntropySliceLoop:
         if noise is not None:
             noise = self._check_in("noise", noise)
         plan, lib, s = self._plan(B, h, w), self.lib, self._stream()
-        out = {k: torch.empty_like(y) for k in ("y_hat", "means", "scales", "likelihoods")}
-        out["log2_lik_sum"] = torch.empty(1, device=self.device)
         sym = idx = None
+        if out is None:
+            out = {k: torch.empty_like(y) for k in ("y_hat", "means", "scales", "likelihoods")}
+            out["log2_lik_sum"] = torch.empty(1, device=self.device)
+            if want_symbols:
+                out["symbols"] = torch.empty(NUM_SLICES, B, SLICE_CH, h, w, dtype=torch.int32, device=self.device)
+                out["indexes"] = torch.empty_like(out["symbols"])
+        elif out["y_hat"].shape != y.shape or (want_symbols and "symbols" not in out):
+            raise ValueError("out= does not match this call")
         if want_symbols:
-            sym = torch.empty(NUM_SLICES, B, SLICE_CH, h, w, dtype=torch.int32, device=self.device)
-            idx = torch.empty_like(sym)
-            out["symbols"], out["indexes"] = sym, idx
+            sym, idx = out["symbols"], out["indexes"]
         if B == 0 or h == 0 or w == 0:
             return out
         with torch.cuda.device(self.device):

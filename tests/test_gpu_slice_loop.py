@@ -215,3 +215,20 @@ def test_input_validation(lively_params):
         eng.forward(y[:, :64], y, y)
     with pytest.raises(ValueError):
         eng.forward(y, y[:, :, :2], y)
+
+
+def test_host_pipeline_matches_direct_calls(lively_params):
+    """dcae_b200.HostPipeline (pinned host in/out, overlapped copies) returns exactly what forward() returns."""
+    from dcae_b200.pipeline import HostPipeline
+    eng = engine(lively_params, "tf32x3")
+    B, h, w = 2, 7, 9
+    gen = torch.Generator().manual_seed(5)
+    batches = [[(4 * torch.randn(B, 320, h, w, generator=gen)).pin_memory(), torch.randn(B, 320, h, w, generator=gen).pin_memory(),
+                torch.randn(B, 320, h, w, generator=gen).pin_memory()] for _ in range(5)]
+    pipe = HostPipeline(eng, B, h, w, depth=2, want_symbols=True)
+    got = [{k: v.clone() for k, v in res.items()} for res in pipe.run(batches)]
+    assert len(got) == 5
+    for b, res in zip(batches, got):
+        want = eng.forward(*[t.cuda() for t in b], want_symbols=True)
+        for k in ("y_hat", "means", "scales", "likelihoods", "symbols", "indexes"):
+            assert torch.equal(res[k], want[k].cpu()), k

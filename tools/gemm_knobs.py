@@ -10,7 +10,7 @@ B, h, w = 16, 32, 48
 T = B * h * w
 lib = _lib.load()
 dev = torch.device("cuda:0")
-KNOBS = ("DCAE_TC_BN", "DCAE_TC_STAGES", "DCAE_TC_NOSPLIT", "DCAE_TC_NOSTORE", "DCAE_TC_CHUNK")
+KNOBS = ("DCAE_TC_BN", "DCAE_TC_STAGES", "DCAE_TC_NOSPLIT", "DCAE_TC_NOSTORE", "DCAE_TC_CHUNK", "DCAE_TC_EPI")
 
 
 def bench(Kd, N, math, taps=1, reps=10, **env):
@@ -39,9 +39,18 @@ def bench(Kd, N, math, taps=1, reps=10, **env):
     print(json.dumps({"K": Kd, "N": N, "taps": taps, "math": math, **env, "ms": round(ms, 4), "mma_TFLOPs": round(tf, 1)}), flush=True)
 
 
+QUICK = len(sys.argv) > 1 and sys.argv[1] == "quick"
 for math in ("tf32x3", "tf32"):
-    for Kd, N, taps, bn in [(640, 640, 1, 160), (640, 640, 1, 128), (2560, 640, 1, 160), (640, 2560, 1, 256), (8640, 672, 9, 224)]:
+    for Kd, N, taps, bn in [(640, 640, 1, 160), (640, 640, 1, 128), (2560, 640, 1, 160), (640, 2560, 1, 256), (8640, 672, 9, 224),
+                            (2016, 128, 9, 128), (1152, 64, 9, 64), (640, 320, 1, 160)]:
         bench(Kd, N, math, taps, bn=bn)
+        if len(sys.argv) > 1 and sys.argv[1] == "epi":
+            for v in (1, 2, 3):
+                bench(Kd, N, math, taps, bn=bn, epi=v)
+            bench(Kd, N, math, taps, bn=bn, nostore=1)
+            continue
+        if QUICK:
+            continue
         for st in (1, 2, 3):
             bench(Kd, N, math, taps, bn=bn, stages=st)
         bench(Kd, N, math, taps, bn=bn, nostore=1)
