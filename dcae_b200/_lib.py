@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdcae_b200.so")
 
 OK = 0
-MATH = {"fp32": 0, "tf32x3": 1, "tf32": 2}
+MATH = {"fp32": 0, "tf32x3": 1, "tf32": 2, "f16x3": 3}
 GC_EVAL, GC_NOISE, GC_DECODE = 0, 1, 2
 ACT_NONE, ACT_GELU, ACT_HALF_TANH = 0, 1, 2
 
@@ -39,7 +39,8 @@ class GcArgs(C.Structure):
 class Operand(C.Structure):
     _fields_ = [("base", c_f32p), ("ld", C.c_int64), ("col0", C.c_int32), ("k0", C.c_int32),
                 ("col1", C.c_int32), ("k1", C.c_int32), ("taps", C.c_int32),
-                ("B", C.c_int32), ("h", C.c_int32), ("w", C.c_int32)]
+                ("B", C.c_int32), ("h", C.c_int32), ("w", C.c_int32),
+                ("planes", C.c_void_p), ("planes_bytes", C.c_int64)]
 
 
 class Epilogue(C.Structure):
@@ -49,7 +50,8 @@ class Epilogue(C.Structure):
 
 
 class Weight(C.Structure):
-    _fields_ = [("w", c_f32p), ("w_hi", c_f32p), ("w_lo", c_f32p), ("N", C.c_int32), ("K", C.c_int32)]
+    _fields_ = [("w", c_f32p), ("w_hi", c_f32p), ("w_lo", c_f32p), ("N", C.c_int32), ("K", C.c_int32),
+                ("w16_hi", C.c_void_p), ("w16_lo", C.c_void_p), ("K16", C.c_int32), ("descale", C.c_float)]
 
 
 class DictKV(C.Structure):
@@ -102,6 +104,8 @@ SIGNATURES = {
     "dcae_reduce_partials": (C.c_int, [_P, _I64, _P, _P]),
     "dcae_op_gemm": (C.c_int, [C.POINTER(Operand), C.POINTER(Weight), C.POINTER(Epilogue), C.c_int, _P]),
     "dcae_split_tf32": (C.c_int, [_P, _P, _P, _I64, _P]),
+    "dcae_split_f16_weight": (C.c_int, [_P, _I32, _I32, _I32, _F, _P, _P, _P]),
+    "dcae_planes_bytes": (_I64, [_I64, _I32]),
     "dcae_op_layernorm": (C.c_int, [_P, _I64, _P, _P, _I32, _I64, _P, _I64, _P]),
     "dcae_op_gelu": (C.c_int, [_P, _I64, _I32, _I64, _P, _I64, _P]),
     "dcae_op_dwconv3x3": (C.c_int, [_P, _I64, _P, _P, _I32, _I32, _I32, _I32, _I32, _P, _I64, _P, _I64, _P]),

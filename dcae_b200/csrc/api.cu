@@ -117,6 +117,7 @@ extern "C" int dcae_op_gemm(const dcae_operand* a, const dcae_weight* w, const d
     case DCAE_MATH_FP32_SIMT: return gemm_simt(a, w, e, (cudaStream_t)stream);
     case DCAE_MATH_TF32X3: return gemm_tcgen05(a, w, e, 3, (cudaStream_t)stream);
     case DCAE_MATH_TF32: return gemm_tcgen05(a, w, e, 1, (cudaStream_t)stream);
+    case DCAE_MATH_F16X3: return gemm_tcgen05_f16x3(a, w, e, (cudaStream_t)stream);
   }
   set_error("dcae_op_gemm: unknown math mode %d", math);
   return DCAE_E_INVALID;
@@ -132,6 +133,7 @@ extern "C" int dcae_op_dict_attention(const float* q, int64_t q_ld, const dcae_d
   switch (math) {
     case DCAE_MATH_FP32_SIMT:
       return dict_attention_simt(q, q_ld, kv->Kh, kv->Vh, kv->head_scale, T, out, out_ld, (cudaStream_t)stream);
+    case DCAE_MATH_F16X3:   // the attention core keeps the 3xTF32 formulation (2 % of the module's flops)
     case DCAE_MATH_TF32X3: return dict_attention_tcgen05(q, q_ld, kv, T, out, out_ld, 3, (cudaStream_t)stream);
     case DCAE_MATH_TF32: return dict_attention_tcgen05(q, q_ld, kv, T, out, out_ld, 1, (cudaStream_t)stream);
   }
@@ -164,6 +166,8 @@ struct dcae_slice_loop {
   // token-major workspace
   Buf sup, y, means, scales, lik, x0, x1, x2, x3, ln, q, ao, so, dc, ga, t1, t2, f, g, h1, h2, l1, l2, stats, part, stage;
   int32_t *sym, *idx, *istage;
+  void* planes;     // fp16 hi/lo operand planes of the GEMM being run (DCAE_MATH_F16X3)
+  int64_t planes_bytes;
   int64_t n_part;   // partial sums per slice
 };
 
@@ -189,6 +193,9 @@ static size_t carve(dcae_slice_loop* p, char* base) {
   p->part.cols = 0;
   p->part.p = base ? reinterpret_cast<float*>(base + off) : nullptr;
   off = align_up(off + (size_t)NS * GC_PARTIALS_MAX * sizeof(float), 256);
+  p->planes_bytes = dcae_planes_bytes((int64_t)T, 4 * D);        // widest operand window: the dense concat
+  p->planes = base ? static_cast<void*>(base + off) : nullptr;
+  off = align_up(off + (size_t)p->planes_bytes, 256);
   return off;
 }
 
@@ -205,7 +212,7 @@ extern "C" int dcae_slice_loop_create(dcae_slice_loop** out, int32_t B, int32_t 
                                       size_t workspace_bytes, int math) {
   DCAE_REQUIRE(out && weights && workspace, "dcae_slice_loop_create: null argument");
   DCAE_REQUIRE(B > 0 && h > 0 && w > 0 && (int64_t)B * h * w < (1ll << 31) / 4, "dcae_slice_loop_create: bad shape B=%d h=%d w=%d", B, h, w);
-  DCAE_REQUIRE(math >= DCAE_MATH_FP32_SIMT && math <= DCAE_MATH_TF32, "dcae_slice_loop_create: bad math mode %d", math);
+  DCAE_REQUIRE(math >= DCAE_MATH_FP32_SIMT && math <= DCAE_MATH_F16X3, "dcae_slice_loop_create: bad math mode %d", math);
   DCAE_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, "dcae_slice_loop_create: workspace must be 256-byte aligned");
   DCAE_TRY(dcae_device_check());
   dcae_slice_loop* p = new (std::nothrow) dcae_slice_loop;
@@ -235,6 +242,7 @@ static dcae_operand opnd(const dcae_slice_loop* p, const float* base, int64_t ld
   dcae_operand a;
   a.base = base; a.ld = ld; a.col0 = col0; a.k0 = k0; a.col1 = col1; a.k1 = k1; a.taps = taps;
   a.B = p->B; a.h = p->h; a.w = p->w;
+  a.planes = p->planes; a.planes_bytes = p->planes_bytes;
   return a;
 }
 static dcae_epilogue epi(const float* bias, float* out, int64_t out_ld, int act = DCAE_ACT_NONE) {

@@ -1,0 +1,375 @@
+// DCAE_MATH_F16X3: the dense / implicit-conv GEMM on fp16 hi/lo operand PLANES (tcgen05 kind::f16).
+//
+// Why (profiles/r01, Little's-law reading of the stage sweeps): the mainloop feed is capped at about
+// (shared memory in flight) / (TMA latency ~ 3700 clk) ~ 55 B/clk/SM whatever the tile shape, so the lever is
+// flops per operand byte.  An fp32 value a is carried as a_hi = fp16(a), a_lo = fp16(a - a_hi): 22 significant
+// bits in 4 bytes (the same accuracy and the same bytes as the TF32 split), but the fp16 MMA runs at twice
+// the TF32 rate and a 128-byte swizzle row holds K = 64 instead of 32 -- half the bytes per flop -- and the
+// planes come straight from TMA, so the in-kernel split warps (and their latency in the stage turnaround)
+// disappear.  Per k-step the MMA warp issues a_lo*w_hi + a_hi*w_lo + a_hi*w_hi into the fp32 TMEM accumulator.
+//
+// Range: activations are converted with saturation (|a| > 65504 clamps instead of becoming inf; the layers
+// of this model are O(1..1e2)).  Weights are pre-scaled by a power of two so that w_lo stays out of the
+// fp16 subnormal range; the epilogue multiplies by the exact inverse.
+//
+// Same structure as gemm_tcgen05.cu otherwise: TMA 4-D boxes (3x3 taps = shifted boxes, hardware zero
+// fill), persistent CTAs, <= 96-MMA accumulation chains in two alternating TMEM buffers summed in fp32
+// registers (RZ-accumulator fix), epilogue overlapped with the next tile.
+#include <cuda_fp16.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace dcae {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK16 = 64;                 // fp16 per k-block = 128 B = one swizzle row
+constexpr int UMMA_K16 = 16;
+constexpr int A16_BYTES = BM * BK16 * 2; // 16 KB per plane tile
+constexpr int MAX_STAGES = 8;
+constexpr int NTHREADS = 384;            // warps 0-3 control (TMA, MMA, 2 idle), 4-11 drain / epilogue
+constexpr int NDRAIN = 256;
+constexpr int REGS_CTRL = 40, REGS_DRAIN = 216;   // 128*40 + 256*216 <= 65536
+constexpr int CHUNK_MMAS = 96;
+constexpr uint32_t SMEM_LIMIT = 227 * 1024;
+
+struct F16Params {
+  dcae_epilogue e;
+  int N, KB;                 // KB = taps * (Kp / 64)
+  int cblk_per_tap, taps;
+  int B, h, w, TH, TW, tw_shift, tiles_x, tiles_y;
+  int BN, stages, tmem_cols;
+  int n_tiles_n, total_tiles, chunk_kb;
+  float descale;
+  uint32_t stage_bytes, b_bytes;
+};
+
+__device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// ---- fp32 window -> fp16 hi/lo planes [T, Kp] (HBM-bound, one float4 -> two 8-byte stores) -------------
+__global__ void __launch_bounds__(256) split_f16_planes_kernel(const float* __restrict__ x, int64_t ld, int col0, int k0, int col1,
+                                                               int kc, int Kp, int64_t T, __half* __restrict__ hi, __half* __restrict__ lo) {
+  const int g4 = Kp >> 2;
+  const int64_t n = T * g4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t t = i / g4;
+    const int c = (int)(i - t * g4) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < kc) {
+      const int col = (c < k0) ? (col0 + c) : (col1 + (c - k0));
+      v = __ldg(reinterpret_cast<const float4*>(x + t * ld + col));
+    }
+    const float f[4] = {v.x, v.y, v.z, v.w};
+    __half h[4], l[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      unsigned short hb, lb;
+      asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(hb) : "f"(f[k]));
+      h[k] = __ushort_as_half(hb);
+      const float r = f[k] - __half2float(h[k]);
+      asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(lb) : "f"(r));
+      l[k] = __ushort_as_half(lb);
+    }
+    *reinterpret_cast<uint2*>(hi + t * Kp + c) = *reinterpret_cast<const uint2*>(h);
+    *reinterpret_cast<uint2*>(lo + t * Kp + c) = *reinterpret_cast<const uint2*>(l);
+  }
+}
+
+__global__ void __launch_bounds__(256) split_f16_weight_kernel(const float* __restrict__ w, int N, int taps, int kc, int Kp, float scale,
+                                                               __half* __restrict__ hi, __half* __restrict__ lo) {
+  const int64_t n = (int64_t)N * taps * Kp;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % Kp);
+    const int64_t r = i / Kp;              // row * taps + tap
+    float v = 0.f;
+    if (c < kc) v = w[r * kc + c] * scale;
+    const __half h = __float2half_rn(v);
+    hi[i] = h;
+    lo[i] = __float2half_rn(v - __half2float(h));
+  }
+}
+
+template <int DUMMY>
+__global__ void __launch_bounds__(NTHREADS, 1)
+gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
+                  const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUtensorMap map_bl, const F16Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES];
+  __shared__ __align__(8) uint64_t tmem_full_bar[2], tmem_empty_bar[2];
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&tmem_full_bar[b]), 1);
+      mbar_init(smem_u32(&tmem_empty_bar[b]), NDRAIN);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_ah) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_al) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_bh) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_bl) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_slot;
+
+  // per-stage smem: [A_hi | A_lo | B_hi | B_lo]
+  const uint32_t off_al = A16_BYTES, off_bh = 2 * A16_BYTES, off_bl = off_bh + p.b_bytes;
+  const int n_chunks = (p.KB + p.chunk_kb - 1) / p.chunk_kb;
+
+  auto tile_coords = [&](int t, int& b, int& y0, int& x0, int& n0) {
+    const int nt = t % p.n_tiles_n;
+    int mt = t / p.n_tiles_n;
+    const int tile_x = mt % p.tiles_x; mt /= p.tiles_x;
+    const int tile_y = mt % p.tiles_y;
+    b = mt / p.tiles_y;
+    x0 = tile_x * p.TW; y0 = tile_y * p.TH; n0 = nt * p.BN;
+  };
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_CTRL));
+    if (warp == 0 && lane == 0) {
+      // ===================== TMA producer =====================
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        int b, y0, x0, n0;
+        tile_coords(t, b, y0, x0, n0);
+        for (int kb = 0; kb < p.KB; ++kb) {
+          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+          const uint32_t sbase = smem0 + stage * p.stage_bytes;
+          const uint32_t fb = smem_u32(&full_bar[stage]);
+          mbar_expect_tx(fb, 2 * A16_BYTES + 2 * p.b_bytes);
+          const int tap = kb / p.cblk_per_tap;
+          const int c = (kb - tap * p.cblk_per_tap) * BK16;
+          int dy = 0, dx = 0;
+          if (p.taps == 9) { dy = tap / 3 - 1; dx = tap % 3 - 1; }
+          tma_load_4d(sbase, &map_ah, fb, c, x0 + dx, y0 + dy, b);
+          tma_load_4d(sbase + off_al, &map_al, fb, c, x0 + dx, y0 + dy, b);
+          tma_load_2d(sbase + off_bh, &map_bh, fb, kb * BK16, n0);
+          tma_load_2d(sbase + off_bl, &map_bl, fb, kb * BK16, n0);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    } else if (warp == 1 && lane == 0) {
+      // ===================== MMA issuer =====================
+      // D = F32 (bit 4), A = B = F16 (format 0), K-major, N >> 3 at bit 17, M >> 4 at bit 24
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0, gchunk = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        for (int ck = 0; ck < n_chunks; ++ck, ++gchunk) {
+          const uint32_t buf = gchunk & 1;
+          mbar_wait(smem_u32(&tmem_empty_bar[buf]), ((gchunk >> 1) & 1) ^ 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t tmem_acc = tmem_base + buf * (uint32_t)p.BN;
+          const int kb_end = min(p.KB, (ck + 1) * p.chunk_kb);
+          for (int kb = ck * p.chunk_kb; kb < kb_end; ++kb) {
+            mbar_wait(smem_u32(&full_bar[stage]), phase);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t sbase = smem0 + stage * p.stage_bytes;
+            const uint32_t first = (kb == ck * p.chunk_kb) ? 0u : 1u;
+#pragma unroll
+            for (int k = 0; k < BK16 / UMMA_K16; ++k) {
+              const uint32_t koff = k * UMMA_K16 * 2;
+              const uint64_t a_hi = make_smem_desc(sbase + koff), a_lo = make_smem_desc(sbase + off_al + koff);
+              const uint64_t b_hi = make_smem_desc(sbase + off_bh + koff), b_lo = make_smem_desc(sbase + off_bl + koff);
+              mma_f16(tmem_acc, a_lo, b_hi, idesc, first | (uint32_t)(k != 0));
+              mma_f16(tmem_acc, a_hi, b_lo, idesc, 1);
+              mma_f16(tmem_acc, a_hi, b_hi, idesc, 1);
+            }
+            mma_commit(smem_u32(&empty_bar[stage]));
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          }
+          mma_commit(smem_u32(&tmem_full_bar[buf]));
+        }
+      }
+    }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_DRAIN));
+    // ===================== drain + epilogue warps =====================
+    const int quarter = warp & 3;
+    const int half = (warp - 4) >> 2;
+    uint32_t gchunk = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      EpiTile et;
+      tile_coords(t, et.b, et.y0, et.x0, et.n0);
+      et.B = p.B; et.h = p.h; et.w = p.w; et.tw_shift = p.tw_shift; et.N = p.N; et.BN = p.BN; et.dbg = 0;
+      float acc[EPI_BLOCKS * 32];
+      for (int ck = 0; ck < n_chunks; ++ck, ++gchunk) {
+        const uint32_t buf = gchunk & 1;
+        mbar_wait(smem_u32(&tmem_full_bar[buf]), (gchunk >> 1) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        drain_chunk(acc, tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * (uint32_t)p.BN, half, p.BN, ck == 0);
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        mbar_arrive(smem_u32(&tmem_empty_bar[buf]));
+      }
+#pragma unroll
+      for (int i = 0; i < EPI_BLOCKS * 32; ++i) acc[i] *= p.descale;     // exact: power of two
+      epilogue_store(acc, p.e, et, quarter, half, lane);
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+  }
+}
+
+int encode_map_f16(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                   const cuuint32_t* box) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return DCAE_E_CUDA;
+  }
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(f16) failed with CUresult %d (rank %d, dims %llu %llu, box %u %u)", (int)r, rank,
+              (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1]);
+    return DCAE_E_CUDA;
+  }
+  return DCAE_OK;
+}
+
+void pick_tile16(int h, int w, int* TH, int* TW) {
+  int best = 1 << 30;
+  for (int tw = 128; tw >= 1; tw >>= 1) {
+    const int th = 128 / tw;
+    const int tiles = ((h + th - 1) / th) * ((w + tw - 1) / tw);
+    if (tiles < best || (tiles == best && tw == 16)) { best = tiles; *TH = th; *TW = tw; }
+  }
+}
+
+inline int pad64(int v) { return (v + 63) / 64 * 64; }
+
+}  // namespace
+
+int gemm_tcgen05_f16x3(const dcae_operand* a, const dcae_weight* w, const dcae_epilogue* e, cudaStream_t s) {
+  const int kc = a->k0 + a->k1, Kp = pad64(kc);
+  const int64_t T = (int64_t)a->B * a->h * a->w;
+  DCAE_REQUIRE(w->w16_hi && w->w16_lo && w->K16 == a->taps * Kp && w->descale > 0.f,
+               "gemm(f16x3): weight has no fp16 planes (dcae_split_f16_weight) or K16=%d != taps*pad64(kc)=%d", w->K16, a->taps * Kp);
+  DCAE_REQUIRE(a->planes != nullptr && a->planes_bytes >= dcae_planes_bytes(T, kc) && (reinterpret_cast<uintptr_t>(a->planes) & 127u) == 0,
+               "gemm(f16x3): operand.planes scratch missing, misaligned (128 B) or smaller than dcae_planes_bytes()");
+  DCAE_REQUIRE(e->act_cols <= 0 || e->act_cols >= w->N || e->act_cols % 32 == 0, "gemm(f16x3): act_cols must be a multiple of 32");
+  if (T == 0) return DCAE_OK;
+  __half* hi = static_cast<__half*>(a->planes);
+  __half* lo = hi + T * Kp;
+  {
+    const int64_t n = T * (Kp / 4);
+    int64_t blocks = (n + 255) / 256;
+    const int64_t cap = (int64_t)num_sms() * 16;
+    if (blocks > cap) blocks = cap;
+    split_f16_planes_kernel<<<(unsigned)blocks, 256, 0, s>>>(a->base, a->ld, a->col0, a->k0, a->col1, kc, Kp, T, hi, lo);
+    DCAE_LAUNCH_CHECK();
+  }
+  F16Params p;
+  p.e = *e;
+  p.N = w->N;
+  p.taps = a->taps;
+  p.cblk_per_tap = Kp / BK16;
+  p.KB = a->taps * p.cblk_per_tap;
+  p.B = a->B; p.h = a->h; p.w = a->w;
+  pick_tile16(a->h, a->w, &p.TH, &p.TW);
+  p.tw_shift = 0;
+  while ((1 << p.tw_shift) < p.TW) ++p.tw_shift;
+  p.tiles_x = (a->w + p.TW - 1) / p.TW;
+  p.tiles_y = (a->h + p.TH - 1) / p.TH;
+  p.BN = 0;
+  if (const char* env = getenv("DCAE_TC_BN")) {
+    const int bn = atoi(env);
+    if (bn >= 32 && bn <= 256 && bn % 32 == 0 && w->N % bn == 0) p.BN = bn;
+  }
+  if (p.BN == 0)
+    for (int bn = 256; bn >= 32; bn -= 32)
+      if (w->N % bn == 0) { p.BN = bn; break; }
+  DCAE_REQUIRE(p.BN > 0, "gemm(f16x3): N=%d must be a multiple of 32", w->N);
+  p.tmem_cols = 2 * p.BN <= 64 ? 64 : 2 * p.BN <= 128 ? 128 : 2 * p.BN <= 256 ? 256 : 512;
+  p.n_tiles_n = w->N / p.BN;
+  p.total_tiles = p.n_tiles_n * p.tiles_x * p.tiles_y * a->B;
+  p.chunk_kb = CHUNK_MMAS / 12;
+  if (const char* env = getenv("DCAE_TC_CHUNK")) { const int v = atoi(env); if (v >= 1) p.chunk_kb = v; }
+  p.descale = w->descale;
+  p.b_bytes = (uint32_t)p.BN * BK16 * 2;
+  p.stage_bytes = 2 * A16_BYTES + 2 * p.b_bytes;
+  p.stages = (int)((SMEM_LIMIT - 2048) / p.stage_bytes);
+  if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
+  if (const char* env = getenv("DCAE_TC_STAGES")) { const int v = atoi(env); if (v >= 1 && v < p.stages) p.stages = v; }
+  if (p.stages > p.KB) p.stages = p.KB;
+  const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
+
+  CUtensorMap map_ah, map_al, map_bh, map_bl;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)Kp, (cuuint64_t)a->w, (cuuint64_t)a->h, (cuuint64_t)a->B};
+    cuuint64_t str[3] = {(cuuint64_t)Kp * 2, (cuuint64_t)Kp * 2 * a->w, (cuuint64_t)Kp * 2 * a->w * a->h};
+    cuuint32_t box[4] = {BK16, (cuuint32_t)p.TW, (cuuint32_t)p.TH, 1};
+    DCAE_TRY(encode_map_f16(&map_ah, hi, 4, dims, str, box));
+    DCAE_TRY(encode_map_f16(&map_al, lo, 4, dims, str, box));
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)w->K16, (cuuint64_t)w->N};
+    cuuint64_t str[1] = {(cuuint64_t)w->K16 * 2};
+    cuuint32_t box[2] = {BK16, (cuuint32_t)p.BN};
+    DCAE_TRY(encode_map_f16(&map_bh, w->w16_hi, 2, dims, str, box));
+    DCAE_TRY(encode_map_f16(&map_bl, w->w16_lo, 2, dims, str, box));
+  }
+  static std::once_flag attr_once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(attr_once, [] {
+    attr_err = cudaFuncSetAttribute(gemm_f16x3_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT - 1024);
+  });
+  DCAE_CUDA(attr_err);
+  const int ctas = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+  gemm_f16x3_kernel<0><<<ctas, NTHREADS, smem, s>>>(map_ah, map_al, map_bh, map_bl, p);
+  DCAE_LAUNCH_CHECK();
+  return DCAE_OK;
+}
+
+}  // namespace dcae
+
+extern "C" int64_t dcae_planes_bytes(int64_t T, int32_t cols) {
+  const int64_t Kp = (cols + 63) / 64 * 64;
+  return 2 * T * Kp * 2 + 256;
+}
+
+extern "C" int dcae_split_f16_weight(const float* w, int32_t N, int32_t taps, int32_t kc, float scale, void* hi, void* lo, void* stream) {
+  using namespace dcae;
+  DCAE_REQUIRE(w && hi && lo && N > 0 && taps > 0 && kc > 0 && scale > 0.f, "dcae_split_f16_weight: bad arguments");
+  const int Kp = (kc + 63) / 64 * 64;
+  const int64_t n = (int64_t)N * taps * Kp;
+  int64_t blocks = (n + 255) / 256;
+  const int64_t cap = (int64_t)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  split_f16_weight_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(w, N, taps, kc, Kp, scale, static_cast<__half*>(hi), static_cast<__half*>(lo));
+  DCAE_LAUNCH_CHECK();
+  return DCAE_OK;
+}

@@ -49,9 +49,10 @@ class _Plan:
 
 
 class EntropySliceLoop:
-    """params: reference state dict (hot-path keys).  math: 'fp32' | 'tf32x3' | 'tf32'."""
+    """params: reference state dict (hot-path keys).
+    math: 'f16x3' (default: fp16 hi/lo planes, fp32-level accuracy) | 'tf32x3' | 'fp32' (FFMA) | 'tf32' (reduced)."""
 
-    def __init__(self, params: Dict[str, torch.Tensor], device="cuda:0", math: str = "tf32x3",
+    def __init__(self, params: Dict[str, torch.Tensor], device="cuda:0", math: str = "f16x3",
                  scale_table: Optional[torch.Tensor] = None):
         if math not in _lib.MATH:
             raise ValueError(f"math must be one of {list(_lib.MATH)}")

@@ -15,6 +15,23 @@ from .params import (CC_HID1, CC_HID2, DICT_DIM, DICT_NUM, HEAD_DIM, HEAD_NUM, M
                      SLICE_CH, cq, cs)
 
 
+def f16_weight_planes(lib, w: torch.Tensor, taps: int, stream):
+    """fp16 hi/lo planes of w * 2^e (e chosen so max|w| 2^e lands in [8192, 16384): w_lo stays a normal fp16),
+    each tap's channel run padded to a multiple of 64.  Returns (hi, lo, K16, descale = 2^-e)."""
+    import math
+    N, K = w.shape
+    kc = K // taps
+    Kp = (kc + 63) // 64 * 64
+    amax = float(w.abs().max())
+    e = math.floor(math.log2(16384.0 / amax)) if amax > 0 else 0
+    e = max(min(e, 24), -24)
+    hi = torch.empty(N, taps * Kp, dtype=torch.float16, device=w.device)
+    lo = torch.empty_like(hi)
+    _lib.check(lib.dcae_split_f16_weight(w.data_ptr(), N, taps, kc, float(2.0 ** e), hi.data_ptr(), lo.data_ptr(), stream),
+               "dcae_split_f16_weight")
+    return hi, lo, taps * Kp, float(2.0 ** -e)
+
+
 class PackedWeights:
     """Owns every packed device tensor of the 5 slices and the ctypes array handed to the C ABI."""
 
@@ -39,18 +56,21 @@ class PackedWeights:
     def _vec(self, t: torch.Tensor) -> int:
         return self._dev(t.reshape(-1)).data_ptr()
 
-    def _weight(self, w2d: torch.Tensor) -> _lib.Weight:
-        """[N, K] row-major fp32 (+ its TF32 hi/lo split made by the library)."""
+    def _weight(self, w2d: torch.Tensor, taps: int = 1) -> _lib.Weight:
+        """[N, K] row-major fp32 + its TF32 hi/lo split + its scaled fp16 hi/lo planes (all made by the library)."""
         w = self._dev(w2d)
         N, K = w.shape
         out = _lib.Weight()
         out.w, out.N, out.K = w.data_ptr(), N, K
         if self.split:
+            s = _lib.current_stream(self.device)
             hi, lo = torch.empty_like(w), torch.empty_like(w)
             self._keep += [hi, lo]
-            _lib.check(self.lib.dcae_split_tf32(w.data_ptr(), hi.data_ptr(), lo.data_ptr(), w.numel(),
-                                                _lib.current_stream(self.device)), "dcae_split_tf32")
+            _lib.check(self.lib.dcae_split_tf32(w.data_ptr(), hi.data_ptr(), lo.data_ptr(), w.numel(), s), "dcae_split_tf32")
             out.w_hi, out.w_lo = hi.data_ptr(), lo.data_ptr()
+            h16, l16, K16, descale = f16_weight_planes(self.lib, w, taps, s)
+            self._keep += [h16, l16]
+            out.w16_hi, out.w16_lo, out.K16, out.descale = h16.data_ptr(), l16.data_ptr(), K16, descale
         return out
 
     @staticmethod
@@ -110,16 +130,16 @@ class PackedWeights:
         cc1 = torch.cat([self._conv3x3_to_gemm(mean("0.weight"), perm),
                          self._conv3x3_to_gemm(scale("0.weight"), perm),
                          self._conv3x3_to_gemm(lrp0[:, :c_sup], perm)], dim=0)
-        W.cc1 = self._weight(cc1)
+        W.cc1 = self._weight(cc1, taps=9)
         W.cc1_b = self._vec(torch.cat([mean("0.bias"), scale("0.bias"), torch.zeros(CC_HID1)]))
-        W.lrp1y = self._weight(self._conv3x3_to_gemm(lrp0[:, c_sup:]))
+        W.lrp1y = self._weight(self._conv3x3_to_gemm(lrp0[:, c_sup:]), taps=9)
         W.lrp1_b = self._vec(lrp("0.bias"))
-        W.mean2, W.mean2_b = self._weight(self._conv3x3_to_gemm(mean("2.weight"))), self._vec(mean("2.bias"))
-        W.scale2, W.scale2_b = self._weight(self._conv3x3_to_gemm(scale("2.weight"))), self._vec(scale("2.bias"))
-        W.lrp2, W.lrp2_b = self._weight(self._conv3x3_to_gemm(lrp("2.weight"))), self._vec(lrp("2.bias"))
-        W.mean3, W.mean3_b = self._weight(self._conv3x3_to_gemm(mean("4.weight"))), self._vec(mean("4.bias"))
-        W.scale3, W.scale3_b = self._weight(self._conv3x3_to_gemm(scale("4.weight"))), self._vec(scale("4.bias"))
-        W.lrp3, W.lrp3_b = self._weight(self._conv3x3_to_gemm(lrp("4.weight"))), self._vec(lrp("4.bias"))
+        W.mean2, W.mean2_b = self._weight(self._conv3x3_to_gemm(mean("2.weight")), taps=9), self._vec(mean("2.bias"))
+        W.scale2, W.scale2_b = self._weight(self._conv3x3_to_gemm(scale("2.weight")), taps=9), self._vec(scale("2.bias"))
+        W.lrp2, W.lrp2_b = self._weight(self._conv3x3_to_gemm(lrp("2.weight")), taps=9), self._vec(lrp("2.bias"))
+        W.mean3, W.mean3_b = self._weight(self._conv3x3_to_gemm(mean("4.weight")), taps=9), self._vec(mean("4.bias"))
+        W.scale3, W.scale3_b = self._weight(self._conv3x3_to_gemm(scale("4.weight")), taps=9), self._vec(scale("4.bias"))
+        W.lrp3, W.lrp3_b = self._weight(self._conv3x3_to_gemm(lrp("4.weight")), taps=9), self._vec(lrp("4.bias"))
 
     def dictionary_kv(self, dt, ln_w, ln_b, k_w, k_b, head_scale) -> _lib.DictKV:
         """K = k(dict_ln(dt)), V = dict_ln(dt), per head [20, 128, 32] (dcae.py:492-495); batch invariant,

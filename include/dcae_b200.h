@@ -44,7 +44,9 @@ enum {
 enum {
   DCAE_MATH_FP32_SIMT = 0, /* FFMA reference path: fp32 in, fp32 accumulate */
   DCAE_MATH_TF32X3 = 1,    /* tcgen05 kind::tf32, error-compensated 3-pass split: fp32-level accuracy */
-  DCAE_MATH_TF32 = 2       /* tcgen05 kind::tf32 single pass (like torch allow_tf32=True) */
+  DCAE_MATH_TF32 = 2,      /* tcgen05 kind::tf32 single pass (like torch allow_tf32=True) */
+  DCAE_MATH_F16X3 = 3      /* tcgen05 kind::f16 on fp16 hi/lo operand planes, 3-pass: fp32-level accuracy (22-bit
+                              operands) at twice the TF32 MMA rate and half the operand bytes per flop */
 };
 
 int dcae_version(void);
@@ -110,7 +112,11 @@ typedef struct {
   int32_t col0, k0, col1, k1;
   int32_t taps;            /* 1 or 9 */
   int32_t B, h, w;         /* token grid */
+  /* DCAE_MATH_F16X3 only: caller-owned scratch of dcae_planes_bytes(T, k0 + k1) bytes that receives the fp16
+   * hi/lo planes of the operand window (the split runs as its own HBM-bound launch before the GEMM). */
+  void* planes; int64_t planes_bytes;
 } dcae_operand;
+int64_t dcae_planes_bytes(int64_t T, int32_t cols);
 
 enum { DCAE_ACT_NONE = 0, DCAE_ACT_GELU = 1, DCAE_ACT_HALF_TANH = 2 };
 
@@ -132,7 +138,14 @@ typedef struct {
 typedef struct {
   const float* w; const float* w_hi; const float* w_lo;
   int32_t N; int32_t K;
+  /* DCAE_MATH_F16X3: fp16 hi/lo planes of w * 2^e, [N, K16] with each tap's channel run padded to a multiple
+   * of 64 (K16 = taps * pad64(K / taps)); descale = 2^-e is applied to the accumulator (exact).  Made by
+   * dcae_split_f16_weight. */
+  const void* w16_hi; const void* w16_lo;
+  int32_t K16; float descale;
 } dcae_weight;
+/* w: [N, taps * kc] fp32 -> hi/lo: [N, taps * pad64(kc)] fp16 of w * scale (scale a power of two). */
+int dcae_split_f16_weight(const float* w, int32_t N, int32_t taps, int32_t kc, float scale, void* hi, void* lo, void* stream);
 
 /* nn.Linear / 1x1 conv / 3x3 conv as one GEMM: acc[T, N] = A[T, K] * W[N, K]^T.
  * Replaces F.linear / F.conv2d dispatches of dcae.py:482-507 and :584-611. */

@@ -24,8 +24,13 @@ def gemm(buf, B, h, w, col0, k0, weight2d, math="fp32", taps=1, col1=0, k1=0, bi
     N, K = weight2d.shape
     wt = weight2d.contiguous()
     hi, lo = split_weight(wt)
-    a = _lib.Operand(buf.data_ptr(), ld, col0, k0, col1, k1, taps, B, h, w)
-    W = _lib.Weight(wt.data_ptr(), hi.data_ptr(), lo.data_ptr(), N, K)
+    from dcae_b200.weights import f16_weight_planes
+    nbytes = lib.dcae_planes_bytes(T, k0 + k1)
+    planes = torch.empty(nbytes + 128, dtype=torch.uint8, device=buf.device)
+    pbase = (planes.data_ptr() + 127) // 128 * 128
+    a = _lib.Operand(buf.data_ptr(), ld, col0, k0, col1, k1, taps, B, h, w, pbase, nbytes)
+    h16, l16, K16, descale = f16_weight_planes(lib, wt, taps, _s(buf.device))
+    W = _lib.Weight(wt.data_ptr(), hi.data_ptr(), lo.data_ptr(), N, K, h16.data_ptr(), l16.data_ptr(), K16, descale)
     if out is None:
         out = torch.zeros(T, N, device=buf.device)
     e = _lib.Epilogue()

@@ -13,7 +13,7 @@ from _util import rel_err
 
 pytestmark = pytest.mark.gpu
 
-TOL = {"fp32": 2e-6, "tf32x3": 1e-5, "tf32": 3e-3}
+TOL = {"fp32": 2e-6, "tf32x3": 1e-5, "f16x3": 1e-5, "tf32": 3e-3}
 
 
 def tok(x):   # NCHW -> [T, C] (b, y, x) order
@@ -28,7 +28,7 @@ def g(seed):
     return torch.Generator().manual_seed(seed)
 
 
-@pytest.mark.parametrize("math", ["fp32", "tf32x3", "tf32"])
+@pytest.mark.parametrize("math", ["fp32", "tf32x3", "f16x3", "tf32"])
 @pytest.mark.parametrize("B,h,w,K_,N", [(2, 7, 9, 640, 640), (1, 16, 16, 704, 320), (3, 8, 16, 2560, 640), (1, 5, 3, 64, 224)])
 def test_linear_gemm(math, B, h, w, K_, N):
     x = torch.randn(B * h * w, K_ + 64, generator=g(1))
@@ -39,7 +39,7 @@ def test_linear_gemm(math, B, h, w, K_, N):
     assert rel_err(got.cpu(), want) < TOL[math]
 
 
-@pytest.mark.parametrize("math", ["fp32", "tf32x3", "tf32"])
+@pytest.mark.parametrize("math", ["fp32", "tf32x3", "f16x3", "tf32"])
 @pytest.mark.parametrize("B,h,w,C,N", [(2, 7, 9, 64, 224), (1, 16, 16, 224, 128), (2, 8, 12, 960, 672), (1, 20, 40, 128, 64)])
 def test_conv3x3_implicit_gemm(math, B, h, w, C, N):
     x = torch.randn(B, C, h, w, generator=g(4))
@@ -51,7 +51,7 @@ def test_conv3x3_implicit_gemm(math, B, h, w, C, N):
     assert rel_err(got.cpu(), want) < TOL[math] * (2 if 9 * C > 4096 else 1)
 
 
-@pytest.mark.parametrize("math", ["fp32", "tf32x3"])
+@pytest.mark.parametrize("math", ["fp32", "tf32x3", "f16x3"])
 def test_gemm_two_segments_and_epilogues(math):
     B, h, w = 2, 6, 10
     T = B * h * w
@@ -81,7 +81,7 @@ def test_gemm_two_segments_and_epilogues(math):
 def test_gemm_deterministic_and_batch_invariant():
     x = torch.randn(2, 128, 9, 11, generator=g(13))
     wt = (torch.randn(64, 128, 3, 3, generator=g(14)) * 0.05).permute(0, 2, 3, 1).reshape(64, -1).cuda()
-    for math in ("fp32", "tf32x3"):
+    for math in ("fp32", "tf32x3", "f16x3"):
         full = K.gemm(tok(x).cuda(), 2, 9, 11, 0, 128, wt, math=math, taps=9)
         again = K.gemm(tok(x).cuda(), 2, 9, 11, 0, 128, wt, math=math, taps=9)
         one = K.gemm(tok(x[1:]).cuda(), 1, 9, 11, 0, 128, wt, math=math, taps=9)

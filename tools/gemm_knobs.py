@@ -23,8 +23,12 @@ def bench(Kd, N, math, taps=1, reps=10, **env):
     wt = torch.randn(N, Kd, device=dev) * 0.02
     hi, lo = K.split_weight(wt)
     out = torch.empty(T, N, device=dev)
-    a = _lib.Operand(buf.data_ptr(), C, 0, C, 0, 0, taps, B, h, w)
-    W = _lib.Weight(wt.data_ptr(), hi.data_ptr(), lo.data_ptr(), N, Kd)
+    from dcae_b200.weights import f16_weight_planes
+    nbytes = lib.dcae_planes_bytes(T, C)
+    planes = torch.empty(nbytes + 128, dtype=torch.uint8, device=dev)
+    a = _lib.Operand(buf.data_ptr(), C, 0, C, 0, 0, taps, B, h, w, (planes.data_ptr() + 127) // 128 * 128, nbytes)
+    h16, l16, K16, descale = f16_weight_planes(lib, wt, taps, _lib.current_stream(dev))
+    W = _lib.Weight(wt.data_ptr(), hi.data_ptr(), lo.data_ptr(), N, Kd, h16.data_ptr(), l16.data_ptr(), K16, descale)
     e = _lib.Epilogue(); e.out, e.out_ld = out.data_ptr(), N
     s = _lib.current_stream(dev)
     for _ in range(3):
@@ -35,12 +39,12 @@ def bench(Kd, N, math, taps=1, reps=10, **env):
         lib.dcae_op_gemm(a, W, e, _lib.MATH[math], s)
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
-    tf = 2.0 * T * N * Kd / (ms * 1e-3) / 1e12 * (3 if math == "tf32x3" else 1)
+    tf = 2.0 * T * N * Kd / (ms * 1e-3) / 1e12 * (3 if math in ("tf32x3", "f16x3") else 1)
     print(json.dumps({"K": Kd, "N": N, "taps": taps, "math": math, **env, "ms": round(ms, 4), "mma_TFLOPs": round(tf, 1)}), flush=True)
 
 
 QUICK = len(sys.argv) > 1 and sys.argv[1] == "quick"
-for math in ("tf32x3", "tf32"):
+for math in (sys.argv[2:] or ("tf32x3", "tf32")):
     for Kd, N, taps, bn in [(640, 640, 1, 160), (640, 640, 1, 128), (2560, 640, 1, 160), (640, 2560, 1, 256), (8640, 672, 9, 224),
                             (2016, 128, 9, 128), (1152, 64, 9, 64), (640, 320, 1, 160)]:
         bench(Kd, N, math, taps, bn=bn)
