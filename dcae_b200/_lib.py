@@ -17,6 +17,10 @@ c_f32p = C.c_void_p   # device pointers travel as integers
 c_i32p = C.c_void_p
 
 
+class Planes(C.Structure):
+    _fields_ = [("hi", C.c_void_p), ("lo", C.c_void_p), ("ld", C.c_int64)]
+
+
 class GcArgs(C.Structure):
     _fields_ = [
         ("y", c_f32p), ("y_ld", C.c_int64),
@@ -29,6 +33,7 @@ class GcArgs(C.Structure):
         ("mode", C.c_int32),
         ("rows", C.c_int64), ("inner", C.c_int64),
         ("y_hat", c_f32p), ("y_hat_ld", C.c_int64),
+        ("y_hat16", Planes),
         ("lik", c_f32p), ("lik_ld", C.c_int64),
         ("sym", c_i32p), ("sym_ld", C.c_int64),
         ("idx", c_i32p), ("idx_ld", C.c_int64),
@@ -40,13 +45,13 @@ class Operand(C.Structure):
     _fields_ = [("base", c_f32p), ("ld", C.c_int64), ("col0", C.c_int32), ("k0", C.c_int32),
                 ("col1", C.c_int32), ("k1", C.c_int32), ("taps", C.c_int32),
                 ("B", C.c_int32), ("h", C.c_int32), ("w", C.c_int32),
-                ("planes", C.c_void_p), ("planes_bytes", C.c_int64)]
+                ("planes", C.c_void_p), ("planes_bytes", C.c_int64), ("src16", Planes)]
 
 
 class Epilogue(C.Structure):
     _fields_ = [("bias", c_f32p), ("addend", c_f32p), ("addend_ld", C.c_int64),
                 ("residual", c_f32p), ("residual_ld", C.c_int64), ("res_scale", c_f32p),
-                ("act", C.c_int32), ("act_cols", C.c_int32), ("out", c_f32p), ("out_ld", C.c_int64)]
+                ("act", C.c_int32), ("act_cols", C.c_int32), ("out", c_f32p), ("out_ld", C.c_int64), ("out16", Planes)]
 
 
 class Weight(C.Structure):
@@ -106,12 +111,12 @@ SIGNATURES = {
     "dcae_split_tf32": (C.c_int, [_P, _P, _P, _I64, _P]),
     "dcae_split_f16_weight": (C.c_int, [_P, _I32, _I32, _I32, _F, _P, _P, _P]),
     "dcae_planes_bytes": (_I64, [_I64, _I32]),
-    "dcae_op_layernorm": (C.c_int, [_P, _I64, _P, _P, _I32, _I64, _P, _I64, _P]),
-    "dcae_op_gelu": (C.c_int, [_P, _I64, _I32, _I64, _P, _I64, _P]),
-    "dcae_op_dwconv3x3": (C.c_int, [_P, _I64, _P, _P, _I32, _I32, _I32, _I32, _I32, _P, _I64, _P, _I64, _P]),
+    "dcae_op_layernorm": (C.c_int, [_P, _I64, _P, _P, _I32, _I64, _P, _I64, C.POINTER(Planes), _P]),
+    "dcae_op_gelu": (C.c_int, [_P, _I64, _I32, _I64, _P, _I64, C.POINTER(Planes), _P]),
+    "dcae_op_dwconv3x3": (C.c_int, [_P, _I64, _P, _P, _I32, _I32, _I32, _I32, _I32, _P, _I64, _P, _I64, C.POINTER(Planes), _P]),
     "dcae_op_spatial_gate": (C.c_int, [_P, _I64, _P, _I64, _P, _P, _I32, _I32, _I32, _I32, _P, _P, _I64, _P]),
-    "dcae_op_dict_attention": (C.c_int, [_P, _I64, C.POINTER(DictKV), _I64, _P, _I64, C.c_int, _P]),
-    "dcae_op_nchw_to_tokens": (C.c_int, [_P, _I32, _I32, _I64, _P, _I64, _P]),
+    "dcae_op_dict_attention": (C.c_int, [_P, _I64, C.POINTER(DictKV), _I64, _P, _I64, C.POINTER(Planes), C.c_int, _P]),
+    "dcae_op_nchw_to_tokens": (C.c_int, [_P, _I32, _I32, _I64, _P, _I64, C.POINTER(Planes), _P]),
     "dcae_op_tokens_to_nchw": (C.c_int, [_P, _I64, _I32, _I32, _I64, _P, _P]),
     "dcae_op_tokens_to_nchw_i32": (C.c_int, [_P, _I64, _I32, _I32, _I64, _P, _P]),
     "dcae_op_nchw_to_tokens_i32": (C.c_int, [_P, _I32, _I32, _I64, _P, _I64, _P]),
@@ -126,6 +131,7 @@ SIGNATURES = {
     "dcae_slice_loop_store": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "dcae_slice_loop_forward": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "dcae_slice_loop_tap": (C.c_int, [_P, C.c_char_p, C.POINTER(_P), C.POINTER(_I32), C.POINTER(_I64)]),
+    "dcae_slice_loop_tap16": (C.c_int, [_P, C.c_char_p, C.POINTER(Planes), C.POINTER(_I32)]),
 }
 
 _lib = None

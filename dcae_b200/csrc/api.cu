@@ -93,7 +93,8 @@ extern "C" int dcae_device_check(void) {
 
 static int check_gemm_args(const dcae_operand* a, const dcae_weight* w, const dcae_epilogue* e) {
   DCAE_REQUIRE(a && w && e, "dcae_op_gemm: null argument struct");
-  DCAE_REQUIRE(a->base && e->out, "dcae_op_gemm: null operand/output pointer");
+  DCAE_REQUIRE((a->base || a->src16.hi) && (e->out || e->out16.hi), "dcae_op_gemm: null operand/output pointer");
+  DCAE_REQUIRE(planes_ok(&e->out16) && planes_ok(&a->src16), "dcae_op_gemm: fp16 planes must be 8-byte aligned with ld %% 4 == 0");
   DCAE_REQUIRE(a->taps == 1 || a->taps == 9, "dcae_op_gemm: taps must be 1 or 9 (got %d)", a->taps);
   DCAE_REQUIRE(a->k0 > 0 && a->k0 % 32 == 0 && a->k1 >= 0 && a->k1 % 32 == 0 && a->col0 % 4 == 0 && a->col1 % 4 == 0,
                "dcae_op_gemm: operand segments must be multiples of 32 columns (k0=%d k1=%d)", a->k0, a->k1);
@@ -114,9 +115,15 @@ extern "C" int dcae_op_gemm(const dcae_operand* a, const dcae_weight* w, const d
   DCAE_TRY(check_gemm_args(a, w, e));
   ProfileScope prof(DCAE_PROF_GEMM, 2.0 * a->B * a->h * a->w * (double)w->N * (double)w->K, stream);
   switch (math) {
-    case DCAE_MATH_FP32_SIMT: return gemm_simt(a, w, e, (cudaStream_t)stream);
-    case DCAE_MATH_TF32X3: return gemm_tcgen05(a, w, e, 3, (cudaStream_t)stream);
-    case DCAE_MATH_TF32: return gemm_tcgen05(a, w, e, 1, (cudaStream_t)stream);
+    case DCAE_MATH_FP32_SIMT:
+      DCAE_REQUIRE(a->base && e->out && !e->out16.hi, "dcae_op_gemm(fp32): fp16 planes are a tcgen05-path feature");
+      return gemm_simt(a, w, e, (cudaStream_t)stream);
+    case DCAE_MATH_TF32X3:
+      DCAE_REQUIRE(a->base, "dcae_op_gemm(tf32x3): needs the fp32 operand");
+      return gemm_tcgen05(a, w, e, 3, (cudaStream_t)stream);
+    case DCAE_MATH_TF32:
+      DCAE_REQUIRE(a->base, "dcae_op_gemm(tf32): needs the fp32 operand");
+      return gemm_tcgen05(a, w, e, 1, (cudaStream_t)stream);
     case DCAE_MATH_F16X3: return gemm_tcgen05_f16x3(a, w, e, (cudaStream_t)stream);
   }
   set_error("dcae_op_gemm: unknown math mode %d", math);
@@ -124,9 +131,11 @@ extern "C" int dcae_op_gemm(const dcae_operand* a, const dcae_weight* w, const d
 }
 
 extern "C" int dcae_op_dict_attention(const float* q, int64_t q_ld, const dcae_dict_kv* kv, int64_t T, float* out,
-                                      int64_t out_ld, int math, void* stream) {
-  DCAE_REQUIRE(q && kv && kv->Kh && kv->Vh && kv->head_scale && out, "dcae_op_dict_attention: null pointer");
-  DCAE_REQUIRE(aligned16(q) && aligned16(out) && aligned16(kv->Kh) && aligned16(kv->Vh) && q_ld % 4 == 0 && out_ld % 4 == 0 && q_ld >= 640 && out_ld >= 640,
+                                      int64_t out_ld, const dcae_planes* out16, int math, void* stream) {
+  const dcae_planes o16 = planes_or_null(out16);
+  DCAE_REQUIRE(q && kv && kv->Kh && kv->Vh && kv->head_scale && (out || o16.hi) && planes_ok(out16), "dcae_op_dict_attention: null pointer / bad planes");
+  DCAE_REQUIRE(math != DCAE_MATH_FP32_SIMT || (out && !o16.hi), "dcae_op_dict_attention(fp32): fp16 planes are a tcgen05-path feature");
+  DCAE_REQUIRE(aligned16(q) && aligned16(out) && aligned16(kv->Kh) && aligned16(kv->Vh) && q_ld % 4 == 0 && out_ld % 4 == 0 && q_ld >= 640 && (!out || out_ld >= 640),
                "dcae_op_dict_attention: 16-byte alignment and ld >= 640 required");
   DCAE_REQUIRE(T >= 0 && T < (1ll << 31), "dcae_op_dict_attention: bad token count");
   ProfileScope prof(DCAE_PROF_ATTN, 327680.0 * (double)T, stream);
@@ -134,8 +143,8 @@ extern "C" int dcae_op_dict_attention(const float* q, int64_t q_ld, const dcae_d
     case DCAE_MATH_FP32_SIMT:
       return dict_attention_simt(q, q_ld, kv->Kh, kv->Vh, kv->head_scale, T, out, out_ld, (cudaStream_t)stream);
     case DCAE_MATH_F16X3:   // the attention core keeps the 3xTF32 formulation (2 % of the module's flops)
-    case DCAE_MATH_TF32X3: return dict_attention_tcgen05(q, q_ld, kv, T, out, out_ld, 3, (cudaStream_t)stream);
-    case DCAE_MATH_TF32: return dict_attention_tcgen05(q, q_ld, kv, T, out, out_ld, 1, (cudaStream_t)stream);
+    case DCAE_MATH_TF32X3: return dict_attention_tcgen05(q, q_ld, kv, T, out, out_ld, o16, 3, (cudaStream_t)stream);
+    case DCAE_MATH_TF32: return dict_attention_tcgen05(q, q_ld, kv, T, out, out_ld, o16, 1, (cudaStream_t)stream);
   }
   set_error("dcae_op_dict_attention: unknown math mode %d", math);
   return DCAE_E_INVALID;
@@ -158,15 +167,26 @@ struct Buf {
 
 }  // namespace
 
+// fp16 hi/lo planes buffer [T, ld] (DCAE_MATH_F16X3 data flow: producers write planes, GEMMs read them)
+struct PBuf {
+  __half* hi = nullptr;
+  __half* lo = nullptr;
+  int ld = 0;
+};
+
 struct dcae_slice_loop {
   int B, h, w, math;
+  bool pm;          // planes mode: math == DCAE_MATH_F16X3
   int64_t T, HW;
   dcae_slice_weights wt[NS];
   const float* scale_table;
-  // token-major workspace
+  // token-major fp32 workspace
   Buf sup, y, means, scales, lik, x0, x1, x2, x3, ln, q, ao, so, dc, ga, t1, t2, f, g, h1, h2, l1, l2, stats, part, stage;
+  // fp16 planes (planes mode)
+  PBuf supp, lnp, gap, t2p, dcp, aop, gp, x3p, h1p, h2p, l1p, l2p;
+  char* planes_begin; size_t planes_total;
   int32_t *sym, *idx, *istage;
-  void* planes;     // fp16 hi/lo operand planes of the GEMM being run (DCAE_MATH_F16X3)
+  void* planes;     // scratch for the split pass of operands that have no producer-written planes
   int64_t planes_bytes;
   int64_t n_part;   // partial sums per slice
 };
@@ -196,6 +216,19 @@ static size_t carve(dcae_slice_loop* p, char* base) {
   p->planes_bytes = dcae_planes_bytes((int64_t)T, 4 * D);        // widest operand window: the dense concat
   p->planes = base ? static_cast<void*>(base + off) : nullptr;
   off = align_up(off + (size_t)p->planes_bytes, 256);
+  // planes buffers; widths are multiples of 64 so that a padded K window never leaves the allocation
+  p->planes_begin = base ? base + off : nullptr;
+  const size_t off0 = off;
+  auto takep = [&](PBuf& b, int cols) {
+    b.ld = cols;
+    b.hi = base ? reinterpret_cast<__half*>(base + off) : nullptr;
+    off = align_up(off + T * cols * sizeof(__half), 256);
+    b.lo = base ? reinterpret_cast<__half*>(base + off) : nullptr;
+    off = align_up(off + T * cols * sizeof(__half), 256);
+  };
+  takep(p->supp, SUP_LD); takep(p->lnp, D); takep(p->gap, D); takep(p->t2p, D); takep(p->dcp, 4 * D); takep(p->aop, D);
+  takep(p->gp, 2 * D); takep(p->x3p, D); takep(p->h1p, 704); takep(p->h2p, 256); takep(p->l1p, 256); takep(p->l2p, 128);
+  p->planes_total = off - off0;
   return off;
 }
 
@@ -217,8 +250,9 @@ extern "C" int dcae_slice_loop_create(dcae_slice_loop** out, int32_t B, int32_t 
   DCAE_TRY(dcae_device_check());
   dcae_slice_loop* p = new (std::nothrow) dcae_slice_loop;
   DCAE_REQUIRE(p != nullptr, "dcae_slice_loop_create: out of host memory");
-  memset(p, 0, sizeof(*p));
+  memset(static_cast<void*>(p), 0, sizeof(*p));
   p->B = B; p->h = h; p->w = w; p->math = math;
+  p->pm = math == DCAE_MATH_F16X3;
   p->HW = (int64_t)h * w;
   p->T = (int64_t)B * h * w;
   const size_t need = carve(p, nullptr);
@@ -231,6 +265,15 @@ extern "C" int dcae_slice_loop_create(dcae_slice_loop** out, int32_t B, int32_t 
   memcpy(p->wt, weights, sizeof(dcae_slice_weights) * NS);
   p->scale_table = scale_table;
   p->n_part = dcae_gc_num_partials(p->T, SL);
+  if (p->pm) {
+    // padded K windows over-read a few never-written plane columns (their weight planes are zero): make them finite
+    cudaError_t e = cudaMemset(p->planes_begin, 0, p->planes_total);
+    if (e != cudaSuccess) {
+      set_error("dcae_slice_loop_create: cudaMemset failed: %s", cudaGetErrorString(e));
+      delete p;
+      return DCAE_E_CUDA;
+    }
+  }
   *out = p;
   return DCAE_OK;
 }
@@ -238,17 +281,43 @@ extern "C" int dcae_slice_loop_create(dcae_slice_loop** out, int32_t B, int32_t 
 extern "C" void dcae_slice_loop_destroy(dcae_slice_loop* p) { delete p; }
 
 // ---- small builders --------------------------------------------------------------------------
+static dcae_planes pl(const PBuf& b, int col = 0) {
+  dcae_planes r;
+  r.hi = b.hi ? b.hi + col : nullptr;
+  r.lo = b.lo ? b.lo + col : nullptr;
+  r.ld = b.ld;
+  return r;
+}
+static dcae_planes no_planes() {
+  dcae_planes r;
+  r.hi = nullptr; r.lo = nullptr; r.ld = 0;
+  return r;
+}
+// fp32 operand window (split by the GEMM itself if the mode needs planes)
 static dcae_operand opnd(const dcae_slice_loop* p, const float* base, int64_t ld, int col0, int k0, int taps, int col1 = 0, int k1 = 0) {
   dcae_operand a;
+  memset(&a, 0, sizeof(a));
   a.base = base; a.ld = ld; a.col0 = col0; a.k0 = k0; a.col1 = col1; a.k1 = k1; a.taps = taps;
   a.B = p->B; a.h = p->h; a.w = p->w;
   a.planes = p->planes; a.planes_bytes = p->planes_bytes;
+  return a;
+}
+// operand = planes window in planes mode, the fp32 window otherwise
+static dcae_operand opnd2(const dcae_slice_loop* p, const Buf& f32, int64_t ld, const PBuf& f16, int col0, int k0, int taps) {
+  dcae_operand a = opnd(p, f32.p, ld, col0, k0, taps);
+  if (p->pm) { a.src16 = pl(f16); a.base = nullptr; }
   return a;
 }
 static dcae_epilogue epi(const float* bias, float* out, int64_t out_ld, int act = DCAE_ACT_NONE) {
   dcae_epilogue e;
   memset(&e, 0, sizeof(e));
   e.bias = bias; e.out = out; e.out_ld = out_ld; e.act = act;
+  return e;
+}
+// output = planes window only (planes mode) or the fp32 buffer (other modes)
+static dcae_epilogue epi2(const dcae_slice_loop* p, const float* bias, float* out, int64_t out_ld, const PBuf& f16, int col16, int act = DCAE_ACT_NONE) {
+  dcae_epilogue e = epi(bias, out, out_ld, act);
+  if (p->pm) { e.out = nullptr; e.out16 = pl(f16, col16); }
   return e;
 }
 static int gemm(const dcae_slice_loop* p, const dcae_operand& a, const dcae_weight& w, const dcae_epilogue& e, void* s) {
@@ -259,52 +328,81 @@ extern "C" int dcae_slice_loop_load(dcae_slice_loop* p, const float* y, const fl
                                     const float* latent_means, void* stream) {
   DCAE_REQUIRE(p && latent_scales && latent_means, "dcae_slice_loop_load: null argument");
   g_launches = 0;
-  if (y) DCAE_TRY(dcae_op_nchw_to_tokens(y, p->B, M, p->HW, p->y.p, M, stream));
-  DCAE_TRY(dcae_op_nchw_to_tokens(latent_scales, p->B, M, p->HW, p->sup.p + SUP_LS, SUP_LD, stream));
-  DCAE_TRY(dcae_op_nchw_to_tokens(latent_means, p->B, M, p->HW, p->sup.p + SUP_LM, SUP_LD, stream));
+  if (y) DCAE_TRY(dcae_op_nchw_to_tokens(y, p->B, M, p->HW, p->y.p, M, nullptr, stream));
+  if (p->pm) {   // the latents are only ever GEMM operands: straight to fp16 planes
+    const dcae_planes ls = pl(p->supp, SUP_LS), lm = pl(p->supp, SUP_LM);
+    DCAE_TRY(dcae_op_nchw_to_tokens(latent_scales, p->B, M, p->HW, nullptr, 0, &ls, stream));
+    DCAE_TRY(dcae_op_nchw_to_tokens(latent_means, p->B, M, p->HW, nullptr, 0, &lm, stream));
+  } else {
+    DCAE_TRY(dcae_op_nchw_to_tokens(latent_scales, p->B, M, p->HW, p->sup.p + SUP_LS, SUP_LD, nullptr, stream));
+    DCAE_TRY(dcae_op_nchw_to_tokens(latent_means, p->B, M, p->HW, p->sup.p + SUP_LM, SUP_LD, nullptr, stream));
+  }
   return DCAE_OK;
 }
 
-// dictionary cross-attention module of slice i (dcae.py:479-509) -> SUP[:, 0:320]
+// dictionary cross-attention module of slice i (dcae.py:479-509) -> support columns [0, 320)
 static int run_dca(dcae_slice_loop* p, int i, void* s) {
   const dcae_slice_weights& W = p->wt[i];
   const int64_t T = p->T;
+  const bool pm = p->pm;
   const int cq = 2 * M + SL * i;
+  const dcae_planes none = no_planes();
+  const dcae_planes lnp = pm ? pl(p->lnp) : none;
+  float* ln32 = pm ? nullptr : p->ln.p;
   // x = x_trans(query)                                                       dcae.py:481-482
-  DCAE_TRY(gemm(p, opnd(p, p->sup.p, SUP_LD, SUP_LS, cq, 1), W.x_trans, epi(W.x_trans_b, p->x0.p, D), s));
+  DCAE_TRY(gemm(p, opnd2(p, p->sup, SUP_LD, p->supp, SUP_LS, cq, 1), W.x_trans, epi(W.x_trans_b, p->x0.p, D), s));
   // msa(ln_scale(x))                                                         dcae.py:484, 435-448
-  DCAE_TRY(dcae_op_layernorm(p->x0.p, D, W.ln_scale_g, W.ln_scale_b, D, T, p->ln.p, D, s));
-  DCAE_TRY(gemm(p, opnd(p, p->ln.p, D, 0, D, 1), W.msa_s, epi(W.msa_s_b, p->dc.p, 4 * D), s));
-  for (int j = 0; j < 3; ++j) {                                            // DenseBlock dcae.py:416-433
-    DCAE_TRY(dcae_op_gelu(p->dc.p + D * j, 4 * D, D, T, p->ga.p, D, s));
-    DCAE_TRY(gemm(p, opnd(p, p->ga.p, D, 0, D, 1), W.dense_in[j], epi(W.dense_in_b[j], p->t1.p, D, DCAE_ACT_GELU), s));
-    DCAE_TRY(dcae_op_dwconv3x3(p->t1.p, D, W.dense_dw[j], W.dense_dw_b[j], D, p->B, p->h, p->w, DCAE_ACT_GELU, nullptr, 0, p->t2.p, D, s));
-    DCAE_TRY(gemm(p, opnd(p, p->t2.p, D, 0, D, 1), W.dense_out[j], epi(W.dense_out_b[j], p->dc.p + D * (j + 1), 4 * D), s));
+  DCAE_TRY(dcae_op_layernorm(p->x0.p, D, W.ln_scale_g, W.ln_scale_b, D, T, ln32, D, &lnp, s));
+  {
+    dcae_epilogue e = epi(W.msa_s_b, p->dc.p, 4 * D);
+    if (pm) e.out16 = pl(p->dcp, 0);                                    // fp32 for the GELU prologue, planes for proj
+    DCAE_TRY(gemm(p, opnd2(p, p->ln, D, p->lnp, 0, D, 1), W.msa_s, e, s));
   }
-  DCAE_TRY(gemm(p, opnd(p, p->dc.p, 4 * D, 0, 4 * D, 1), W.dense_proj, epi(W.dense_proj_b, p->so.p, D), s));
+  for (int j = 0; j < 3; ++j) {                                            // DenseBlock dcae.py:416-433
+    const dcae_planes gap = pm ? pl(p->gap) : none, t2p = pm ? pl(p->t2p) : none;
+    DCAE_TRY(dcae_op_gelu(p->dc.p + D * j, 4 * D, D, T, pm ? nullptr : p->ga.p, D, &gap, s));
+    DCAE_TRY(gemm(p, opnd2(p, p->ga, D, p->gap, 0, D, 1), W.dense_in[j], epi(W.dense_in_b[j], p->t1.p, D, DCAE_ACT_GELU), s));
+    DCAE_TRY(dcae_op_dwconv3x3(p->t1.p, D, W.dense_dw[j], W.dense_dw_b[j], D, p->B, p->h, p->w, DCAE_ACT_GELU, nullptr, 0,
+                               pm ? nullptr : p->t2.p, D, &t2p, s));
+    dcae_epilogue e = epi(W.dense_out_b[j], p->dc.p + D * (j + 1), 4 * D);
+    if (pm) {
+      e.out16 = pl(p->dcp, D * (j + 1));
+      if (j == 2) e.out = nullptr;                                      // the last block only feeds proj
+    }
+    DCAE_TRY(gemm(p, opnd2(p, p->t2, D, p->t2p, 0, D, 1), W.dense_out[j], e, s));
+  }
+  DCAE_TRY(gemm(p, opnd2(p, p->dc, 4 * D, p->dcp, 0, 4 * D, 1), W.dense_proj, epi(W.dense_proj_b, p->so.p, D), s));
   // x = s_out * spatial_atte(s_out) + res_scale_1(x)                         dcae.py:446, 484
   DCAE_TRY(dcae_op_spatial_gate(p->so.p, D, p->x0.p, D, W.res_scale_1, W.spatial_w7, D, p->B, p->h, p->w, p->stats.p, p->x1.p, D, s));
   // q = q_trans(lnx(x)); attention against the dictionary                    dcae.py:486-501
-  DCAE_TRY(dcae_op_layernorm(p->x1.p, D, W.lnx_g, W.lnx_b, D, T, p->ln.p, D, s));
-  DCAE_TRY(gemm(p, opnd(p, p->ln.p, D, 0, D, 1), W.q_trans, epi(W.q_trans_b, p->q.p, D), s));
-  DCAE_TRY(dcae_op_dict_attention(p->q.p, D, &W.kv, T, p->ao.p, D, p->math, s));
+  DCAE_TRY(dcae_op_layernorm(p->x1.p, D, W.lnx_g, W.lnx_b, D, T, ln32, D, &lnp, s));
+  DCAE_TRY(gemm(p, opnd2(p, p->ln, D, p->lnp, 0, D, 1), W.q_trans, epi(W.q_trans_b, p->q.p, D), s));
+  {
+    const dcae_planes aop = pm ? pl(p->aop) : none;
+    DCAE_TRY(dcae_op_dict_attention(p->q.p, D, &W.kv, T, pm ? nullptr : p->ao.p, D, &aop, p->math, s));
+  }
   // output = linear(output) + res_scale_2(shortcut)                          dcae.py:503
   {
     dcae_epilogue e = epi(W.linear_b, p->x2.p, D);
     e.residual = p->x1.p; e.residual_ld = D; e.res_scale = W.res_scale_2;
-    DCAE_TRY(gemm(p, opnd(p, p->ao.p, D, 0, D, 1), W.linear, e, s));
+    DCAE_TRY(gemm(p, opnd2(p, p->ao, D, p->aop, 0, D, 1), W.linear, e, s));
   }
   // output = mlp(ln_mlp(output)) + res_scale_3(output)                       dcae.py:505, 312-328
-  DCAE_TRY(dcae_op_layernorm(p->x2.p, D, W.ln_mlp_g, W.ln_mlp_b, D, T, p->ln.p, D, s));
-  DCAE_TRY(gemm(p, opnd(p, p->ln.p, D, 0, D, 1), W.fc1, epi(W.fc1_b, p->f.p, 4 * D), s));
-  DCAE_TRY(dcae_op_dwconv3x3(p->f.p, 4 * D, W.mlp_dw, W.mlp_dw_b, 2 * D, p->B, p->h, p->w, DCAE_ACT_GELU, p->f.p + 2 * D, 4 * D, p->g.p, 2 * D, s));
+  DCAE_TRY(dcae_op_layernorm(p->x2.p, D, W.ln_mlp_g, W.ln_mlp_b, D, T, ln32, D, &lnp, s));
+  DCAE_TRY(gemm(p, opnd2(p, p->ln, D, p->lnp, 0, D, 1), W.fc1, epi(W.fc1_b, p->f.p, 4 * D), s));
   {
-    dcae_epilogue e = epi(W.fc2_b, p->x3.p, D);
+    const dcae_planes gp = pm ? pl(p->gp) : none;
+    DCAE_TRY(dcae_op_dwconv3x3(p->f.p, 4 * D, W.mlp_dw, W.mlp_dw_b, 2 * D, p->B, p->h, p->w, DCAE_ACT_GELU, p->f.p + 2 * D, 4 * D,
+                               pm ? nullptr : p->g.p, 2 * D, &gp, s));
+  }
+  {
+    dcae_epilogue e = epi2(p, W.fc2_b, p->x3.p, D, p->x3p, 0);
     e.residual = p->x2.p; e.residual_ld = D; e.res_scale = W.res_scale_3;
-    DCAE_TRY(gemm(p, opnd(p, p->g.p, 2 * D, 0, 2 * D, 1), W.fc2, e, s));
+    DCAE_TRY(gemm(p, opnd2(p, p->g, 2 * D, p->gp, 0, 2 * D, 1), W.fc2, e, s));
   }
   // dict_info = output_trans(output)                                         dcae.py:507
-  DCAE_TRY(gemm(p, opnd(p, p->x3.p, D, 0, D, 1), W.output_trans, epi(W.output_trans_b, p->sup.p + SUP_DICT, SUP_LD), s));
+  DCAE_TRY(gemm(p, opnd2(p, p->x3, D, p->x3p, 0, D, 1), W.output_trans,
+                epi2(p, W.output_trans_b, p->sup.p + SUP_DICT, SUP_LD, p->supp, SUP_DICT), s));
   return DCAE_OK;
 }
 
@@ -315,14 +413,15 @@ extern "C" int dcae_slice_loop_params(dcae_slice_loop* p, int32_t i, void* s) {
   const int cs = 3 * M + SL * i;   // support channels of slice i (dcae.py:647)
   // layer 1 of cc_mean | cc_scale | lrp(support part) share the A operand: N = 672       dcae.py:649-655, 661-662
   {
-    dcae_epilogue e = epi(W.cc1_b, p->h1.p, 672, DCAE_ACT_GELU);
+    dcae_epilogue e = epi(W.cc1_b, p->h1.p, 672, DCAE_ACT_GELU);       // fp32 kept: columns 448.. are the LRP addend
     e.act_cols = 448;
-    DCAE_TRY(gemm(p, opnd(p, p->sup.p, SUP_LD, 0, cs, 9), W.cc1, e, s));
+    if (p->pm) e.out16 = pl(p->h1p, 0);
+    DCAE_TRY(gemm(p, opnd2(p, p->sup, SUP_LD, p->supp, 0, cs, 9), W.cc1, e, s));
   }
-  DCAE_TRY(gemm(p, opnd(p, p->h1.p, 672, 0, 224, 9), W.mean2, epi(W.mean2_b, p->h2.p, 256, DCAE_ACT_GELU), s));
-  DCAE_TRY(gemm(p, opnd(p, p->h1.p, 672, 224, 224, 9), W.scale2, epi(W.scale2_b, p->h2.p + 128, 256, DCAE_ACT_GELU), s));
-  DCAE_TRY(gemm(p, opnd(p, p->h2.p, 256, 0, 128, 9), W.mean3, epi(W.mean3_b, p->means.p + SL * i, M), s));
-  DCAE_TRY(gemm(p, opnd(p, p->h2.p, 256, 128, 128, 9), W.scale3, epi(W.scale3_b, p->scales.p + SL * i, M), s));
+  DCAE_TRY(gemm(p, opnd2(p, p->h1, 672, p->h1p, 0, 224, 9), W.mean2, epi2(p, W.mean2_b, p->h2.p, 256, p->h2p, 0, DCAE_ACT_GELU), s));
+  DCAE_TRY(gemm(p, opnd2(p, p->h1, 672, p->h1p, 224, 224, 9), W.scale2, epi2(p, W.scale2_b, p->h2.p + 128, 256, p->h2p, 128, DCAE_ACT_GELU), s));
+  DCAE_TRY(gemm(p, opnd2(p, p->h2, 256, p->h2p, 0, 128, 9), W.mean3, epi(W.mean3_b, p->means.p + SL * i, M), s));
+  DCAE_TRY(gemm(p, opnd2(p, p->h2, 256, p->h2p, 128, 128, 9), W.scale3, epi(W.scale3_b, p->scales.p + SL * i, M), s));
   return DCAE_OK;
 }
 
@@ -330,15 +429,16 @@ extern "C" int dcae_slice_loop_params(dcae_slice_loop* p, int32_t i, void* s) {
 static int run_lrp(dcae_slice_loop* p, int i, void* s) {
   const dcae_slice_weights& W = p->wt[i];
   {
-    dcae_epilogue e = epi(W.lrp1_b, p->l1.p, 224, DCAE_ACT_GELU);
+    dcae_epilogue e = epi2(p, W.lrp1_b, p->l1.p, 224, p->l1p, 0, DCAE_ACT_GELU);
     e.addend = p->h1.p + 448; e.addend_ld = 672;     // support part of lrp layer 1, accumulated with cc1
-    DCAE_TRY(gemm(p, opnd(p, p->sup.p, SUP_LD, SUP_PRE, SL, 9), W.lrp1y, e, s));
+    DCAE_TRY(gemm(p, opnd2(p, p->sup, SUP_LD, p->supp, SUP_PRE, SL, 9), W.lrp1y, e, s));
   }
-  DCAE_TRY(gemm(p, opnd(p, p->l1.p, 224, 0, 224, 9), W.lrp2, epi(W.lrp2_b, p->l2.p, 128, DCAE_ACT_GELU), s));
+  DCAE_TRY(gemm(p, opnd2(p, p->l1, 224, p->l1p, 0, 224, 9), W.lrp2, epi2(p, W.lrp2_b, p->l2.p, 128, p->l2p, 0, DCAE_ACT_GELU), s));
   {
-    dcae_epilogue e = epi(W.lrp3_b, p->sup.p + SUP_YHAT + SL * i, SUP_LD, DCAE_ACT_HALF_TANH);
+    dcae_epilogue e = epi(W.lrp3_b, p->sup.p + SUP_YHAT + SL * i, SUP_LD, DCAE_ACT_HALF_TANH);   // fp32: the loop's output
     e.residual = p->sup.p + SUP_PRE; e.residual_ld = SUP_LD;
-    DCAE_TRY(gemm(p, opnd(p, p->l2.p, 128, 0, 128, 9), W.lrp3, e, s));
+    if (p->pm) e.out16 = pl(p->supp, SUP_YHAT + SL * i);                                        // planes: later slices' operand
+    DCAE_TRY(gemm(p, opnd2(p, p->l2, 128, p->l2p, 0, 128, 9), W.lrp3, e, s));
   }
   return DCAE_OK;
 }
@@ -361,10 +461,11 @@ extern "C" int dcae_slice_loop_encode(dcae_slice_loop* p, int32_t i, int32_t gc_
   a.mode = gc_mode;
   a.y = p->y.p + SL * i; a.y_ld = M;
   if (gc_mode == DCAE_GC_NOISE) {
-    DCAE_TRY(dcae_op_nchw_to_tokens(noise, p->B, SL, p->HW, p->stage.p, SL, s));
+    DCAE_TRY(dcae_op_nchw_to_tokens(noise, p->B, SL, p->HW, p->stage.p, SL, nullptr, s));
     a.noise = p->stage.p; a.noise_ld = SL;
   }
   a.y_hat = p->sup.p + SUP_PRE; a.y_hat_ld = SUP_LD;
+  if (p->pm) a.y_hat16 = pl(p->supp, SUP_PRE);
   a.lik = p->lik.p + SL * i; a.lik_ld = M;
   a.sym = p->sym + SL * i; a.sym_ld = M;
   if (p->scale_table) { a.idx = p->idx + SL * i; a.idx_ld = M; }
@@ -391,6 +492,7 @@ extern "C" int dcae_slice_loop_decode(dcae_slice_loop* p, int32_t i, const int32
   a.scale = nullptr;
   a.sym_in = p->istage; a.sym_in_ld = SL;
   a.y_hat = p->sup.p + SUP_PRE; a.y_hat_ld = SUP_LD;
+  if (p->pm) a.y_hat16 = pl(p->supp, SUP_PRE);
   DCAE_TRY(dcae_gc_fused(&a, s));
   return run_lrp(p, i, s);
 }
@@ -439,5 +541,21 @@ extern "C" int dcae_slice_loop_tap(dcae_slice_loop* p, const char* name, const f
       return DCAE_OK;
     }
   set_error("dcae_slice_loop_tap: unknown buffer '%s'", name);
+  return DCAE_E_INVALID;
+}
+
+extern "C" int dcae_slice_loop_tap16(dcae_slice_loop* p, const char* name, dcae_planes* planes, int32_t* cols) {
+  DCAE_REQUIRE(p && name && planes && cols, "dcae_slice_loop_tap16: null argument");
+  DCAE_REQUIRE(p->pm, "dcae_slice_loop_tap16: the plan is not in DCAE_MATH_F16X3 mode");
+  struct { const char* n; PBuf* b; } tbl[] = {
+      {"support", &p->supp}, {"ln", &p->lnp}, {"gelu", &p->gap}, {"dw", &p->t2p}, {"dense", &p->dcp}, {"attn", &p->aop},
+      {"glu", &p->gp}, {"x3", &p->x3p}, {"h1", &p->h1p}, {"h2", &p->h2p}, {"l1", &p->l1p}, {"l2", &p->l2p}};
+  for (auto& t : tbl)
+    if (strcmp(t.n, name) == 0) {
+      planes->hi = t.b->hi; planes->lo = t.b->lo; planes->ld = t.b->ld;
+      *cols = t.b->ld;
+      return DCAE_OK;
+    }
+  set_error("dcae_slice_loop_tap16: unknown planes buffer '%s'", name);
   return DCAE_E_INVALID;
 }

@@ -32,6 +32,7 @@ constexpr uint32_t TM_S = 0, TM_PHI = 128, TM_PLO = 256, TM_O = 384;
 
 struct AtParams {
   const float* head_scale;
+  dcae_planes out16;
   float* out;
   int64_t out_ld;
   int64_t T;
@@ -164,12 +165,13 @@ dict_attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const _
       mbar_wait(smem_u32(&s_full), g & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       float s[AT_ND];
+      {
+        uint32_t raw[AT_ND];
 #pragma unroll
-      for (int c = 0; c < AT_ND / 16; ++c) {
-        uint32_t raw[16];
-        tmem_ld16(lane_addr + TM_S + c * 16, raw);
+        for (int c = 0; c < AT_ND / 16; ++c) tmem_ld16_nowait(lane_addr + TM_S + c * 16, raw + c * 16);   // 8 loads in flight
+        tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) s[c * 16 + j] = __uint_as_float(raw[j]) * sc;   // sim * scale (dcae.py:498)
+        for (int j = 0; j < AT_ND; ++j) s[j] = __uint_as_float(raw[j]) * sc;   // sim * scale (dcae.py:498)
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive(smem_u32(&s_free));                           // S may be overwritten by head g+1
@@ -202,18 +204,24 @@ dict_attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const _
       mbar_wait(smem_u32(&o_full), g & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       uint32_t o0[16], o1[16];
-      tmem_ld16(lane_addr + TM_O, o0);
-      tmem_ld16(lane_addr + TM_O + 16, o1);
+      tmem_ld16_nowait(lane_addr + TM_O, o0);
+      tmem_ld16_nowait(lane_addr + TM_O + 16, o1);
+      tmem_ld_wait();
       const int64_t token = (int64_t)tile * AT_M + r;
       if (token < p.T) {
         const float inv = 1.0f / l;
-        float4* dst = reinterpret_cast<float4*>(p.out + token * p.out_ld + head * AT_HD);
+        float4* dst = p.out ? reinterpret_cast<float4*>(p.out + token * p.out_ld + head * AT_HD) : nullptr;
 #pragma unroll
         for (int j = 0; j < 16; j += 4) {
-          dst[j / 4] = make_float4(__uint_as_float(o0[j]) * inv, __uint_as_float(o0[j + 1]) * inv,
-                                   __uint_as_float(o0[j + 2]) * inv, __uint_as_float(o0[j + 3]) * inv);
-          dst[4 + j / 4] = make_float4(__uint_as_float(o1[j]) * inv, __uint_as_float(o1[j + 1]) * inv,
+          const float4 a = make_float4(__uint_as_float(o0[j]) * inv, __uint_as_float(o0[j + 1]) * inv,
+                                       __uint_as_float(o0[j + 2]) * inv, __uint_as_float(o0[j + 3]) * inv);
+          const float4 b = make_float4(__uint_as_float(o1[j]) * inv, __uint_as_float(o1[j + 1]) * inv,
                                        __uint_as_float(o1[j + 2]) * inv, __uint_as_float(o1[j + 3]) * inv);
+          if (dst) { dst[j / 4] = a; dst[4 + j / 4] = b; }
+          if (p.out16.hi) {
+            store_planes4(p.out16, token, head * AT_HD + j, a);
+            store_planes4(p.out16, token, head * AT_HD + 16 + j, b);
+          }
         }
       }
     }
@@ -252,13 +260,14 @@ dict_attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const _
 }  // namespace
 
 int dict_attention_tcgen05(const float* q, int64_t q_ld, const dcae_dict_kv* kv, int64_t T, float* out, int64_t out_ld,
-                           int passes, cudaStream_t s) {
+                           dcae_planes out16, int passes, cudaStream_t s) {
   DCAE_REQUIRE(kv->Kh_hi && kv->Vt_hi && (passes == 1 || (kv->Kh_lo && kv->Vt_lo)),
                "dict_attention(tcgen05): dictionary K/V have no TF32 split (Kh_hi/Kh_lo/Vt_hi/Vt_lo)");
   if (T == 0) return DCAE_OK;
   AtParams p;
   p.head_scale = kv->head_scale;
   p.out = out; p.out_ld = out_ld; p.T = T;
+  p.out16 = out16;
   p.tiles = (int)((T + AT_M - 1) / AT_M);
   p.stage_bytes = (passes == 3 ? 6 : 3) * AT_TILE;
   p.stages = (passes == 3) ? 2 : 4;

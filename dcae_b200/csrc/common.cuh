@@ -1,5 +1,6 @@
 // Shared host/device helpers for libdcae_b200.so (sm_100a only).
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -67,6 +68,30 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
 }
 
+// v -> (hi, lo) fp16 with v ~= hi + lo to 22 bits; saturating (never inf)
+__device__ __forceinline__ void f16_split(float v, unsigned short& h, unsigned short& l) {
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(h) : "f"(v));
+  const float hf = __half2float(__ushort_as_half(h));
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(l) : "f"(v - hf));
+}
+// four consecutive columns of one row into both planes (two 8-byte stores); p pre-offset to the window
+__device__ __forceinline__ void store_planes4(const dcae_planes& p, int64_t row, int col, float4 v) {
+  unsigned short h[4], l[4];
+  f16_split(v.x, h[0], l[0]); f16_split(v.y, h[1], l[1]); f16_split(v.z, h[2], l[2]); f16_split(v.w, h[3], l[3]);
+  const uint2 hv = make_uint2((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16));
+  const uint2 lv = make_uint2((uint32_t)l[0] | ((uint32_t)l[1] << 16), (uint32_t)l[2] | ((uint32_t)l[3] << 16));
+  *reinterpret_cast<uint2*>(static_cast<__half*>(p.hi) + row * p.ld + col) = hv;
+  *reinterpret_cast<uint2*>(static_cast<__half*>(p.lo) + row * p.ld + col) = lv;
+}
+inline bool planes_ok(const dcae_planes* p) {
+  return p == nullptr || p->hi == nullptr ||
+         (p->lo != nullptr && p->ld % 4 == 0 && (reinterpret_cast<uintptr_t>(p->hi) & 7u) == 0 && (reinterpret_cast<uintptr_t>(p->lo) & 7u) == 0);
+}
+inline dcae_planes planes_or_null(const dcae_planes* p) {
+  dcae_planes z; z.hi = nullptr; z.lo = nullptr; z.ld = 0;
+  return (p && p->hi) ? *p : z;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -92,7 +117,7 @@ int gemm_tcgen05(const dcae_operand* a, const dcae_weight* w, const dcae_epilogu
 int gemm_tcgen05_f16x3(const dcae_operand* a, const dcae_weight* w, const dcae_epilogue* e, cudaStream_t s);
 int gemm_tcgen05_2cta(const dcae_operand* a, const dcae_weight* w, const dcae_epilogue* e, int passes, int bn, cudaStream_t s);
 int dict_attention_tcgen05(const float* q, int64_t q_ld, const dcae_dict_kv* kv, int64_t T, float* out, int64_t out_ld,
-                           int passes, cudaStream_t s);
+                           dcae_planes out16, int passes, cudaStream_t s);
 int dict_attention_simt(const float* q, int64_t q_ld, const float* Kh, const float* Vh, const float* head_scale,
                         int64_t T, float* out, int64_t out_ld, cudaStream_t s);
 

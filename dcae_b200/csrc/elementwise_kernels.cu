@@ -13,7 +13,7 @@ template <int V>  // V = C / 128 float4 per lane
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, int64_t x_ld,
                                                         const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, int64_t T,
-                                                        float* __restrict__ out, int64_t out_ld) {
+                                                        float* __restrict__ out, int64_t out_ld, const dcae_planes o16) {
   const int lane = threadIdx.x & 31;
   const int64_t t = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (t >= T) return;
@@ -45,18 +45,20 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
     o.y = (v[k].y - mean) * rstd * g.y + b.y;
     o.z = (v[k].z - mean) * rstd * g.z + b.z;
     o.w = (v[k].w - mean) * rstd * g.w + b.w;
-    orow[lane + 32 * k] = o;
+    if (out) orow[lane + 32 * k] = o;
+    if (o16.hi) store_planes4(o16, t, (lane + 32 * k) * 4, o);
   }
 }
 
 __global__ void __launch_bounds__(256) gelu_kernel(const float* __restrict__ x, int64_t x_ld, int C4, int64_t n4,
-                                                   float* __restrict__ out, int64_t out_ld) {
+                                                   float* __restrict__ out, int64_t out_ld, const dcae_planes o16) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t t = i / C4;
     const int c = (int)(i - t * C4) * 4;
     float4 v = __ldg(reinterpret_cast<const float4*>(x + t * x_ld + c));
     v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w);
-    *reinterpret_cast<float4*>(out + t * out_ld + c) = v;
+    if (out) *reinterpret_cast<float4*>(out + t * out_ld + c) = v;
+    if (o16.hi) store_planes4(o16, t, c, v);
   }
 }
 
@@ -73,7 +75,7 @@ __global__ void __launch_bounds__(128) dwconv3x3_kernel(const float* __restrict_
                                                         const float* __restrict__ wt, const float* __restrict__ bias,
                                                         int C4, int B, int h, int w, int act,
                                                         const float* __restrict__ gate, int64_t gate_ld,
-                                                        float* __restrict__ out, int64_t out_ld) {
+                                                        float* __restrict__ out, int64_t out_ld, const dcae_planes o16) {
   const int xg = (w + DW_X - 1) / DW_X;
   const int64_t n = (int64_t)B * h * xg * C4;
   const int C = C4 * 4;
@@ -125,7 +127,8 @@ __global__ void __launch_bounds__(128) dwconv3x3_kernel(const float* __restrict_
         const float4 g = __ldg(reinterpret_cast<const float4*>(gate + t * gate_ld + c));
         a.x *= g.x; a.y *= g.y; a.z *= g.z; a.w *= g.w;
       }
-      *reinterpret_cast<float4*>(out + t * out_ld + c) = a;
+      if (out) *reinterpret_cast<float4*>(out + t * out_ld + c) = a;
+      if (o16.hi) store_planes4(o16, t, c, a);
     }
   }
 }
@@ -216,6 +219,35 @@ __global__ void __launch_bounds__(256) nchw_to_tokens_kernel(const T* __restrict
   }
 }
 
+// fp32 NCHW -> token-major fp16 hi/lo planes (and optionally fp32), same 32x33 tile transpose
+__global__ void __launch_bounds__(256) nchw_to_token_planes_kernel(const float* __restrict__ src, int C, int64_t HW,
+                                                                   float* __restrict__ dst, int64_t dst_ld, const dcae_planes o16) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int64_t p0 = (int64_t)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8) {
+    const int c = c0 + r;
+    const int64_t p = p0 + tx;
+    tile[r][tx] = (c < C && p < HW) ? src[((int64_t)b * C + c) * HW + p] : 0.f;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int64_t p = p0 + r;
+    const int c = c0 + tx;
+    if (c < C && p < HW) {
+      const float v = tile[tx][r];
+      const int64_t t = (int64_t)b * HW + p;
+      if (dst) dst[t * dst_ld + c] = v;
+      unsigned short h, l;
+      f16_split(v, h, l);
+      static_cast<__half*>(o16.hi)[t * o16.ld + c] = __ushort_as_half(h);
+      static_cast<__half*>(o16.lo)[t * o16.ld + c] = __ushort_as_half(l);
+    }
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) tokens_to_nchw_kernel(const T* __restrict__ src, int64_t src_ld, int C,
                                                              int64_t HW, T* __restrict__ dst) {
@@ -261,9 +293,10 @@ static inline unsigned grid_for(int64_t n, int threads) {
 using namespace dcae;
 
 extern "C" int dcae_op_layernorm(const float* x, int64_t x_ld, const float* gamma, const float* beta, int32_t C,
-                                 int64_t T, float* out, int64_t out_ld, void* stream) {
+                                 int64_t T, float* out, int64_t out_ld, const dcae_planes* out16, void* stream) {
   ProfileScope prof(DCAE_PROF_OTHER, 0.0, stream);
-  DCAE_REQUIRE(x && gamma && beta && out, "dcae_op_layernorm: null pointer");
+  const dcae_planes o16 = planes_or_null(out16);
+  DCAE_REQUIRE(x && gamma && beta && (out || o16.hi) && planes_ok(out16), "dcae_op_layernorm: null pointer / bad planes");
   DCAE_REQUIRE(C % 128 == 0 && C >= 128 && C <= 1024, "dcae_op_layernorm: C=%d must be a multiple of 128 in [128,1024]", C);
   DCAE_REQUIRE(aligned16(x) && aligned16(out) && aligned16(gamma) && aligned16(beta) && x_ld % 4 == 0 && out_ld % 4 == 0,
                "dcae_op_layernorm: 16-byte alignment required");
@@ -271,7 +304,7 @@ extern "C" int dcae_op_layernorm(const float* x, int64_t x_ld, const float* gamm
   const unsigned blocks = (unsigned)((T + 7) / 8);
   cudaStream_t s = (cudaStream_t)stream;
   switch (C / 128) {
-#define LN_CASE(V) case V: layernorm_kernel<V><<<blocks, 256, 0, s>>>(x, x_ld, gamma, beta, T, out, out_ld); break;
+#define LN_CASE(V) case V: layernorm_kernel<V><<<blocks, 256, 0, s>>>(x, x_ld, gamma, beta, T, out, out_ld, o16); break;
     LN_CASE(1) LN_CASE(2) LN_CASE(3) LN_CASE(4) LN_CASE(5) LN_CASE(6) LN_CASE(7) LN_CASE(8)
 #undef LN_CASE
   }
@@ -279,27 +312,30 @@ extern "C" int dcae_op_layernorm(const float* x, int64_t x_ld, const float* gamm
   return DCAE_OK;
 }
 
-extern "C" int dcae_op_gelu(const float* x, int64_t x_ld, int32_t C, int64_t T, float* out, int64_t out_ld, void* stream) {
+extern "C" int dcae_op_gelu(const float* x, int64_t x_ld, int32_t C, int64_t T, float* out, int64_t out_ld,
+                            const dcae_planes* out16, void* stream) {
   ProfileScope prof(DCAE_PROF_OTHER, 0.0, stream);
-  DCAE_REQUIRE(x && out && C % 4 == 0 && x_ld % 4 == 0 && out_ld % 4 == 0 && aligned16(x) && aligned16(out), "dcae_op_gelu: bad arguments");
+  const dcae_planes o16 = planes_or_null(out16);
+  DCAE_REQUIRE(x && (out || o16.hi) && planes_ok(out16) && C % 4 == 0 && x_ld % 4 == 0 && out_ld % 4 == 0 && aligned16(x) && aligned16(out), "dcae_op_gelu: bad arguments");
   if (T == 0) return DCAE_OK;
   const int64_t n4 = T * (C / 4);
-  gelu_kernel<<<grid_for(n4, 256), 256, 0, (cudaStream_t)stream>>>(x, x_ld, C / 4, n4, out, out_ld);
+  gelu_kernel<<<grid_for(n4, 256), 256, 0, (cudaStream_t)stream>>>(x, x_ld, C / 4, n4, out, out_ld, o16);
   DCAE_LAUNCH_CHECK();
   return DCAE_OK;
 }
 
 extern "C" int dcae_op_dwconv3x3(const float* x, int64_t x_ld, const float* wt, const float* bias, int32_t C, int32_t B,
                                  int32_t h, int32_t w, int32_t act, const float* gate, int64_t gate_ld, float* out,
-                                 int64_t out_ld, void* stream) {
+                                 int64_t out_ld, const dcae_planes* out16, void* stream) {
   ProfileScope prof(DCAE_PROF_OTHER, 0.0, stream);
-  DCAE_REQUIRE(x && wt && bias && out, "dcae_op_dwconv3x3: null pointer");
+  const dcae_planes o16 = planes_or_null(out16);
+  DCAE_REQUIRE(x && wt && bias && (out || o16.hi) && planes_ok(out16), "dcae_op_dwconv3x3: null pointer / bad planes");
   DCAE_REQUIRE(C % 4 == 0 && x_ld % 4 == 0 && out_ld % 4 == 0 && (gate == nullptr || gate_ld % 4 == 0), "dcae_op_dwconv3x3: C and lds must be multiples of 4");
   DCAE_REQUIRE(aligned16(x) && aligned16(wt) && aligned16(bias) && aligned16(out) && aligned16(gate), "dcae_op_dwconv3x3: 16-byte alignment required");
   DCAE_REQUIRE(act == DCAE_ACT_NONE || act == DCAE_ACT_GELU, "dcae_op_dwconv3x3: act must be NONE or GELU");
   const int64_t n4 = (int64_t)B * h * ((w + DW_X - 1) / DW_X) * (C / 4);
   if (n4 == 0) return DCAE_OK;
-  dwconv3x3_kernel<<<grid_for(n4, 128), 128, 0, (cudaStream_t)stream>>>(x, x_ld, wt, bias, C / 4, B, h, w, act, gate, gate_ld, out, out_ld);
+  dwconv3x3_kernel<<<grid_for(n4, 128), 128, 0, (cudaStream_t)stream>>>(x, x_ld, wt, bias, C / 4, B, h, w, act, gate, gate_ld, out, out_ld, o16);
   DCAE_LAUNCH_CHECK();
   return DCAE_OK;
 }
@@ -353,8 +389,16 @@ static int transpose_out(const T* src, int64_t src_ld, int32_t B, int32_t C, int
   return DCAE_OK;
 }
 
-extern "C" int dcae_op_nchw_to_tokens(const float* src, int32_t B, int32_t C, int64_t HW, float* dst, int64_t dst_ld, void* stream) {
-  return transpose_in<float>(src, B, C, HW, dst, dst_ld, stream);
+extern "C" int dcae_op_nchw_to_tokens(const float* src, int32_t B, int32_t C, int64_t HW, float* dst, int64_t dst_ld,
+                                      const dcae_planes* dst16, void* stream) {
+  if (dst16 == nullptr || dst16->hi == nullptr) return transpose_in<float>(src, B, C, HW, dst, dst_ld, stream);
+  ProfileScope prof(DCAE_PROF_OTHER, 0.0, stream);
+  DCAE_REQUIRE(src && planes_ok(dst16) && B >= 0 && C >= 0 && HW >= 0, "nchw_to_tokens(planes): bad arguments");
+  if (B == 0 || C == 0 || HW == 0) return DCAE_OK;
+  dim3 grid((unsigned)((HW + 31) / 32), (unsigned)((C + 31) / 32), (unsigned)B);
+  nchw_to_token_planes_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, C, HW, dst, dst_ld, *dst16);
+  DCAE_LAUNCH_CHECK();
+  return DCAE_OK;
 }
 extern "C" int dcae_op_tokens_to_nchw(const float* src, int64_t src_ld, int32_t B, int32_t C, int64_t HW, float* dst, void* stream) {
   return transpose_out<float>(src, src_ld, B, C, HW, dst, stream);

@@ -115,6 +115,7 @@ __global__ void __launch_bounds__(GC_THREADS) gc_fused_kernel(const GcParams p) 
       if (want_log2) log2_acc += __log2f(lk[k]);   // bpp numerator: lik in [1e-9, 1], MUFU.LG2 is ample
     }
     if (a.y_hat) *reinterpret_cast<float4*>(a.y_hat + row * a.y_hat_ld + col) = make_float4(yh[0], yh[1], yh[2], yh[3]);
+    if (a.y_hat16.hi) store_planes4(a.y_hat16, row, (int)col, make_float4(yh[0], yh[1], yh[2], yh[3]));
     if (a.lik && want_lik) *reinterpret_cast<float4*>(a.lik + row * a.lik_ld + col) = make_float4(lk[0], lk[1], lk[2], lk[3]);
     if (a.sym) *reinterpret_cast<int4*>(a.sym + row * a.sym_ld + col) = make_int4(sy[0], sy[1], sy[2], sy[3]);
     if (a.idx) *reinterpret_cast<int4*>(a.idx + row * a.idx_ld + col) = make_int4(ix[0], ix[1], ix[2], ix[3]);
@@ -166,7 +167,8 @@ extern "C" int dcae_gc_fused(const dcae_gc_args* a, void* stream) {
   DCAE_REQUIRE(a->rows >= 0 && a->inner >= 0 && a->inner % 4 == 0, "dcae_gc_fused: inner (%lld) must be a multiple of 4",
                (long long)a->inner);
   DCAE_REQUIRE(a->mu != nullptr, "dcae_gc_fused: mu is required");
-  const bool need_y = a->mode != DCAE_GC_DECODE && (a->y_hat || a->lik || a->sym || a->log2_partials);
+  const bool need_y = a->mode != DCAE_GC_DECODE && (a->y_hat || a->y_hat16.hi || a->lik || a->sym || a->log2_partials);
+  DCAE_REQUIRE(planes_ok(&a->y_hat16), "dcae_gc_fused: y_hat16 planes must be 8-byte aligned with ld %% 4 == 0");
   DCAE_REQUIRE(a->mode == DCAE_GC_DECODE ? a->sym_in != nullptr : (!need_y || a->y != nullptr), "dcae_gc_fused: missing input for mode %d", a->mode);
   DCAE_REQUIRE(a->mode != DCAE_GC_NOISE || a->noise != nullptr, "dcae_gc_fused: NOISE mode needs a noise tensor");
   const bool need_scale = a->idx != nullptr || ((a->lik != nullptr || a->log2_partials != nullptr) && a->mode != DCAE_GC_DECODE);

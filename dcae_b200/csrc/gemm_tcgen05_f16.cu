@@ -35,6 +35,10 @@ constexpr int NDRAIN = 256;
 constexpr int REGS_CTRL = 40, REGS_DRAIN = 216;   // 128*40 + 256*216 <= 65536
 constexpr int CHUNK_MMAS = 96;
 constexpr uint32_t SMEM_LIMIT = 227 * 1024;
+// epilogue staging per drain group (the 4 warps that own the same 32-column blocks):
+// [fp32 block 128 x 128 B, SWIZZLE_128B | fp16 hi 128 x 64 B, SWIZZLE_64B | fp16 lo]
+// one 16 KB buffer per group, used for the fp32 block and then (if both are requested) for the two fp16 planes
+constexpr uint32_t STG_O32 = 0, STG_HI = 0, STG_LO = 8192, STG_BYTES = 16384;
 
 struct F16Params {
   dcae_epilogue e;
@@ -44,6 +48,8 @@ struct F16Params {
   int BN, stages, tmem_cols;
   int n_tiles_n, total_tiles, chunk_kb;
   float descale;
+  int dbg_nostore;
+  int has_o32, has_o16;
   uint32_t stage_bytes, b_bytes;
 };
 
@@ -54,6 +60,71 @@ __device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// Epilogue of one tile through shared-memory staging and TMA tensor stores.  The thread owns tile row r; each of
+// its 32-column blocks goes bias / addend / activation / residual in registers, then into the group's staging
+// buffer in the swizzled box layout (conflict-free st.shared.v4), and one thread issues the bulk store(s):
+// full 128-byte lines, ragged tiles clipped by the hardware, no per-thread global address arithmetic.
+template <int ACT>
+__device__ __forceinline__ void finalize_block(float* r, const dcae_epilogue& e, bool row_ok, int64_t token, int n0) {
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) {
+    const int n = n0 + j;
+    float4 x = make_float4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+    if (e.bias) {
+      const float4 bv = __ldg(reinterpret_cast<const float4*>(e.bias + n));
+      x.x += bv.x; x.y += bv.y; x.z += bv.z; x.w += bv.w;
+    }
+    if (e.addend && row_ok) {
+      const float4 ad = __ldg(reinterpret_cast<const float4*>(e.addend + token * e.addend_ld + n));
+      x.x += ad.x; x.y += ad.y; x.z += ad.z; x.w += ad.w;
+    }
+    if (ACT == DCAE_ACT_GELU) { x.x = gelu_erf(x.x); x.y = gelu_erf(x.y); x.z = gelu_erf(x.z); x.w = gelu_erf(x.w); }
+    if (ACT == DCAE_ACT_HALF_TANH) { x.x = 0.5f * tanhf(x.x); x.y = 0.5f * tanhf(x.y); x.z = 0.5f * tanhf(x.z); x.w = 0.5f * tanhf(x.w); }
+    if (e.residual && row_ok) {
+      const float4 rv = __ldg(reinterpret_cast<const float4*>(e.residual + token * e.residual_ld + n));
+      float4 rs = make_float4(1.f, 1.f, 1.f, 1.f);
+      if (e.res_scale) rs = __ldg(reinterpret_cast<const float4*>(e.res_scale + n));
+      x.x = fmaf(rv.x, rs.x, x.x); x.y = fmaf(rv.y, rs.y, x.y); x.z = fmaf(rv.z, rs.z, x.z); x.w = fmaf(rv.w, rs.w, x.w);
+    }
+    r[j] = x.x; r[j + 1] = x.y; r[j + 2] = x.z; r[j + 3] = x.w;
+  }
+}
+// row `row` of a [128 x 32] fp32 block into the SWIZZLE_128B box layout (128-byte rows)
+__device__ __forceinline__ void stage_f32(const float* v, int row, uint32_t stg) {
+  const uint32_t base = stg + STG_O32 + (uint32_t)row * 128;
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(base + (uint32_t)((c ^ (row & 7)) << 4)),
+                 "f"(v[4 * c]), "f"(v[4 * c + 1]), "f"(v[4 * c + 2]), "f"(v[4 * c + 3]) : "memory");
+}
+// the same row as fp16 hi / lo planes, each a [128 x 32] block in the SWIZZLE_64B box layout (64-byte rows)
+__device__ __forceinline__ void stage_f16(const float* v, int row, uint32_t stg) {
+  const uint32_t bh = stg + STG_HI + (uint32_t)row * 64, bl = stg + STG_LO + (uint32_t)row * 64;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint32_t hw[4], lw[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      unsigned short h0, l0, h1, l1;
+      f16_split(v[8 * c + 2 * q], h0, l0);
+      f16_split(v[8 * c + 2 * q + 1], h1, l1);
+      hw[q] = (uint32_t)h0 | ((uint32_t)h1 << 16);
+      lw[q] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+    }
+    const uint32_t off = (uint32_t)((c ^ ((row >> 1) & 3)) << 4);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(bh + off), "r"(hw[0]), "r"(hw[1]), "r"(hw[2]), "r"(hw[3]) : "memory");
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(bl + off), "r"(lw[0]), "r"(lw[1]), "r"(lw[2]), "r"(lw[3]) : "memory");
+  }
 }
 
 // ---- fp32 window -> fp16 hi/lo planes [T, Kp] (HBM-bound, one float4 -> two 8-byte stores) -------------
@@ -102,7 +173,9 @@ __global__ void __launch_bounds__(256) split_f16_weight_kernel(const float* __re
 template <int DUMMY>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
-                  const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUtensorMap map_bl, const F16Params p) {
+                  const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUtensorMap map_bl,
+                  const __grid_constant__ CUtensorMap map_o32, const __grid_constant__ CUtensorMap map_oh,
+                  const __grid_constant__ CUtensorMap map_ol, const F16Params p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES];
   __shared__ __align__(8) uint64_t tmem_full_bar[2], tmem_empty_bar[2];
@@ -137,8 +210,9 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_const
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_base_slot;
 
-  // per-stage smem: [A_hi | A_lo | B_hi | B_lo]
+  // per-stage smem: [A_hi | A_lo | B_hi | B_lo]; the two epilogue staging buffers follow the stages
   const uint32_t off_al = A16_BYTES, off_bh = 2 * A16_BYTES, off_bl = off_bh + p.b_bytes;
+  const uint32_t stg_base = smem0 + (uint32_t)p.stages * p.stage_bytes;
   const int n_chunks = (p.KB + p.chunk_kb - 1) / p.chunk_kb;
 
   auto tile_coords = [&](int t, int& b, int& y0, int& x0, int& n0) {
@@ -230,8 +304,53 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_const
       }
 #pragma unroll
       for (int i = 0; i < EPI_BLOCKS * 32; ++i) acc[i] *= p.descale;     // exact: power of two
-      epilogue_store(acc, p.e, et, quarter, half, lane);
+      if (p.dbg_nostore) continue;
+      // ---- epilogue: registers -> swizzled staging -> TMA tensor store, one 32-column block at a time ----
+      const dcae_epilogue& e = p.e;
+      const int act_cols = (e.act_cols <= 0 || e.act_cols > p.N) ? p.N : e.act_cols;
+      const int row = quarter * 32 + lane;
+      const int yy = et.y0 + (row >> p.tw_shift), xx = et.x0 + (row & ((1 << p.tw_shift) - 1));
+      const bool row_ok = yy < p.h && xx < p.w;
+      const int64_t token = ((int64_t)et.b * p.h + yy) * p.w + xx;
+      const uint32_t stg = stg_base + (uint32_t)half * STG_BYTES;
+      const bool issuer = quarter == 0 && lane == 0;
+#pragma unroll
+      for (int g = 0; g < EPI_BLOCKS; ++g) {
+        const int blk = 2 * g + half;
+        if (blk * 32 < p.BN) {                                  // uniform over the group
+          const int nb0 = et.n0 + blk * 32;
+          const int act = (nb0 < act_cols) ? e.act : DCAE_ACT_NONE;
+          float* r = acc + g * 32;
+          if (act == DCAE_ACT_GELU) finalize_block<DCAE_ACT_GELU>(r, e, row_ok, token, nb0);
+          else if (act == DCAE_ACT_HALF_TANH) finalize_block<DCAE_ACT_HALF_TANH>(r, e, row_ok, token, nb0);
+          else finalize_block<DCAE_ACT_NONE>(r, e, row_ok, token, nb0);
+          if (p.has_o32) {
+            if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the previous store has read the buffer
+            named_bar_sync(1 + half, 128);
+            stage_f32(r, row, stg);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            named_bar_sync(1 + half, 128);
+            if (issuer) {
+              tma_store_4d(&map_o32, stg + STG_O32, nb0, et.x0, et.y0, et.b);
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+          }
+          if (p.has_o16) {
+            if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            named_bar_sync(1 + half, 128);
+            stage_f16(r, row, stg);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            named_bar_sync(1 + half, 128);
+            if (issuer) {
+              tma_store_4d(&map_oh, stg + STG_HI, nb0, et.x0, et.y0, et.b);
+              tma_store_4d(&map_ol, stg + STG_LO, nb0, et.x0, et.y0, et.b);
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+          }
+        }
+      }
     }
+    if (quarter == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all stores landed before exit
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -242,7 +361,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_const
 }
 
 int encode_map_f16(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-                   const cuuint32_t* box) {
+                   const cuuint32_t* box, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn enc = get_encode();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled is not available from the driver");
@@ -250,7 +369,7 @@ int encode_map_f16(CUtensorMap* m, const void* base, int rank, const cuuint64_t*
   }
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled(f16) failed with CUresult %d (rank %d, dims %llu %llu, box %u %u)", (int)r, rank,
@@ -278,13 +397,19 @@ int gemm_tcgen05_f16x3(const dcae_operand* a, const dcae_weight* w, const dcae_e
   const int64_t T = (int64_t)a->B * a->h * a->w;
   DCAE_REQUIRE(w->w16_hi && w->w16_lo && w->K16 == a->taps * Kp && w->descale > 0.f,
                "gemm(f16x3): weight has no fp16 planes (dcae_split_f16_weight) or K16=%d != taps*pad64(kc)=%d", w->K16, a->taps * Kp);
-  DCAE_REQUIRE(a->planes != nullptr && a->planes_bytes >= dcae_planes_bytes(T, kc) && (reinterpret_cast<uintptr_t>(a->planes) & 127u) == 0,
+  const bool direct = a->src16.hi != nullptr;     // the producer already wrote fp16 planes: no split pass
+  DCAE_REQUIRE(direct || (a->base && a->planes != nullptr && a->planes_bytes >= dcae_planes_bytes(T, kc) && (reinterpret_cast<uintptr_t>(a->planes) & 127u) == 0),
                "gemm(f16x3): operand.planes scratch missing, misaligned (128 B) or smaller than dcae_planes_bytes()");
+  DCAE_REQUIRE(!direct || (a->k1 == 0 && a->src16.lo && a->src16.ld % 8 == 0 && a->col0 % 8 == 0 &&
+                           (reinterpret_cast<uintptr_t>(a->src16.hi) & 15u) == 0 && (reinterpret_cast<uintptr_t>(a->src16.lo) & 15u) == 0),
+               "gemm(f16x3): src16 planes need one segment, 16-byte aligned planes and col0 / ld multiples of 8");
   DCAE_REQUIRE(e->act_cols <= 0 || e->act_cols >= w->N || e->act_cols % 32 == 0, "gemm(f16x3): act_cols must be a multiple of 32");
+  DCAE_REQUIRE(e->out || e->out16.hi, "gemm(f16x3): no output");
   if (T == 0) return DCAE_OK;
-  __half* hi = static_cast<__half*>(a->planes);
-  __half* lo = hi + T * Kp;
-  {
+  __half* hi = direct ? static_cast<__half*>(a->src16.hi) + a->col0 : static_cast<__half*>(a->planes);
+  __half* lo = direct ? static_cast<__half*>(a->src16.lo) + a->col0 : hi + T * Kp;
+  const int64_t ldp = direct ? a->src16.ld : Kp;
+  if (!direct) {
     const int64_t n = T * (Kp / 4);
     int64_t blocks = (n + 255) / 256;
     const int64_t cap = (int64_t)num_sms() * 16;
@@ -309,9 +434,13 @@ int gemm_tcgen05_f16x3(const dcae_operand* a, const dcae_weight* w, const dcae_e
     const int bn = atoi(env);
     if (bn >= 32 && bn <= 256 && bn % 32 == 0 && w->N % bn == 0) p.BN = bn;
   }
-  if (p.BN == 0)
-    for (int bn = 256; bn >= 32; bn -= 32)
+  if (p.BN == 0) {
+    // 256 and 128 first: with the 32 KB of epilogue staging, 128 keeps three 64 KB stages in flight (N = 640: 128 beats
+    // 160, which only fits two); then the largest divisor (672 -> 224, 320 -> 160).  profiles/r01/gemm_f16_sweep.jsonl
+    static const int order[] = {256, 128, 224, 192, 160, 96, 64, 32};
+    for (int bn : order)
       if (w->N % bn == 0) { p.BN = bn; break; }
+  }
   DCAE_REQUIRE(p.BN > 0, "gemm(f16x3): N=%d must be a multiple of 32", w->N);
   p.tmem_cols = 2 * p.BN <= 64 ? 64 : 2 * p.BN <= 128 ? 128 : 2 * p.BN <= 256 ? 256 : 512;
   p.n_tiles_n = w->N / p.BN;
@@ -319,18 +448,39 @@ int gemm_tcgen05_f16x3(const dcae_operand* a, const dcae_weight* w, const dcae_e
   p.chunk_kb = CHUNK_MMAS / 12;
   if (const char* env = getenv("DCAE_TC_CHUNK")) { const int v = atoi(env); if (v >= 1) p.chunk_kb = v; }
   p.descale = w->descale;
+  p.dbg_nostore = getenv("DCAE_TC_NOSTORE") != nullptr;
   p.b_bytes = (uint32_t)p.BN * BK16 * 2;
   p.stage_bytes = 2 * A16_BYTES + 2 * p.b_bytes;
-  p.stages = (int)((SMEM_LIMIT - 2048) / p.stage_bytes);
+  p.stages = (int)((SMEM_LIMIT - 2048 - 2 * STG_BYTES) / p.stage_bytes);
   if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
   if (const char* env = getenv("DCAE_TC_STAGES")) { const int v = atoi(env); if (v >= 1 && v < p.stages) p.stages = v; }
   if (p.stages > p.KB) p.stages = p.KB;
-  const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
+  DCAE_REQUIRE(p.stages >= 1, "gemm(f16x3): tile does not fit in shared memory");
+  const size_t smem = (size_t)p.stages * p.stage_bytes + 2 * STG_BYTES + 1024;
+  p.has_o32 = e->out != nullptr;
+  p.has_o16 = e->out16.hi != nullptr;
 
-  CUtensorMap map_ah, map_al, map_bh, map_bl;
+  CUtensorMap map_ah, map_al, map_bh, map_bl, map_o32, map_oh, map_ol;
   {
+    // output boxes {32 columns, TW, TH, 1}; dims[0] = N clips a ragged last block, (w, h) clip ragged token tiles
+    cuuint32_t box[4] = {32, (cuuint32_t)p.TW, (cuuint32_t)p.TH, 1};
+    cuuint64_t dims[4] = {(cuuint64_t)w->N, (cuuint64_t)a->w, (cuuint64_t)a->h, (cuuint64_t)a->B};
+    if (p.has_o32) {
+      DCAE_REQUIRE(aligned16(e->out) && e->out_ld % 4 == 0, "gemm(f16x3): fp32 output must be 16-byte aligned with ld %% 4 == 0");
+      cuuint64_t str[3] = {(cuuint64_t)e->out_ld * 4, (cuuint64_t)e->out_ld * 4 * a->w, (cuuint64_t)e->out_ld * 4 * a->w * a->h};
+      DCAE_TRY(encode_map(&map_o32, e->out, 4, dims, str, box));
+    }
+    if (p.has_o16) {
+      DCAE_REQUIRE(aligned16(e->out16.hi) && aligned16(e->out16.lo) && e->out16.ld % 8 == 0, "gemm(f16x3): output planes must be 16-byte aligned with ld %% 8 == 0");
+      cuuint64_t str[3] = {(cuuint64_t)e->out16.ld * 2, (cuuint64_t)e->out16.ld * 2 * a->w, (cuuint64_t)e->out16.ld * 2 * a->w * a->h};
+      DCAE_TRY(encode_map_f16(&map_oh, e->out16.hi, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B));
+      DCAE_TRY(encode_map_f16(&map_ol, e->out16.lo, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B));
+    }
+  }
+  {
+    // dims[0] = Kp: a window that is not a multiple of 64 wide over-reads into the next columns (zero weights there)
     cuuint64_t dims[4] = {(cuuint64_t)Kp, (cuuint64_t)a->w, (cuuint64_t)a->h, (cuuint64_t)a->B};
-    cuuint64_t str[3] = {(cuuint64_t)Kp * 2, (cuuint64_t)Kp * 2 * a->w, (cuuint64_t)Kp * 2 * a->w * a->h};
+    cuuint64_t str[3] = {(cuuint64_t)ldp * 2, (cuuint64_t)ldp * 2 * a->w, (cuuint64_t)ldp * 2 * a->w * a->h};
     cuuint32_t box[4] = {BK16, (cuuint32_t)p.TW, (cuuint32_t)p.TH, 1};
     DCAE_TRY(encode_map_f16(&map_ah, hi, 4, dims, str, box));
     DCAE_TRY(encode_map_f16(&map_al, lo, 4, dims, str, box));
@@ -342,6 +492,8 @@ int gemm_tcgen05_f16x3(const dcae_operand* a, const dcae_weight* w, const dcae_e
     DCAE_TRY(encode_map_f16(&map_bh, w->w16_hi, 2, dims, str, box));
     DCAE_TRY(encode_map_f16(&map_bl, w->w16_lo, 2, dims, str, box));
   }
+  if (!p.has_o32) map_o32 = map_bh;       // unused by the kernel
+  if (!p.has_o16) { map_oh = map_bh; map_ol = map_bh; }
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(attr_once, [] {
@@ -349,7 +501,7 @@ int gemm_tcgen05_f16x3(const dcae_operand* a, const dcae_weight* w, const dcae_e
   });
   DCAE_CUDA(attr_err);
   const int ctas = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-  gemm_f16x3_kernel<0><<<ctas, NTHREADS, smem, s>>>(map_ah, map_al, map_bh, map_bl, p);
+  gemm_f16x3_kernel<0><<<ctas, NTHREADS, smem, s>>>(map_ah, map_al, map_bh, map_bl, map_o32, map_oh, map_ol, p);
   DCAE_LAUNCH_CHECK();
   return DCAE_OK;
 }

@@ -95,6 +95,15 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ float tf32_rna(float v) {
   uint32_t o;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(o) : "f"(v));
@@ -195,20 +204,30 @@ __device__ __forceinline__ float epi_act(float v, int act) {
   return v;
 }
 
-// acc (+)= the chain partial sitting in TMEM at taddr (this warp's lane quarter, start of the chain buffer)
+// acc (+)= the chain partial sitting in TMEM at taddr (this warp's lane quarter, start of the chain buffer).
+// Both tcgen05.ld of a 32-column block are in flight per wait (more would spill next to the 128 running sums).
 __device__ __forceinline__ void drain_chunk(float* acc, uint32_t taddr, int half, int BN, bool first) {
 #pragma unroll
-  for (int g = 0; g < EPI_BLOCKS; ++g) {
-    const int blk = 2 * g + half;
-    if (blk * 32 < BN) {                      // warp-uniform
+  for (int gg = 0; gg < EPI_BLOCKS; gg += 1) {
+    uint32_t raw[32];
 #pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        uint32_t raw[16];
-        tmem_ld16(taddr + blk * 32 + hh * 16, raw);
+    for (int g = gg; g < gg + 1; ++g) {
+      const int blk = 2 * g + half;
+      if (blk * 32 < BN) {                      // warp-uniform
+        tmem_ld16_nowait(taddr + blk * 32, raw + (g - gg) * 32);
+        tmem_ld16_nowait(taddr + blk * 32 + 16, raw + (g - gg) * 32 + 16);
+      }
+    }
+    tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int i = g * 32 + hh * 16 + j;
-          acc[i] = first ? __uint_as_float(raw[j]) : __fadd_rn(acc[i], __uint_as_float(raw[j]));
+    for (int g = gg; g < gg + 1; ++g) {
+      const int blk = 2 * g + half;
+      if (blk * 32 < BN) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int i = g * 32 + j;
+          const float v = __uint_as_float(raw[(g - gg) * 32 + j]);
+          acc[i] = first ? v : __fadd_rn(acc[i], v);
         }
       }
     }
@@ -227,7 +246,7 @@ struct EpiTile {
 // store pattern, was what made the epilogue slower than the single-pass mainloop).
 template <int ACT>
 __device__ __forceinline__ void epi_block(const float* r, const dcae_epilogue& e, int64_t token, int n0) {
-  float* orow = e.out + token * e.out_ld + n0;
+  float* orow = e.out ? e.out + token * e.out_ld + n0 : nullptr;
 #pragma unroll
   for (int j = 0; j < 32; j += 4) {
     const int n = n0 + j;
@@ -248,7 +267,8 @@ __device__ __forceinline__ void epi_block(const float* r, const dcae_epilogue& e
       if (e.res_scale) rs = __ldg(reinterpret_cast<const float4*>(e.res_scale + n));
       v.x = fmaf(rv.x, rs.x, v.x); v.y = fmaf(rv.y, rs.y, v.y); v.z = fmaf(rv.z, rs.z, v.z); v.w = fmaf(rv.w, rs.w, v.w);
     }
-    *reinterpret_cast<float4*>(orow + j) = v;
+    if (orow) *reinterpret_cast<float4*>(orow + j) = v;
+    if (e.out16.hi) store_planes4(e.out16, token, n, v);
   }
 }
 

@@ -184,6 +184,24 @@ class EntropySliceLoop:
         return flat[off: off + T * ld.value].view(T, ld.value)[:, : cols.value].clone()
 
 
+def _tap16(self, name: str, B: int, h: int, w: int) -> torch.Tensor:
+    """f16x3 mode: a planes-only intermediate [T, cols] reconstructed as fp32 (hi + lo)."""
+    plan = self._plan(B, h, w)
+    pl, cols = _lib.Planes(), C.c_int32()
+    _lib.check(self.lib.dcae_slice_loop_tap16(plan.handle, name.encode(), C.byref(pl), C.byref(cols)), "tap16")
+    T, ld = B * h * w, int(pl.ld)
+    ws = plan.workspace
+
+    def view(ptr):
+        off = ptr - ws.data_ptr()
+        return ws[off: off + T * ld * 2].view(torch.float16).view(T, ld)
+
+    return (view(pl.hi).float() + view(pl.lo).float())[:, : cols.value].clone()
+
+
+EntropySliceLoop.tap16 = _tap16
+
+
 def bits_per_pixel(log2_lik_sum: torch.Tensor, num_pixels: int) -> torch.Tensor:
     """train.py:82-85 with the log2 sum the slice loop already reduced: bpp = -sum(log2 lik) / num_pixels."""
     return -log2_lik_sum / float(num_pixels)

@@ -150,10 +150,10 @@ class PackedWeights:
         d = torch.empty(DICT_NUM, DICT_DIM, device=self.device)
         gam, bet = self._dev(ln_w), self._dev(ln_b)
         _lib.check(lib.dcae_op_layernorm(dt.data_ptr(), DICT_DIM, gam.data_ptr(), bet.data_ptr(), DICT_DIM, DICT_NUM,
-                                         d.data_ptr(), DICT_DIM, s), "dcae_op_layernorm")
+                                         d.data_ptr(), DICT_DIM, None, s), "dcae_op_layernorm")
         kw, kb = self._dev(k_w), self._dev(k_b)
         k = torch.empty(DICT_NUM, DICT_DIM, device=self.device)
-        a = _lib.Operand(d.data_ptr(), DICT_DIM, 0, DICT_DIM, 0, 0, 1, 1, 1, DICT_NUM)
+        a = _lib.Operand(d.data_ptr(), DICT_DIM, 0, DICT_DIM, 0, 0, 1, 1, 1, DICT_NUM, None, 0)
         w = _lib.Weight(kw.data_ptr(), None, None, DICT_DIM, DICT_DIM)
         e = _lib.Epilogue()
         e.bias, e.out, e.out_ld = kb.data_ptr(), k.data_ptr(), DICT_DIM

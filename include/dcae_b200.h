@@ -49,6 +49,11 @@ enum {
                               operands) at twice the TF32 MMA rate and half the operand bytes per flop */
 };
 
+/* fp16 hi/lo planes of a token-major matrix: value = float(hi[t, c]) + float(lo[t, c]) (22 significant bits).
+ * Both planes are [T, ld] fp16; the pointers may be pre-offset to a column window (8-byte aligned, ld % 4 == 0).
+ * Producers write them directly (out16 arguments below) so that DCAE_MATH_F16X3 GEMMs need no split pass. */
+typedef struct { void* hi; void* lo; int64_t ld; } dcae_planes;
+
 int dcae_version(void);
 const char* dcae_last_error(void);
 /* 0 if the current device is compute capability 10.x, DCAE_E_DEVICE otherwise. */
@@ -88,6 +93,7 @@ typedef struct {
   int32_t mode;
   int64_t rows; int64_t inner;
   float* y_hat;   int64_t y_hat_ld;
+  dcae_planes y_hat16;                            /* optional: y_hat also as fp16 planes (LRP conv operand) */
   float* lik;     int64_t lik_ld;
   int32_t* sym;   int64_t sym_ld;
   int32_t* idx;   int64_t idx_ld;
@@ -115,6 +121,10 @@ typedef struct {
   /* DCAE_MATH_F16X3 only: caller-owned scratch of dcae_planes_bytes(T, k0 + k1) bytes that receives the fp16
    * hi/lo planes of the operand window (the split runs as its own HBM-bound launch before the GEMM). */
   void* planes; int64_t planes_bytes;
+  /* DCAE_MATH_F16X3: if src16.hi != NULL the window [col0, col0 + k0) is read from these planes directly
+   * (k1 must be 0; base may be NULL; the window may be over-read up to the next multiple of 64 columns, which
+   * must be allocated and finite -- the weight planes are zero there). */
+  dcae_planes src16;
 } dcae_operand;
 int64_t dcae_planes_bytes(int64_t T, int32_t cols);
 
@@ -129,7 +139,8 @@ typedef struct {
   const float* residual; int64_t residual_ld;
   const float* res_scale;
   int32_t act; int32_t act_cols;
-  float* out; int64_t out_ld;
+  float* out; int64_t out_ld;          /* may be NULL when out16 is given */
+  dcae_planes out16;                   /* tcgen05 paths only: also (or only) write the result as fp16 planes */
 } dcae_epilogue;
 
 /* Dense weight [N, K] row-major (K contiguous; nn.Linear layout).  `w` is the fp32 weight;
@@ -154,14 +165,16 @@ int dcae_split_tf32(const float* w, float* w_hi, float* w_lo, int64_t n, void* s
 
 /* LayerNorm over C channels per token, eps 1e-5 (dcae.py:461,465,467,471). */
 int dcae_op_layernorm(const float* x, int64_t x_ld, const float* gamma, const float* beta, int32_t C,
-                      int64_t T, float* out, int64_t out_ld, void* stream);
+                      int64_t T, float* out, int64_t out_ld, const dcae_planes* out16, void* stream);
 /* out = gelu(x) (exact erf form), [T, C] (dcae.py:421-423 prologue GELU of the dense block). */
-int dcae_op_gelu(const float* x, int64_t x_ld, int32_t C, int64_t T, float* out, int64_t out_ld, void* stream);
+int dcae_op_gelu(const float* x, int64_t x_ld, int32_t C, int64_t T, float* out, int64_t out_ld,
+                 const dcae_planes* out16, void* stream);
+/* In every operator below `out` may be NULL when `out16` (fp16 planes of the same result) is given. */
 /* Depthwise 3x3, stride 1, pad 1 on a token grid (dcae.py:303,404): wt is [9, C] tap-major.
  * out = act(dw(x) + bias) * gate   (gate nullable: ConvolutionalGLU, dcae.py:325-326). */
 int dcae_op_dwconv3x3(const float* x, int64_t x_ld, const float* wt, const float* bias, int32_t C,
                       int32_t B, int32_t h, int32_t w, int32_t act, const float* gate, int64_t gate_ld,
-                      float* out, int64_t out_ld, void* stream);
+                      float* out, int64_t out_ld, const dcae_planes* out16, void* stream);
 /* SpatialAttentionModule + residual (dcae.py:386-397, 446, 484):
  * out = s_out * sigmoid(conv7x7([mean_c s_out, max_c s_out])) + res_scale * x0.
  * stats: scratch [T, 2].  w7: [2, 7, 7]. */
@@ -182,9 +195,10 @@ typedef struct {
   const float* head_scale;     /* [20] learned per-head scale (dcae.py:457,498) */
 } dcae_dict_kv;
 int dcae_op_dict_attention(const float* q, int64_t q_ld, const dcae_dict_kv* kv, int64_t T, float* out,
-                           int64_t out_ld, int math, void* stream);
+                           int64_t out_ld, const dcae_planes* out16, int math, void* stream);
 /* 'b c h w -> (b h w) c' and back, for a channel window of the token-major buffer. */
-int dcae_op_nchw_to_tokens(const float* src, int32_t B, int32_t C, int64_t HW, float* dst, int64_t dst_ld, void* stream);
+int dcae_op_nchw_to_tokens(const float* src, int32_t B, int32_t C, int64_t HW, float* dst, int64_t dst_ld,
+                           const dcae_planes* dst16, void* stream);
 int dcae_op_tokens_to_nchw(const float* src, int64_t src_ld, int32_t B, int32_t C, int64_t HW, float* dst, void* stream);
 int dcae_op_tokens_to_nchw_i32(const int32_t* src, int64_t src_ld, int32_t B, int32_t C, int64_t HW, int32_t* dst, void* stream);
 int dcae_op_nchw_to_tokens_i32(const int32_t* src, int32_t B, int32_t C, int64_t HW, int32_t* dst, int64_t dst_ld, void* stream);
@@ -264,6 +278,9 @@ int dcae_slice_loop_forward(dcae_slice_loop* p, const float* y, const float* lat
 /* Debug/test access to a named token-major intermediate of the last call ("x0","x1","q","attn","x2",
  * "x3","support","h1"...): returns pointer, columns and ld; 0 on success. */
 int dcae_slice_loop_tap(dcae_slice_loop* p, const char* name, const float** ptr, int32_t* cols, int64_t* ld);
+/* Same for intermediates that only exist as fp16 planes in DCAE_MATH_F16X3 mode ("support", "ln", "gelu", "dw",
+ * "dense", "attn", "glu", "x3", "h1", "h2", "l1", "l2"). */
+int dcae_slice_loop_tap16(dcae_slice_loop* p, const char* name, dcae_planes* planes, int32_t* cols);
 /* Number of kernels the last dcae_slice_loop_* call enqueued (bench `gpu_launches`). */
 int64_t dcae_launch_count(void);
 

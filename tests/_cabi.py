@@ -17,7 +17,9 @@ def split_weight(w2d: torch.Tensor):
 
 
 def gemm(buf, B, h, w, col0, k0, weight2d, math="fp32", taps=1, col1=0, k1=0, bias=None, addend=None,
-         residual=None, res_scale=None, act=0, act_cols=0, out=None, out_col=0):
+         residual=None, res_scale=None, act=0, act_cols=0, out=None, out_col=0, src16=None, out16=None):
+    """src16 = (hi, lo) fp16 planes [T, ld] to read the operand window from (f16x3); out16 = (hi, lo) planes to
+    also write the result to."""
     """buf: token-major [T, ld] CUDA fp32.  weight2d: [N, K].  Returns out [T, N] (or writes into `out`)."""
     lib = _lib.load()
     T, ld = buf.shape
@@ -29,6 +31,9 @@ def gemm(buf, B, h, w, col0, k0, weight2d, math="fp32", taps=1, col1=0, k1=0, bi
     planes = torch.empty(nbytes + 128, dtype=torch.uint8, device=buf.device)
     pbase = (planes.data_ptr() + 127) // 128 * 128
     a = _lib.Operand(buf.data_ptr(), ld, col0, k0, col1, k1, taps, B, h, w, pbase, nbytes)
+    if src16 is not None:
+        a.src16 = _lib.Planes(src16[0].data_ptr(), src16[1].data_ptr(), src16[0].stride(0))
+        a.base = None
     h16, l16, K16, descale = f16_weight_planes(lib, wt, taps, _s(buf.device))
     W = _lib.Weight(wt.data_ptr(), hi.data_ptr(), lo.data_ptr(), N, K, h16.data_ptr(), l16.data_ptr(), K16, descale)
     if out is None:
@@ -42,33 +47,44 @@ def gemm(buf, B, h, w, col0, k0, weight2d, math="fp32", taps=1, col1=0, k1=0, bi
     e.res_scale = _lib.ptr(res_scale)
     e.act, e.act_cols = act, act_cols
     e.out, e.out_ld = out.data_ptr() + 4 * out_col, out.stride(0)
+    if out16 is not None:
+        e.out16 = _lib.Planes(out16[0].data_ptr(), out16[1].data_ptr(), out16[0].stride(0))
     _lib.check(lib.dcae_op_gemm(a, W, e, _lib.MATH[math], _s(buf.device)), "dcae_op_gemm")
     return out
 
 
-def layernorm(x, g, b):
+def _planes(T, C, dev):
+    hi = torch.zeros(T, C, dtype=torch.float16, device=dev)
+    lo = torch.zeros(T, C, dtype=torch.float16, device=dev)
+    return _lib.Planes(hi.data_ptr(), lo.data_ptr(), C), hi, lo
+
+
+def layernorm(x, g, b, planes=False):
     lib = _lib.load()
     out = torch.empty_like(x)
+    p16, hi, lo = _planes(x.shape[0], x.shape[1], x.device) if planes else (None, None, None)
     _lib.check(lib.dcae_op_layernorm(x.data_ptr(), x.stride(0), g.data_ptr(), b.data_ptr(), x.shape[1], x.shape[0],
-                                     out.data_ptr(), out.stride(0), _s(x.device)))
-    return out
+                                     out.data_ptr(), out.stride(0), p16, _s(x.device)))
+    return (out, hi, lo) if planes else out
 
 
-def gelu(x):
+def gelu(x, planes=False):
     lib = _lib.load()
     out = torch.empty_like(x)
-    _lib.check(lib.dcae_op_gelu(x.data_ptr(), x.stride(0), x.shape[1], x.shape[0], out.data_ptr(), out.stride(0), _s(x.device)))
-    return out
+    p16, hi, lo = _planes(x.shape[0], x.shape[1], x.device) if planes else (None, None, None)
+    _lib.check(lib.dcae_op_gelu(x.data_ptr(), x.stride(0), x.shape[1], x.shape[0], out.data_ptr(), out.stride(0), p16, _s(x.device)))
+    return (out, hi, lo) if planes else out
 
 
-def dwconv3x3(x, wt9c, bias, B, h, w, act=0, gate=None):
+def dwconv3x3(x, wt9c, bias, B, h, w, act=0, gate=None, planes=False):
     lib = _lib.load()
     C = wt9c.shape[1]
     out = torch.empty(x.shape[0], C, device=x.device)
+    p16, hi, lo = _planes(x.shape[0], C, x.device) if planes else (None, None, None)
     _lib.check(lib.dcae_op_dwconv3x3(x.data_ptr(), x.stride(0), wt9c.data_ptr(), bias.data_ptr(), C, B, h, w, act,
                                      _lib.ptr(gate), gate.stride(0) if gate is not None else 0,
-                                     out.data_ptr(), out.stride(0), _s(x.device)))
-    return out
+                                     out.data_ptr(), out.stride(0), p16, _s(x.device)))
+    return (out, hi, lo) if planes else out
 
 
 def spatial_gate(s_out, x0, res_scale, w7, B, h, w):
@@ -81,7 +97,7 @@ def spatial_gate(s_out, x0, res_scale, w7, B, h, w):
     return out
 
 
-def dict_attention(q, Kh, Vh, head_scale, math="fp32"):
+def dict_attention(q, Kh, Vh, head_scale, math="fp32", planes=False):
     lib = _lib.load()
     out = torch.empty_like(q)
     Kh, Vh = Kh.contiguous(), Vh.contiguous()
@@ -90,16 +106,21 @@ def dict_attention(q, Kh, Vh, head_scale, math="fp32"):
     vhi, vlo = split_weight(Vt)
     kv = _lib.DictKV(Kh.data_ptr(), Vh.data_ptr(), khi.data_ptr(), klo.data_ptr(), vhi.data_ptr(), vlo.data_ptr(),
                      head_scale.data_ptr())
-    _lib.check(lib.dcae_op_dict_attention(q.data_ptr(), q.stride(0), kv, q.shape[0], out.data_ptr(), out.stride(0),
+    p16, hi, lo = _planes(q.shape[0], q.shape[1], q.device) if planes else (None, None, None)
+    _lib.check(lib.dcae_op_dict_attention(q.data_ptr(), q.stride(0), kv, q.shape[0], out.data_ptr(), out.stride(0), p16,
                                           _lib.MATH[math], _s(q.device)), "dcae_op_dict_attention")
-    return out
+    return (out, hi, lo) if planes else out
 
 
-def nchw_to_tokens(x):
+def nchw_to_tokens(x, planes=False):
     lib = _lib.load()
     B, C, H, W = x.shape
     out = torch.empty(B * H * W, C, device=x.device, dtype=x.dtype)
     fn = lib.dcae_op_nchw_to_tokens if x.dtype == torch.float32 else lib.dcae_op_nchw_to_tokens_i32
+    if x.dtype == torch.float32:
+        p16, hi, lo = _planes(B * H * W, C, x.device) if planes else (None, None, None)
+        _lib.check(fn(x.contiguous().data_ptr(), B, C, H * W, out.data_ptr(), C, p16, _s(x.device)))
+        return (out, hi, lo) if planes else out
     _lib.check(fn(x.contiguous().data_ptr(), B, C, H * W, out.data_ptr(), C, _s(x.device)))
     return out
 

@@ -156,3 +156,49 @@ def test_transposes_roundtrip():
     xi = torch.randint(-100, 100, (2, 64, 4, 6), dtype=torch.int32)
     ti = K.nchw_to_tokens(xi.cuda())
     assert torch.equal(K.tokens_to_nchw(ti, 2, 4, 6).cpu(), xi)
+
+
+def _planes_close(hi, lo, want):
+    """fp16 hi + lo carries 22 bits: |hi + lo - v| <= 2^-21 |v| (+ the fp16 subnormal quantum)."""
+    got = hi.float() + lo.float()
+    return bool(((got - want).abs() <= 2.0 ** -21 * want.abs() + 1.2e-7).all())
+
+
+def test_producers_write_fp16_planes():
+    """Every producer of a GEMM operand can emit the fp16 hi/lo planes the f16x3 GEMM reads (no split pass)."""
+    x = torch.randn(257, 640, generator=g(40)) * 3
+    gm, bt = torch.rand(640, generator=g(41)) + 0.5, torch.randn(640, generator=g(42))
+    out, hi, lo = K.layernorm(x.cuda(), gm.cuda(), bt.cuda(), planes=True)
+    assert _planes_close(hi, lo, out)
+    out, hi, lo = K.gelu(x.cuda(), planes=True)
+    assert _planes_close(hi, lo, out)
+    B, h, w, C = 2, 7, 9, 640
+    xi = torch.randn(B, C, h, w, generator=g(43))
+    out, hi, lo = K.dwconv3x3(tok(xi).cuda(), (torch.randn(C, 9, generator=g(44)) / 3).t().contiguous().cuda(),
+                              torch.randn(C, generator=g(45)).cuda(), B, h, w, act=1, planes=True)
+    assert _planes_close(hi, lo, out)
+    out, hi, lo = K.nchw_to_tokens(xi.cuda(), planes=True)
+    assert _planes_close(hi, lo, out) and torch.equal(out.cpu(), tok(xi))
+    q = torch.randn(300, 640, generator=g(46))
+    Kh, Vh = torch.randn(20, 128, 32, generator=g(47)) * 0.5, torch.randn(20, 128, 32, generator=g(48))
+    out, hi, lo = K.dict_attention(q.cuda(), Kh.cuda(), Vh.cuda(), (torch.rand(20, generator=g(49)) + 0.5).cuda(), math="tf32x3", planes=True)
+    assert _planes_close(hi, lo, out)
+
+
+def test_f16x3_gemm_reads_and_writes_planes_directly():
+    B, h, w, C, N = 2, 7, 9, 224, 128
+    T = B * h * w
+    x = torch.randn(B, 704, h, w, generator=g(50))
+    wt = torch.randn(N, C, 3, 3, generator=g(51)) / (9 * C) ** 0.5
+    b = torch.randn(N, generator=g(52))
+    xt = tok(x).cuda()                                    # [T, 704]; the operand is the window [224, 448)
+    hi = xt.half()
+    lo = (xt - hi.float()).half()
+    want = tok(torch.nn.functional.gelu(torch.nn.functional.conv2d(x[:, 224:448], wt, b, padding=1)))
+    w2d = wt.permute(0, 2, 3, 1).reshape(N, 9 * C).cuda()
+    o_hi = torch.zeros(T, 256, dtype=torch.float16, device="cuda")
+    o_lo = torch.zeros_like(o_hi)
+    got = K.gemm(xt, B, h, w, 224, C, w2d, math="f16x3", taps=9, bias=b.cuda(), act=1, src16=(hi, lo), out16=(o_hi, o_lo))
+    assert rel_err(got.cpu(), want) < 1e-5
+    assert _planes_close(o_hi[:, :N], o_lo[:, :N], got)
+    assert float(o_hi[:, N:].abs().max()) == 0.0

@@ -48,6 +48,14 @@ for math in (sys.argv[2:] or ("tf32x3", "tf32")):
     for Kd, N, taps, bn in [(640, 640, 1, 160), (640, 640, 1, 128), (2560, 640, 1, 160), (640, 2560, 1, 256), (8640, 672, 9, 224),
                             (2016, 128, 9, 128), (1152, 64, 9, 64), (640, 320, 1, 160)]:
         bench(Kd, N, math, taps, bn=bn)
+        if len(sys.argv) > 1 and sys.argv[1] == "f16":
+            bench(Kd, N, math, taps, bn=bn, nostore=1)
+            for st in (2, 3):
+                bench(Kd, N, math, taps, bn=bn, stages=st)
+            for b2 in (64, 96, 128, 192):
+                if N % b2 == 0 and b2 != bn:
+                    bench(Kd, N, math, taps, bn=b2)
+            continue
         if len(sys.argv) > 1 and sys.argv[1] == "epi":
             for v in (1, 2, 3):
                 bench(Kd, N, math, taps, bn=bn, epi=v)
