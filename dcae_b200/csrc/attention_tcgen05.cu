@@ -159,8 +159,36 @@ dict_attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const _
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;
     const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
-    for (int g = 0; g < total; ++g) {
+    // O(g-1) is read back only after the exponentials of head g are done, so the PV MMAs of head g-1 run
+    // underneath the softmax arithmetic of head g (and S(g+1) underneath that of head g, see the MMA warp).
+    auto write_out = [&](int g, float inv) {
       const int tile = blockIdx.x + (g / AT_HEADS) * gridDim.x, head = g % AT_HEADS;
+      mbar_wait(smem_u32(&o_full), g & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      uint32_t o0[16], o1[16];
+      tmem_ld16_nowait(lane_addr + TM_O, o0);
+      tmem_ld16_nowait(lane_addr + TM_O + 16, o1);
+      tmem_ld_wait();
+      const int64_t token = (int64_t)tile * AT_M + r;
+      if (token < p.T) {
+        float4* dst = p.out ? reinterpret_cast<float4*>(p.out + token * p.out_ld + head * AT_HD) : nullptr;
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          const float4 a = make_float4(__uint_as_float(o0[j]) * inv, __uint_as_float(o0[j + 1]) * inv,
+                                       __uint_as_float(o0[j + 2]) * inv, __uint_as_float(o0[j + 3]) * inv);
+          const float4 b = make_float4(__uint_as_float(o1[j]) * inv, __uint_as_float(o1[j + 1]) * inv,
+                                       __uint_as_float(o1[j + 2]) * inv, __uint_as_float(o1[j + 3]) * inv);
+          if (dst) { dst[j / 4] = a; dst[4 + j / 4] = b; }
+          if (p.out16.hi) {
+            store_planes4(p.out16, token, head * AT_HD + j, a);
+            store_planes4(p.out16, token, head * AT_HD + 16 + j, b);
+          }
+        }
+      }
+    };
+    float inv_prev = 0.f;
+    for (int g = 0; g < total; ++g) {
+      const int head = g % AT_HEADS;
       const float sc = __ldg(p.head_scale + head);
       mbar_wait(smem_u32(&s_full), g & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -184,7 +212,8 @@ dict_attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const _
         s[j] = expf(s[j] - mx);
         l += s[j];
       }
-      // P(g) may overwrite P(g-1): the PV MMAs of head g-1 completed before o_full(g-1), waited below
+      if (g > 0) write_out(g - 1, inv_prev);                   // also guarantees PV(g-1) has finished reading P
+      inv_prev = 1.0f / l;
 #pragma unroll
       for (int c = 0; c < AT_ND / 16; ++c) {
         uint32_t hi[16], lo[16];
@@ -201,30 +230,8 @@ dict_attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const _
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive(smem_u32(&p_ready));
-      mbar_wait(smem_u32(&o_full), g & 1);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      uint32_t o0[16], o1[16];
-      tmem_ld16_nowait(lane_addr + TM_O, o0);
-      tmem_ld16_nowait(lane_addr + TM_O + 16, o1);
-      tmem_ld_wait();
-      const int64_t token = (int64_t)tile * AT_M + r;
-      if (token < p.T) {
-        const float inv = 1.0f / l;
-        float4* dst = p.out ? reinterpret_cast<float4*>(p.out + token * p.out_ld + head * AT_HD) : nullptr;
-#pragma unroll
-        for (int j = 0; j < 16; j += 4) {
-          const float4 a = make_float4(__uint_as_float(o0[j]) * inv, __uint_as_float(o0[j + 1]) * inv,
-                                       __uint_as_float(o0[j + 2]) * inv, __uint_as_float(o0[j + 3]) * inv);
-          const float4 b = make_float4(__uint_as_float(o1[j]) * inv, __uint_as_float(o1[j + 1]) * inv,
-                                       __uint_as_float(o1[j + 2]) * inv, __uint_as_float(o1[j + 3]) * inv);
-          if (dst) { dst[j / 4] = a; dst[4 + j / 4] = b; }
-          if (p.out16.hi) {
-            store_planes4(p.out16, token, head * AT_HD + j, a);
-            store_planes4(p.out16, token, head * AT_HD + 16 + j, b);
-          }
-        }
-      }
     }
+    if (total > 0) write_out(total - 1, inv_prev);
   } else {
     // ===================== Q splitters (3-pass): q -> (q_hi in place, q_lo) =====================
     if (PASSES == 3) {

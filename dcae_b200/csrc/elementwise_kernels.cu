@@ -69,23 +69,24 @@ __global__ void __launch_bounds__(256) gelu_kernel(const float* __restrict__ x, 
 // once (3.75 float4 loads per output instead of 9), consecutive threads take consecutive channel
 // groups so every load/store is a coalesced 16-byte access.
 // ---------------------------------------------------------------------------------------------
-constexpr int DW_X = 8;
+constexpr int DW_X = 8, DW_ROWS = 4;
 
-__global__ void __launch_bounds__(128) dwconv3x3_kernel(const float* __restrict__ x, int64_t x_ld,
+// grid = (ceil(C4 / 32), ceil(h / DW_ROWS), B * ceil(w / DW_X)); block = 32 channel groups x DW_ROWS token rows, so the
+// three input rows a thread needs are shared with its neighbours in the block through L1.
+__global__ void __launch_bounds__(32 * DW_ROWS) dwconv3x3_kernel(const float* __restrict__ x, int64_t x_ld,
                                                         const float* __restrict__ wt, const float* __restrict__ bias,
                                                         int C4, int B, int h, int w, int act,
                                                         const float* __restrict__ gate, int64_t gate_ld,
                                                         float* __restrict__ out, int64_t out_ld, const dcae_planes o16) {
   const int xg = (w + DW_X - 1) / DW_X;
-  const int64_t n = (int64_t)B * h * xg * C4;
   const int C = C4 * 4;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C4) * 4;
-    int64_t r = i / C4;
-    const int x0 = (int)(r % xg) * DW_X;
-    r /= xg;
-    const int yy = (int)(r % h);
-    const int b = (int)(r / h);
+  const int c4 = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int yy = blockIdx.y * DW_ROWS + (threadIdx.x >> 5);
+  const int b = blockIdx.z / xg;
+  const int x0 = (blockIdx.z - b * xg) * DW_X;
+  if (c4 >= C4 || yy >= h) return;
+  {
+    const int c = c4 * 4;
     float4 k[9];
 #pragma unroll
     for (int t = 0; t < 9; ++t) k[t] = __ldg(reinterpret_cast<const float4*>(wt + t * C + c));
@@ -333,9 +334,11 @@ extern "C" int dcae_op_dwconv3x3(const float* x, int64_t x_ld, const float* wt, 
   DCAE_REQUIRE(C % 4 == 0 && x_ld % 4 == 0 && out_ld % 4 == 0 && (gate == nullptr || gate_ld % 4 == 0), "dcae_op_dwconv3x3: C and lds must be multiples of 4");
   DCAE_REQUIRE(aligned16(x) && aligned16(wt) && aligned16(bias) && aligned16(out) && aligned16(gate), "dcae_op_dwconv3x3: 16-byte alignment required");
   DCAE_REQUIRE(act == DCAE_ACT_NONE || act == DCAE_ACT_GELU, "dcae_op_dwconv3x3: act must be NONE or GELU");
-  const int64_t n4 = (int64_t)B * h * ((w + DW_X - 1) / DW_X) * (C / 4);
-  if (n4 == 0) return DCAE_OK;
-  dwconv3x3_kernel<<<grid_for(n4, 128), 128, 0, (cudaStream_t)stream>>>(x, x_ld, wt, bias, C / 4, B, h, w, act, gate, gate_ld, out, out_ld, o16);
+  if ((int64_t)B * h * w == 0) return DCAE_OK;
+  const int xg = (w + DW_X - 1) / DW_X;
+  DCAE_REQUIRE((int64_t)B * xg <= 65535 && (h + DW_ROWS - 1) / DW_ROWS <= 65535, "dcae_op_dwconv3x3: token grid too large");
+  dim3 grid((unsigned)((C / 4 + 31) / 32), (unsigned)((h + DW_ROWS - 1) / DW_ROWS), (unsigned)(B * xg));
+  dwconv3x3_kernel<<<grid, 32 * DW_ROWS, 0, (cudaStream_t)stream>>>(x, x_ld, wt, bias, C / 4, B, h, w, act, gate, gate_ld, out, out_ld, o16);
   DCAE_LAUNCH_CHECK();
   return DCAE_OK;
 }
