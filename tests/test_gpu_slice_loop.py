@@ -235,3 +235,29 @@ def test_host_pipeline_matches_direct_calls(lively_params):
         want = eng.forward(*[t.cuda() for t in b], want_symbols=True)
         for k in ("y_hat", "means", "scales", "likelihoods", "symbols", "indexes"):
             assert torch.equal(res[k], want[k].cpu()), k
+
+
+@pytest.mark.parametrize("name,B,h,w", [("config1_256x256", 1, 16, 16), ("config3_clic_2048x1408", 1, 88, 128),
+                                        ("config5_4k_3840x2176", 1, 136, 240)])
+def test_baseline_config_shapes(name, B, h, w, lively_params):
+    """BASELINE.json configs #1 / #3 / #5 at their full latent sizes (one image): slice 0 against the CPU oracle
+    (nothing has cascaded yet), then the size-independent properties of the whole loop."""
+    eng = engine(lively_params, "f16x3")
+    gen = torch.Generator().manual_seed(1234)
+    y = 4 * torch.randn(B, 320, h, w, generator=gen)
+    ls = torch.randn(B, 320, h, w, generator=gen)
+    lm = torch.randn(B, 320, h, w, generator=gen)
+    yc, lsc, lmc = y.cuda(), ls.cuda(), lm.cuda()
+    enc = eng.compress(yc, lsc, lmc, with_likelihoods=True)
+    _, mu0, sc0 = SliceLoopOracle(lively_params).slice_params(0, ls, lm, [])
+    e_mu, e_sc = rel_err(enc["means"][:, :64].cpu(), mu0), rel_err(enc["scales"][:, :64].cpu(), sc0)
+    print(f"\n[{name}] T={B * h * w}: slice-0 rel_err mu {e_mu:.2e} scale {e_sc:.2e}, launches {eng.last_launches}")
+    assert e_mu < FP32_TOL and e_sc < FP32_TOL
+    assert mismatch_rate(enc["symbols"][0].cpu(), ogc.quantize(y[:, :64], "symbols", mu0)) <= 1e-3
+    assert bool(torch.isfinite(enc["y_hat"]).all())
+    assert bool(((enc["likelihoods"] >= 1e-9) & (enc["likelihoods"] <= 1)).all())
+    assert int(enc["indexes"].min()) >= 0 and int(enc["indexes"].max()) <= 63
+    sym = torch.stack([torch.round(yc[:, 64 * i:64 * i + 64] - enc["means"][:, 64 * i:64 * i + 64]).int() for i in range(5)])
+    assert torch.equal(sym, enc["symbols"])
+    dec = eng.decompress(lsc, lmc, lambda i, idx: enc["symbols"][i])
+    assert torch.equal(dec["indexes"], enc["indexes"]) and torch.equal(dec["y_hat"], enc["y_hat"])
