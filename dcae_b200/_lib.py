@@ -51,7 +51,8 @@ class Operand(C.Structure):
 class Epilogue(C.Structure):
     _fields_ = [("bias", c_f32p), ("addend", c_f32p), ("addend_ld", C.c_int64),
                 ("residual", c_f32p), ("residual_ld", C.c_int64), ("res_scale", c_f32p),
-                ("act", C.c_int32), ("act_cols", C.c_int32), ("out", c_f32p), ("out_ld", C.c_int64), ("out16", Planes)]
+                ("act", C.c_int32), ("act_cols", C.c_int32), ("out", c_f32p), ("out_ld", C.c_int64), ("out16", Planes),
+                ("out16_act", Planes), ("act2", C.c_int32)]
 
 
 class Weight(C.Structure):
@@ -104,6 +105,7 @@ SIGNATURES = {
     "dcae_launch_count": (_I64, []),
     "dcae_profile_start": (C.c_int, []),
     "dcae_profile_stop": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_I64)]),
+    "dcae_profile_dump": (C.c_int, [C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_I64)]),
     "dcae_gc_fused": (C.c_int, [C.POINTER(GcArgs), _P]),
     "dcae_gc_num_partials": (_I64, [_I64, _I64]),
     "dcae_reduce_partials": (C.c_int, [_P, _I64, _P, _P]),

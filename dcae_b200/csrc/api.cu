@@ -59,22 +59,30 @@ extern "C" int dcae_profile_start(void) {
   return DCAE_OK;
 }
 
-extern "C" int dcae_profile_stop(double* ms, double* work, int64_t* launches) {
+extern "C" int dcae_profile_dump(const char* path, double* ms, double* work, int64_t* launches) {
   DCAE_REQUIRE(ms && work && launches, "dcae_profile_stop: null output");
   g_prof_on = false;
   DCAE_CUDA(cudaDeviceSynchronize());
-  for (int f = 0; f < DCAE_PROF_FAMILIES; ++f) { ms[f] = 0; work[f] = 0; launches[f] = 0; }
+  FILE* f = path ? fopen(path, "w") : nullptr;
+  if (f) fprintf(f, "index,family,work,ms\n");
+  for (int k = 0; k < DCAE_PROF_FAMILIES; ++k) { ms[k] = 0; work[k] = 0; launches[k] = 0; }
+  int i = 0;
   for (const ProfRec& r : g_prof) {
     float t = 0.f;
     DCAE_CUDA(cudaEventElapsedTime(&t, r.a, r.b));
     ms[r.family] += t;
     work[r.family] += r.work;
     launches[r.family] += 1;
+    if (f) fprintf(f, "%d,%d,%.6g,%.6f\n", i, r.family, r.work, t);
+    ++i;
   }
+  if (f) fclose(f);
   g_prof.clear();
   g_prof_used = 0;
   return DCAE_OK;
 }
+
+extern "C" int dcae_profile_stop(double* ms, double* work, int64_t* launches) { return dcae_profile_dump(nullptr, ms, work, launches); }
 
 extern "C" int dcae_version(void) { return DCAE_B200_VERSION; }
 extern "C" const char* dcae_last_error(void) { return g_error; }
@@ -93,8 +101,8 @@ extern "C" int dcae_device_check(void) {
 
 static int check_gemm_args(const dcae_operand* a, const dcae_weight* w, const dcae_epilogue* e) {
   DCAE_REQUIRE(a && w && e, "dcae_op_gemm: null argument struct");
-  DCAE_REQUIRE((a->base || a->src16.hi) && (e->out || e->out16.hi), "dcae_op_gemm: null operand/output pointer");
-  DCAE_REQUIRE(planes_ok(&e->out16) && planes_ok(&a->src16), "dcae_op_gemm: fp16 planes must be 8-byte aligned with ld %% 4 == 0");
+  DCAE_REQUIRE((a->base || a->src16.hi) && (e->out || e->out16.hi || e->out16_act.hi), "dcae_op_gemm: null operand/output pointer");
+  DCAE_REQUIRE(planes_ok(&e->out16) && planes_ok(&e->out16_act) && planes_ok(&a->src16), "dcae_op_gemm: fp16 planes must be 8-byte aligned with ld %% 4 == 0");
   DCAE_REQUIRE(a->taps == 1 || a->taps == 9, "dcae_op_gemm: taps must be 1 or 9 (got %d)", a->taps);
   DCAE_REQUIRE(a->k0 > 0 && a->k0 % 32 == 0 && a->k1 >= 0 && a->k1 % 32 == 0 && a->col0 % 4 == 0 && a->col1 % 4 == 0,
                "dcae_op_gemm: operand segments must be multiples of 32 columns (k0=%d k1=%d)", a->k0, a->k1);
@@ -113,6 +121,7 @@ static int check_gemm_args(const dcae_operand* a, const dcae_weight* w, const dc
 
 extern "C" int dcae_op_gemm(const dcae_operand* a, const dcae_weight* w, const dcae_epilogue* e, int math, void* stream) {
   DCAE_TRY(check_gemm_args(a, w, e));
+  DCAE_REQUIRE(math == DCAE_MATH_F16X3 || !e->out16_act.hi, "dcae_op_gemm: out16_act is a DCAE_MATH_F16X3 feature");
   ProfileScope prof(DCAE_PROF_GEMM, 2.0 * a->B * a->h * a->w * (double)w->N * (double)w->K, stream);
   switch (math) {
     case DCAE_MATH_FP32_SIMT:
@@ -355,19 +364,22 @@ static int run_dca(dcae_slice_loop* p, int i, void* s) {
   DCAE_TRY(dcae_op_layernorm(p->x0.p, D, W.ln_scale_g, W.ln_scale_b, D, T, ln32, D, &lnp, s));
   {
     dcae_epilogue e = epi(W.msa_s_b, p->dc.p, 4 * D);
-    if (pm) e.out16 = pl(p->dcp, 0);                                    // fp32 for the GELU prologue, planes for proj
+    if (pm) {   // planes for proj + planes of GELU(.) = the prologue of dense layer 0; no fp32 copy at all
+      e.out = nullptr; e.out16 = pl(p->dcp, 0); e.out16_act = pl(p->gap); e.act2 = DCAE_ACT_GELU;
+    }
     DCAE_TRY(gemm(p, opnd2(p, p->ln, D, p->lnp, 0, D, 1), W.msa_s, e, s));
   }
   for (int j = 0; j < 3; ++j) {                                            // DenseBlock dcae.py:416-433
-    const dcae_planes gap = pm ? pl(p->gap) : none, t2p = pm ? pl(p->t2p) : none;
-    DCAE_TRY(dcae_op_gelu(p->dc.p + D * j, 4 * D, D, T, pm ? nullptr : p->ga.p, D, &gap, s));
+    const dcae_planes t2p = pm ? pl(p->t2p) : none;
+    if (!pm) DCAE_TRY(dcae_op_gelu(p->dc.p + D * j, 4 * D, D, T, p->ga.p, D, nullptr, s));
     DCAE_TRY(gemm(p, opnd2(p, p->ga, D, p->gap, 0, D, 1), W.dense_in[j], epi(W.dense_in_b[j], p->t1.p, D, DCAE_ACT_GELU), s));
     DCAE_TRY(dcae_op_dwconv3x3(p->t1.p, D, W.dense_dw[j], W.dense_dw_b[j], D, p->B, p->h, p->w, DCAE_ACT_GELU, nullptr, 0,
                                pm ? nullptr : p->t2.p, D, &t2p, s));
     dcae_epilogue e = epi(W.dense_out_b[j], p->dc.p + D * (j + 1), 4 * D);
     if (pm) {
+      e.out = nullptr;
       e.out16 = pl(p->dcp, D * (j + 1));
-      if (j == 2) e.out = nullptr;                                      // the last block only feeds proj
+      if (j < 2) { e.out16_act = pl(p->gap); e.act2 = DCAE_ACT_GELU; }   // GELU prologue of the next dense layer
     }
     DCAE_TRY(gemm(p, opnd2(p, p->t2, D, p->t2p, 0, D, 1), W.dense_out[j], e, s));
   }

@@ -37,17 +37,26 @@ __device__ __forceinline__ float gaussian_likelihood(float out, float mu, float 
 
 __device__ __forceinline__ int table_index(float s, const float* tbl, int n, float log_t0, float inv_step) {
   // idx = (n-1) - sum_{j<n-1} [s <= tbl[j]]  ==  #{ j < n-1 : tbl[j] < s }   (NaN -> n-1)
-  if (s != s) return n - 1;
-  float g = (__log2f(s) - log_t0) * inv_step;
-  int j = (int)fminf(fmaxf(g, 0.0f), (float)(n - 1));
-  while (j < n - 1 && tbl[j] < s) ++j;
-  while (j > 0 && !(tbl[j - 1] < s)) --j;
-  return j;
+  // Log-domain guess j0, one branch-free step up or down, then a check of the far neighbour; the search
+  // loop only runs for tables that are not log-uniform (exact for ANY sorted table).
+  const float g = (__log2f(s) - log_t0) * inv_step;
+  const int j0 = (int)fminf(fmaxf(g, 0.0f), (float)(n - 1));
+  const bool up = (j0 < n - 1) && (tbl[j0] < s);
+  const bool down = (j0 > 0) && !(tbl[max(j0 - 1, 0)] < s);     // never together with `up` (sorted table)
+  int j = j0 + (int)up - (int)down;
+  const float far = tbl[up ? min(j0 + 1, n - 1) : max(j0 - 2, 0)];
+  const bool bad = up ? (j < n - 1 && far < s) : (down && j > 0 && !(far < s));
+  if (bad) {
+    while (j < n - 1 && tbl[j] < s) ++j;
+    while (j > 0 && !(tbl[j - 1] < s)) --j;
+  }
+  return (s != s) ? n - 1 : j;
 }
 
 // One float4 group of every tensor lives at row * ld + col; `row, col` come from a shift when inner/4 is a
 // power of two (token-major slices: inner = 64), from a 32-bit divide otherwise.
-template <bool POW2>
+// MODE, LIK (likelihood wanted) and IDX (indexes wanted) are compile-time so the element loop is straight-line code.
+template <int MODE, bool LIK, bool IDX, bool POW2>
 __global__ void __launch_bounds__(GC_THREADS) gc_fused_kernel(const GcParams p) {
   __shared__ float tbl[GC_MAX_TABLE];
   __shared__ float red[GC_THREADS / 32];
@@ -56,13 +65,12 @@ __global__ void __launch_bounds__(GC_THREADS) gc_fused_kernel(const GcParams p) 
   for (int i = threadIdx.x; i < n; i += GC_THREADS) tbl[i] = a.scale_table ? a.scale_table[i] : 0.0f;
   __syncthreads();
   float log_t0 = 0.f, inv_step = 0.f;
-  if (a.idx != nullptr && n > 1) {
+  if (IDX && n > 1) {
     log_t0 = __log2f(tbl[0]);
     inv_step = (float)(n - 1) / (__log2f(tbl[n - 1]) - log_t0);
   }
-  const int mode = a.mode;
-  const bool want_lik = (a.lik != nullptr || a.log2_partials != nullptr) && mode != DCAE_GC_DECODE && a.y != nullptr;
-  const bool want_idx = a.idx != nullptr;
+  constexpr int mode = MODE;
+  constexpr bool want_lik = LIK, want_idx = IDX;
   const bool want_log2 = a.log2_partials != nullptr;
   const float scale_bound = a.scale_bound, lik_bound = a.lik_bound;
   float log2_acc = 0.f;
@@ -193,8 +201,27 @@ extern "C" int dcae_gc_fused(const dcae_gc_args* a, void* stream) {
   const bool pow2 = (p.inner4 & (p.inner4 - 1)) == 0;
   p.shift = 0;
   while (pow2 && (1u << p.shift) < p.inner4) ++p.shift;
-  if (pow2) gc_fused_kernel<true><<<(unsigned)blocks, GC_THREADS, 0, (cudaStream_t)stream>>>(p);
-  else gc_fused_kernel<false><<<(unsigned)blocks, GC_THREADS, 0, (cudaStream_t)stream>>>(p);
+  const bool lik = (a->lik != nullptr || a->log2_partials != nullptr) && a->mode != DCAE_GC_DECODE && a->y != nullptr;
+  const bool idx = a->idx != nullptr;
+  const unsigned nb = (unsigned)blocks;
+  cudaStream_t st = (cudaStream_t)stream;
+#define GC_LAUNCH(M, L, I)                                                        \
+  do {                                                                            \
+    if (pow2) gc_fused_kernel<M, L, I, true><<<nb, GC_THREADS, 0, st>>>(p);       \
+    else gc_fused_kernel<M, L, I, false><<<nb, GC_THREADS, 0, st>>>(p);           \
+  } while (0)
+#define GC_LAUNCH_MODE(M)                                                         \
+  do {                                                                            \
+    if (lik && idx) GC_LAUNCH(M, true, true);                                     \
+    else if (lik) GC_LAUNCH(M, true, false);                                      \
+    else if (idx) GC_LAUNCH(M, false, true);                                      \
+    else GC_LAUNCH(M, false, false);                                              \
+  } while (0)
+  if (a->mode == DCAE_GC_EVAL) GC_LAUNCH_MODE(DCAE_GC_EVAL);
+  else if (a->mode == DCAE_GC_NOISE) GC_LAUNCH_MODE(DCAE_GC_NOISE);
+  else GC_LAUNCH_MODE(DCAE_GC_DECODE);
+#undef GC_LAUNCH_MODE
+#undef GC_LAUNCH
   DCAE_LAUNCH_CHECK();
   return DCAE_OK;
 }

@@ -49,7 +49,7 @@ struct F16Params {
   int n_tiles_n, total_tiles, chunk_kb;
   float descale;
   int dbg_nostore;
-  int has_o32, has_o16;
+  int has_o32, has_o16, has_o16a;
   uint32_t stage_bytes, b_bytes;
 };
 
@@ -170,12 +170,42 @@ __global__ void __launch_bounds__(256) split_f16_weight_kernel(const float* __re
   }
 }
 
-template <int DUMMY>
-__global__ void __launch_bounds__(NTHREADS, 1)
-gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
-                  const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUtensorMap map_bl,
-                  const __grid_constant__ CUtensorMap map_o32, const __grid_constant__ CUtensorMap map_oh,
-                  const __grid_constant__ CUtensorMap map_ol, const F16Params p) {
+__device__ __forceinline__ void mma_f16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cl(uint32_t bar, uint32_t parity) {   // cluster-scope acquire (peer CTA wrote / signalled)
+  uint32_t done = 0, spins = 0;
+  uint64_t t0 = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (done) break;
+    if ((++spins & 1023u) == 0) {
+      uint64_t now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 2000000000ull) __trap();
+    }
+  }
+}
+
+// PAIR = false: one CTA per 128-token tile.  PAIR = true: thread-block pair (cta_group::2): the pair computes a
+// 256-token x BN tile with M = 256 MMAs issued by the leader; each CTA loads its own A planes and HALF of the weight
+// planes (BN/2 rows), TMA completion of both CTAs is credited to the leader's full barrier, tcgen05.commit is
+// multicast to both CTAs, the drain warps of both CTAs release the leader's TMEM-empty barrier.
+template <bool PAIR>
+__device__ __forceinline__ void gemm_f16x3_body(const CUtensorMap& map_ah, const CUtensorMap& map_al, const CUtensorMap& map_bh,
+                                                const CUtensorMap& map_bl, const CUtensorMap& map_o32, const CUtensorMap& map_oh,
+                                                const CUtensorMap& map_ol, const CUtensorMap& map_oha, const CUtensorMap& map_ola,
+                                                const F16Params& p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES];
   __shared__ __align__(8) uint64_t tmem_full_bar[2], tmem_empty_bar[2];
@@ -183,6 +213,10 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_const
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
+  const int unit = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;          // which persistent worker (CTA or pair)
+  const int nunits = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
@@ -191,7 +225,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_const
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(smem_u32(&tmem_full_bar[b]), 1);
-      mbar_init(smem_u32(&tmem_empty_bar[b]), NDRAIN);
+      mbar_init(smem_u32(&tmem_empty_bar[b]), PAIR ? 2 * NDRAIN : NDRAIN);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -202,11 +236,17 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_const
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_bl) : "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(p.tmem_cols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(p.tmem_cols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(p.tmem_cols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (PAIR) cluster_sync_all();     // the peer's barriers exist before anything signals them
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_base_slot;
 
@@ -217,7 +257,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_const
 
   auto tile_coords = [&](int t, int& b, int& y0, int& x0, int& n0) {
     const int nt = t % p.n_tiles_n;
-    int mt = t / p.n_tiles_n;
+    int mt = PAIR ? (t / p.n_tiles_n) * 2 + (int)rank : t / p.n_tiles_n;   // b may reach B for a pair's odd tail tile
     const int tile_x = mt % p.tiles_x; mt /= p.tiles_x;
     const int tile_y = mt % p.tiles_y;
     b = mt / p.tiles_y;
@@ -230,40 +270,51 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_const
       // ===================== TMA producer =====================
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      for (int t = unit; t < p.total_tiles; t += nunits) {
         int b, y0, x0, n0;
         tile_coords(t, b, y0, x0, n0);
         for (int kb = 0; kb < p.KB; ++kb) {
           mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
           const uint32_t sbase = smem0 + stage * p.stage_bytes;
           const uint32_t fb = smem_u32(&full_bar[stage]);
-          mbar_expect_tx(fb, 2 * A16_BYTES + 2 * p.b_bytes);
           const int tap = kb / p.cblk_per_tap;
           const int c = (kb - tap * p.cblk_per_tap) * BK16;
           int dy = 0, dx = 0;
           if (p.taps == 9) { dy = tap / 3 - 1; dx = tap % 3 - 1; }
-          tma_load_4d(sbase, &map_ah, fb, c, x0 + dx, y0 + dy, b);
-          tma_load_4d(sbase + off_al, &map_al, fb, c, x0 + dx, y0 + dy, b);
-          tma_load_2d(sbase + off_bh, &map_bh, fb, kb * BK16, n0);
-          tma_load_2d(sbase + off_bl, &map_bl, fb, kb * BK16, n0);
+          if (PAIR) {
+            if (leader) mbar_expect_tx(fb, 2 * (2 * A16_BYTES + 2 * p.b_bytes));      // bytes landing in BOTH CTAs
+            const int nrow = n0 + (int)rank * (p.BN >> 1);
+            tma_load_4d_2sm(sbase, &map_ah, fb, c, x0 + dx, y0 + dy, b);
+            tma_load_4d_2sm(sbase + off_al, &map_al, fb, c, x0 + dx, y0 + dy, b);
+            tma_load_2d_2sm(sbase + off_bh, &map_bh, fb, kb * BK16, nrow);
+            tma_load_2d_2sm(sbase + off_bl, &map_bl, fb, kb * BK16, nrow);
+          } else {
+            mbar_expect_tx(fb, 2 * A16_BYTES + 2 * p.b_bytes);
+            tma_load_4d(sbase, &map_ah, fb, c, x0 + dx, y0 + dy, b);
+            tma_load_4d(sbase + off_al, &map_al, fb, c, x0 + dx, y0 + dy, b);
+            tma_load_2d(sbase + off_bh, &map_bh, fb, kb * BK16, n0);
+            tma_load_2d(sbase + off_bl, &map_bl, fb, kb * BK16, n0);
+          }
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
-    } else if (warp == 1 && lane == 0) {
-      // ===================== MMA issuer =====================
+    } else if (warp == 1 && lane == 0 && leader) {
+      // ===================== MMA issuer (the leader CTA of a pair) =====================
       // D = F32 (bit 4), A = B = F16 (format 0), K-major, N >> 3 at bit 17, M >> 4 at bit 24
-      const uint32_t idesc = (1u << 4) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(((PAIR ? 2 : 1) * BM) >> 4) << 24);
       int stage = 0;
       uint32_t phase = 0, gchunk = 0;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      for (int t = unit; t < p.total_tiles; t += nunits) {
         for (int ck = 0; ck < n_chunks; ++ck, ++gchunk) {
           const uint32_t buf = gchunk & 1;
-          mbar_wait(smem_u32(&tmem_empty_bar[buf]), ((gchunk >> 1) & 1) ^ 1);
+          if (PAIR) mbar_wait_cl(smem_u32(&tmem_empty_bar[buf]), ((gchunk >> 1) & 1) ^ 1);
+          else mbar_wait(smem_u32(&tmem_empty_bar[buf]), ((gchunk >> 1) & 1) ^ 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t tmem_acc = tmem_base + buf * (uint32_t)p.BN;
           const int kb_end = min(p.KB, (ck + 1) * p.chunk_kb);
           for (int kb = ck * p.chunk_kb; kb < kb_end; ++kb) {
-            mbar_wait(smem_u32(&full_bar[stage]), phase);
+            if (PAIR) mbar_wait_cl(smem_u32(&full_bar[stage]), phase);
+            else mbar_wait(smem_u32(&full_bar[stage]), phase);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t sbase = smem0 + stage * p.stage_bytes;
             const uint32_t first = (kb == ck * p.chunk_kb) ? 0u : 1u;
@@ -272,14 +323,20 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_const
               const uint32_t koff = k * UMMA_K16 * 2;
               const uint64_t a_hi = make_smem_desc(sbase + koff), a_lo = make_smem_desc(sbase + off_al + koff);
               const uint64_t b_hi = make_smem_desc(sbase + off_bh + koff), b_lo = make_smem_desc(sbase + off_bl + koff);
-              mma_f16(tmem_acc, a_lo, b_hi, idesc, first | (uint32_t)(k != 0));
-              mma_f16(tmem_acc, a_hi, b_lo, idesc, 1);
-              mma_f16(tmem_acc, a_hi, b_hi, idesc, 1);
+              if (PAIR) {
+                mma_f16_2sm(tmem_acc, a_lo, b_hi, idesc, first | (uint32_t)(k != 0));
+                mma_f16_2sm(tmem_acc, a_hi, b_lo, idesc, 1);
+                mma_f16_2sm(tmem_acc, a_hi, b_hi, idesc, 1);
+              } else {
+                mma_f16(tmem_acc, a_lo, b_hi, idesc, first | (uint32_t)(k != 0));
+                mma_f16(tmem_acc, a_hi, b_lo, idesc, 1);
+                mma_f16(tmem_acc, a_hi, b_hi, idesc, 1);
+              }
             }
-            mma_commit(smem_u32(&empty_bar[stage]));
+            if (PAIR) mma_commit_2sm(smem_u32(&empty_bar[stage])); else mma_commit(smem_u32(&empty_bar[stage]));
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
-          mma_commit(smem_u32(&tmem_full_bar[buf]));
+          if (PAIR) mma_commit_2sm(smem_u32(&tmem_full_bar[buf])); else mma_commit(smem_u32(&tmem_full_bar[buf]));
         }
       }
     }
@@ -289,7 +346,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_const
     const int quarter = warp & 3;
     const int half = (warp - 4) >> 2;
     uint32_t gchunk = 0;
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+    for (int t = unit; t < p.total_tiles; t += nunits) {
       EpiTile et;
       tile_coords(t, et.b, et.y0, et.x0, et.n0);
       et.B = p.B; et.h = p.h; et.w = p.w; et.tw_shift = p.tw_shift; et.N = p.N; et.BN = p.BN; et.dbg = 0;
@@ -300,7 +357,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_const
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         drain_chunk(acc, tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * (uint32_t)p.BN, half, p.BN, ck == 0);
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        mbar_arrive(smem_u32(&tmem_empty_bar[buf]));
+        if (PAIR) mbar_arrive_cluster(smem_u32(&tmem_empty_bar[buf]), 0); else mbar_arrive(smem_u32(&tmem_empty_bar[buf]));
       }
 #pragma unroll
       for (int i = 0; i < EPI_BLOCKS * 32; ++i) acc[i] *= p.descale;     // exact: power of two
@@ -310,14 +367,14 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_const
       const int act_cols = (e.act_cols <= 0 || e.act_cols > p.N) ? p.N : e.act_cols;
       const int row = quarter * 32 + lane;
       const int yy = et.y0 + (row >> p.tw_shift), xx = et.x0 + (row & ((1 << p.tw_shift) - 1));
-      const bool row_ok = yy < p.h && xx < p.w;
+      const bool row_ok = yy < p.h && xx < p.w && et.b < p.B;
       const int64_t token = ((int64_t)et.b * p.h + yy) * p.w + xx;
       const uint32_t stg = stg_base + (uint32_t)half * STG_BYTES;
       const bool issuer = quarter == 0 && lane == 0;
 #pragma unroll
       for (int g = 0; g < EPI_BLOCKS; ++g) {
         const int blk = 2 * g + half;
-        if (blk * 32 < p.BN) {                                  // uniform over the group
+        if (blk * 32 < p.BN && et.n0 + blk * 32 < p.N) {        // uniform over the group; ragged last N tile
           const int nb0 = et.n0 + blk * 32;
           const int act = (nb0 < act_cols) ? e.act : DCAE_ACT_NONE;
           float* r = acc + g * 32;
@@ -347,6 +404,22 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_const
               asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
           }
+          if (p.has_o16a) {        // planes of act2(result): the next layer's GELU prologue, fused here
+            if (e.act2 == DCAE_ACT_GELU) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) r[j] = gelu_erf(r[j]);
+            }
+            if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            named_bar_sync(1 + half, 128);
+            stage_f16(r, row, stg);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            named_bar_sync(1 + half, 128);
+            if (issuer) {
+              tma_store_4d(&map_oha, stg + STG_HI, nb0, et.x0, et.y0, et.b);
+              tma_store_4d(&map_ola, stg + STG_LO, nb0, et.x0, et.y0, et.b);
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+          }
         }
       }
     }
@@ -355,9 +428,29 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_const
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (PAIR) cluster_sync_all();     // neither CTA may free TMEM / exit while the pair still uses its smem or TMEM
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
   }
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
+                  const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUtensorMap map_bl,
+                  const __grid_constant__ CUtensorMap map_o32, const __grid_constant__ CUtensorMap map_oh,
+                  const __grid_constant__ CUtensorMap map_ol, const __grid_constant__ CUtensorMap map_oha,
+                  const __grid_constant__ CUtensorMap map_ola, const F16Params p) {
+  gemm_f16x3_body<false>(map_ah, map_al, map_bh, map_bl, map_o32, map_oh, map_ol, map_oha, map_ola, p);
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
+gemm_f16x3_pair_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
+                       const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUtensorMap map_bl,
+                       const __grid_constant__ CUtensorMap map_o32, const __grid_constant__ CUtensorMap map_oh,
+                       const __grid_constant__ CUtensorMap map_ol, const __grid_constant__ CUtensorMap map_oha,
+                       const __grid_constant__ CUtensorMap map_ola, const F16Params p) {
+  gemm_f16x3_body<true>(map_ah, map_al, map_bh, map_bl, map_o32, map_oh, map_ol, map_oha, map_ola, p);
 }
 
 int encode_map_f16(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
@@ -404,7 +497,7 @@ int gemm_tcgen05_f16x3(const dcae_operand* a, const dcae_weight* w, const dcae_e
                            (reinterpret_cast<uintptr_t>(a->src16.hi) & 15u) == 0 && (reinterpret_cast<uintptr_t>(a->src16.lo) & 15u) == 0),
                "gemm(f16x3): src16 planes need one segment, 16-byte aligned planes and col0 / ld multiples of 8");
   DCAE_REQUIRE(e->act_cols <= 0 || e->act_cols >= w->N || e->act_cols % 32 == 0, "gemm(f16x3): act_cols must be a multiple of 32");
-  DCAE_REQUIRE(e->out || e->out16.hi, "gemm(f16x3): no output");
+  DCAE_REQUIRE(e->out || e->out16.hi || e->out16_act.hi, "gemm(f16x3): no output");
   if (T == 0) return DCAE_OK;
   __half* hi = direct ? static_cast<__half*>(a->src16.hi) + a->col0 : static_cast<__half*>(a->planes);
   __half* lo = direct ? static_cast<__half*>(a->src16.lo) + a->col0 : hi + T * Kp;
@@ -430,9 +523,9 @@ int gemm_tcgen05_f16x3(const dcae_operand* a, const dcae_weight* w, const dcae_e
   p.tiles_x = (a->w + p.TW - 1) / p.TW;
   p.tiles_y = (a->h + p.TH - 1) / p.TH;
   p.BN = 0;
-  if (const char* env = getenv("DCAE_TC_BN")) {
+  if (const char* env = getenv("DCAE_TC_BN")) {        // tuning override; BN need not divide N (ragged last tile)
     const int bn = atoi(env);
-    if (bn >= 32 && bn <= 256 && bn % 32 == 0 && w->N % bn == 0) p.BN = bn;
+    if (bn >= 32 && bn <= 256 && bn % 32 == 0) p.BN = bn;
   }
   if (p.BN == 0) {
     // 256 and 128 first: with the 32 KB of epilogue staging, 128 keeps three 64 KB stages in flight (N = 640: 128 beats
@@ -443,13 +536,20 @@ int gemm_tcgen05_f16x3(const dcae_operand* a, const dcae_weight* w, const dcae_e
   }
   DCAE_REQUIRE(p.BN > 0, "gemm(f16x3): N=%d must be a multiple of 32", w->N);
   p.tmem_cols = 2 * p.BN <= 64 ? 64 : 2 * p.BN <= 128 ? 128 : 2 * p.BN <= 256 ? 256 : 512;
-  p.n_tiles_n = w->N / p.BN;
-  p.total_tiles = p.n_tiles_n * p.tiles_x * p.tiles_y * a->B;
+  p.n_tiles_n = (w->N + p.BN - 1) / p.BN;      // a ragged last tile reads zero-filled weight rows and stores clipped
+  const int m_tiles = p.tiles_x * p.tiles_y * a->B;
+  // thread-block pairs (cta_group::2): DCAE_F16_PAIR = 1 / 0 forces it on / off, default = heuristic below
+  static const int pair_mode = [] { const char* v = getenv("DCAE_F16_PAIR"); return v ? atoi(v) : -1; }();
+  // A/B sweep (profiles/r01/gemm_f16_pair_ab.jsonl): pairs win where the mainloop is long or wide (cc1 +15 %, proj +15 %,
+  // fc1 +11 %) and are neutral or slightly worse on the short 640x640 and the small-N conv layers.
+  const bool pair_heur = (int64_t)a->taps * Kp >= 2048 || w->N >= 2048;
+  const bool pair = m_tiles >= 2 && p.BN % 32 == 0 && (pair_mode == 1 || (pair_mode == -1 && pair_heur));
+  p.total_tiles = p.n_tiles_n * (pair ? (m_tiles + 1) / 2 : m_tiles);
   p.chunk_kb = CHUNK_MMAS / 12;
   if (const char* env = getenv("DCAE_TC_CHUNK")) { const int v = atoi(env); if (v >= 1) p.chunk_kb = v; }
   p.descale = w->descale;
   p.dbg_nostore = getenv("DCAE_TC_NOSTORE") != nullptr;
-  p.b_bytes = (uint32_t)p.BN * BK16 * 2;
+  p.b_bytes = (uint32_t)(pair ? p.BN / 2 : p.BN) * BK16 * 2;     // a pair's CTA holds half of the weight rows
   p.stage_bytes = 2 * A16_BYTES + 2 * p.b_bytes;
   p.stages = (int)((SMEM_LIMIT - 2048 - 2 * STG_BYTES) / p.stage_bytes);
   if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
@@ -459,8 +559,10 @@ int gemm_tcgen05_f16x3(const dcae_operand* a, const dcae_weight* w, const dcae_e
   const size_t smem = (size_t)p.stages * p.stage_bytes + 2 * STG_BYTES + 1024;
   p.has_o32 = e->out != nullptr;
   p.has_o16 = e->out16.hi != nullptr;
+  p.has_o16a = e->out16_act.hi != nullptr;
+  DCAE_REQUIRE(!p.has_o16a || e->act2 == DCAE_ACT_NONE || e->act2 == DCAE_ACT_GELU, "gemm(f16x3): act2 must be NONE or GELU");
 
-  CUtensorMap map_ah, map_al, map_bh, map_bl, map_o32, map_oh, map_ol;
+  CUtensorMap map_ah, map_al, map_bh, map_bl, map_o32, map_oh, map_ol, map_oha, map_ola;
   {
     // output boxes {32 columns, TW, TH, 1}; dims[0] = N clips a ragged last block, (w, h) clip ragged token tiles
     cuuint32_t box[4] = {32, (cuuint32_t)p.TW, (cuuint32_t)p.TH, 1};
@@ -476,6 +578,12 @@ int gemm_tcgen05_f16x3(const dcae_operand* a, const dcae_weight* w, const dcae_e
       DCAE_TRY(encode_map_f16(&map_oh, e->out16.hi, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B));
       DCAE_TRY(encode_map_f16(&map_ol, e->out16.lo, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B));
     }
+    if (p.has_o16a) {
+      DCAE_REQUIRE(aligned16(e->out16_act.hi) && aligned16(e->out16_act.lo) && e->out16_act.ld % 8 == 0, "gemm(f16x3): out16_act planes must be 16-byte aligned with ld %% 8 == 0");
+      cuuint64_t str[3] = {(cuuint64_t)e->out16_act.ld * 2, (cuuint64_t)e->out16_act.ld * 2 * a->w, (cuuint64_t)e->out16_act.ld * 2 * a->w * a->h};
+      DCAE_TRY(encode_map_f16(&map_oha, e->out16_act.hi, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B));
+      DCAE_TRY(encode_map_f16(&map_ola, e->out16_act.lo, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B));
+    }
   }
   {
     // dims[0] = Kp: a window that is not a multiple of 64 wide over-reads into the next columns (zero weights there)
@@ -488,20 +596,29 @@ int gemm_tcgen05_f16x3(const dcae_operand* a, const dcae_weight* w, const dcae_e
   {
     cuuint64_t dims[2] = {(cuuint64_t)w->K16, (cuuint64_t)w->N};
     cuuint64_t str[1] = {(cuuint64_t)w->K16 * 2};
-    cuuint32_t box[2] = {BK16, (cuuint32_t)p.BN};
+    cuuint32_t box[2] = {BK16, (cuuint32_t)(pair ? p.BN / 2 : p.BN)};
     DCAE_TRY(encode_map_f16(&map_bh, w->w16_hi, 2, dims, str, box));
     DCAE_TRY(encode_map_f16(&map_bl, w->w16_lo, 2, dims, str, box));
   }
   if (!p.has_o32) map_o32 = map_bh;       // unused by the kernel
   if (!p.has_o16) { map_oh = map_bh; map_ol = map_bh; }
+  if (!p.has_o16a) { map_oha = map_bh; map_ola = map_bh; }
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(attr_once, [] {
-    attr_err = cudaFuncSetAttribute(gemm_f16x3_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT - 1024);
+    attr_err = cudaFuncSetAttribute(gemm_f16x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT - 1024);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(gemm_f16x3_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT - 1024);
   });
   DCAE_CUDA(attr_err);
-  const int ctas = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-  gemm_f16x3_kernel<0><<<ctas, NTHREADS, smem, s>>>(map_ah, map_al, map_bh, map_bl, map_o32, map_oh, map_ol, p);
+  if (pair) {
+    const int max_pairs = num_sms() / 2;
+    const int pairs = p.total_tiles < max_pairs ? p.total_tiles : max_pairs;
+    gemm_f16x3_pair_kernel<<<2 * pairs, NTHREADS, smem, s>>>(map_ah, map_al, map_bh, map_bl, map_o32, map_oh, map_ol, map_oha, map_ola, p);
+  } else {
+    const int ctas = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+    gemm_f16x3_kernel<<<ctas, NTHREADS, smem, s>>>(map_ah, map_al, map_bh, map_bl, map_o32, map_oh, map_ol, map_oha, map_ola, p);
+  }
   DCAE_LAUNCH_CHECK();
   return DCAE_OK;
 }

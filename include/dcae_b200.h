@@ -141,6 +141,9 @@ typedef struct {
   int32_t act; int32_t act_cols;
   float* out; int64_t out_ld;          /* may be NULL when out16 is given */
   dcae_planes out16;                   /* tcgen05 paths only: also (or only) write the result as fp16 planes */
+  dcae_planes out16_act;               /* DCAE_MATH_F16X3 only: planes of act2(result), e.g. the GELU prologue of the
+                                          next dense layer (dcae.py:421-423) produced by this layer's epilogue */
+  int32_t act2;
 } dcae_epilogue;
 
 /* Dense weight [N, K] row-major (K contiguous; nn.Linear layout).  `w` is the fp32 weight;
@@ -291,6 +294,8 @@ int64_t dcae_launch_count(void);
 enum { DCAE_PROF_GEMM = 0, DCAE_PROF_ATTN = 1, DCAE_PROF_GC = 2, DCAE_PROF_OTHER = 3, DCAE_PROF_FAMILIES = 4 };
 int dcae_profile_start(void);
 int dcae_profile_stop(double* ms, double* work, int64_t* launches);
+/* Like dcae_profile_stop, but also writes one CSV line per recorded op (index, family, work, ms) to `path`. */
+int dcae_profile_dump(const char* path, double* ms, double* work, int64_t* launches);
 
 #ifdef __cplusplus
 }

@@ -17,7 +17,7 @@ def split_weight(w2d: torch.Tensor):
 
 
 def gemm(buf, B, h, w, col0, k0, weight2d, math="fp32", taps=1, col1=0, k1=0, bias=None, addend=None,
-         residual=None, res_scale=None, act=0, act_cols=0, out=None, out_col=0, src16=None, out16=None):
+         residual=None, res_scale=None, act=0, act_cols=0, out=None, out_col=0, src16=None, out16=None, out16_act=None, act2=0):
     """src16 = (hi, lo) fp16 planes [T, ld] to read the operand window from (f16x3); out16 = (hi, lo) planes to
     also write the result to."""
     """buf: token-major [T, ld] CUDA fp32.  weight2d: [N, K].  Returns out [T, N] (or writes into `out`)."""
@@ -49,6 +49,9 @@ def gemm(buf, B, h, w, col0, k0, weight2d, math="fp32", taps=1, col1=0, k1=0, bi
     e.out, e.out_ld = out.data_ptr() + 4 * out_col, out.stride(0)
     if out16 is not None:
         e.out16 = _lib.Planes(out16[0].data_ptr(), out16[1].data_ptr(), out16[0].stride(0))
+    if out16_act is not None:
+        e.out16_act = _lib.Planes(out16_act[0].data_ptr(), out16_act[1].data_ptr(), out16_act[0].stride(0))
+        e.act2 = act2
     _lib.check(lib.dcae_op_gemm(a, W, e, _lib.MATH[math], _s(buf.device)), "dcae_op_gemm")
     return out
 

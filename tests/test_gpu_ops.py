@@ -202,3 +202,20 @@ def test_f16x3_gemm_reads_and_writes_planes_directly():
     assert rel_err(got.cpu(), want) < 1e-5
     assert _planes_close(o_hi[:, :N], o_lo[:, :N], got)
     assert float(o_hi[:, N:].abs().max()) == 0.0
+
+
+def test_f16x3_gemm_second_planes_output_carries_the_next_gelu():
+    """dcae.py:421-423: GELU is the first op of every dense layer; the producing GEMM writes planes of GELU(out)."""
+    B, h, w, C, N = 2, 7, 9, 640, 160
+    T = B * h * w
+    x = torch.randn(T, C, generator=g(53))
+    wt = torch.randn(N, C, generator=g(54)) / C ** 0.5
+    b = torch.randn(N, generator=g(55))
+    want = x @ wt.t() + b
+    o_hi, o_lo, a_hi, a_lo = (torch.zeros(T, 192, dtype=torch.float16, device="cuda") for _ in range(4))
+    got = K.gemm(x.cuda(), B, h, w, 0, C, wt.cuda(), math="f16x3", bias=b.cuda(), out16=(o_hi, o_lo),
+                 out16_act=(a_hi, a_lo), act2=1)
+    assert rel_err(got.cpu(), want) < 1e-5
+    assert _planes_close(o_hi[:, :N], o_lo[:, :N], got)
+    assert _planes_close(a_hi[:, :N], a_lo[:, :N], torch.nn.functional.gelu(got))
+    assert float(a_hi[:, N:].abs().max()) == 0.0

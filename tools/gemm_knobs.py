@@ -48,6 +48,11 @@ for math in (sys.argv[2:] or ("tf32x3", "tf32")):
     for Kd, N, taps, bn in [(640, 640, 1, 160), (640, 640, 1, 128), (2560, 640, 1, 160), (640, 2560, 1, 256), (8640, 672, 9, 224),
                             (2016, 128, 9, 128), (1152, 64, 9, 64), (640, 320, 1, 160)]:
         bench(Kd, N, math, taps, bn=bn)
+        if len(sys.argv) > 1 and sys.argv[1] == "ragged":
+            if N == 640:
+                os.environ["DCAE_F16_PAIR"] = "1"; bench(Kd, N, math, taps, bn=256); bench(Kd, N, math, taps, bn=160); bench(Kd, N, math, taps, bn=128)
+                os.environ["DCAE_F16_PAIR"] = "0"; bench(Kd, N, math, taps, bn=256); bench(Kd, N, math, taps, bn=128)
+            continue
         if len(sys.argv) > 1 and sys.argv[1] == "f16":
             bench(Kd, N, math, taps, bn=bn, nostore=1)
             for st in (2, 3):
