@@ -20,6 +20,7 @@
 
 #include "common.cuh"
 #include "tc_common.cuh"
+#include <vector>
 
 namespace dcae {
 
@@ -51,7 +52,9 @@ struct F16Params {
   int dbg_nostore;
   int has_o32, has_o16, has_o16a;
   uint32_t stage_bytes, b_bytes;
+  unsigned long long* dbg;   // DCAE_F16_DBG=1: per-CTA role counters (16 u64 each), see dump in the host wrapper
 };
+
 
 __device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -74,29 +77,49 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 // its 32-column blocks goes bias / addend / activation / residual in registers, then into the group's staging
 // buffer in the swizzled box layout (conflict-free st.shared.v4), and one thread issues the bulk store(s):
 // full 128-byte lines, ragged tiles clipped by the hardware, no per-thread global address arithmetic.
-template <int ACT>
-__device__ __forceinline__ void finalize_block(float* r, const dcae_epilogue& e, bool row_ok, int64_t token, int n0) {
+// One instance, run-time activation: the three branches are disjoint loops (nothing for ptxas to if-convert into
+// "evaluate erf AND tanh"), and the epilogue must stay SMALL -- see the note at the block loop.
+__device__ __forceinline__ void finalize_block(float* r, const dcae_epilogue& e, int act, bool row_ok, int64_t token, int n0,
+                                               float bias_lane, float rs_lane) {
+  // bias / res_scale of column n0 + lane were loaded by this lane before the accumulator wait (a global load issued
+  // here would pay the loaded L2 latency on the critical path of every block); broadcast by shuffle.
 #pragma unroll
-  for (int j = 0; j < 32; j += 4) {
-    const int n = n0 + j;
-    float4 x = make_float4(r[j], r[j + 1], r[j + 2], r[j + 3]);
-    if (e.bias) {
-      const float4 bv = __ldg(reinterpret_cast<const float4*>(e.bias + n));
-      x.x += bv.x; x.y += bv.y; x.z += bv.z; x.w += bv.w;
+  for (int j = 0; j < 32; ++j) r[j] += __shfl_sync(0xffffffffu, bias_lane, j);
+  if (e.addend && row_ok) {
+    const float4* ap = reinterpret_cast<const float4*>(e.addend + token * e.addend_ld + n0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 ad = __ldg(ap + j);
+      r[4 * j] += ad.x; r[4 * j + 1] += ad.y; r[4 * j + 2] += ad.z; r[4 * j + 3] += ad.w;
     }
-    if (e.addend && row_ok) {
-      const float4 ad = __ldg(reinterpret_cast<const float4*>(e.addend + token * e.addend_ld + n));
-      x.x += ad.x; x.y += ad.y; x.z += ad.z; x.w += ad.w;
+  }
+  if (act == DCAE_ACT_GELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) r[j] = gelu_fast(r[j]);
+  } else if (act == DCAE_ACT_HALF_TANH) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) r[j] = 0.5f * tanhf(r[j]);
+  }
+  if (e.residual) {
+    const float4* rp = reinterpret_cast<const float4*>(e.residual + token * e.residual_ld + n0);
+#pragma unroll
+    for (int hq = 0; hq < 2; ++hq) {                 // two halves: 16 registers of loads in flight, not 32
+      float4 rv[4];
+      if (row_ok) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) rv[j] = __ldg(rp + 4 * hq + j);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = 16 * hq + 4 * j;
+        const float s0 = __shfl_sync(0xffffffffu, rs_lane, c), s1 = __shfl_sync(0xffffffffu, rs_lane, c + 1);
+        const float s2 = __shfl_sync(0xffffffffu, rs_lane, c + 2), s3 = __shfl_sync(0xffffffffu, rs_lane, c + 3);
+        if (row_ok) {
+          r[c] = fmaf(rv[j].x, s0, r[c]); r[c + 1] = fmaf(rv[j].y, s1, r[c + 1]);
+          r[c + 2] = fmaf(rv[j].z, s2, r[c + 2]); r[c + 3] = fmaf(rv[j].w, s3, r[c + 3]);
+        }
+      }
     }
-    if (ACT == DCAE_ACT_GELU) { x.x = gelu_erf(x.x); x.y = gelu_erf(x.y); x.z = gelu_erf(x.z); x.w = gelu_erf(x.w); }
-    if (ACT == DCAE_ACT_HALF_TANH) { x.x = 0.5f * tanhf(x.x); x.y = 0.5f * tanhf(x.y); x.z = 0.5f * tanhf(x.z); x.w = 0.5f * tanhf(x.w); }
-    if (e.residual && row_ok) {
-      const float4 rv = __ldg(reinterpret_cast<const float4*>(e.residual + token * e.residual_ld + n));
-      float4 rs = make_float4(1.f, 1.f, 1.f, 1.f);
-      if (e.res_scale) rs = __ldg(reinterpret_cast<const float4*>(e.res_scale + n));
-      x.x = fmaf(rv.x, rs.x, x.x); x.y = fmaf(rv.y, rs.y, x.y); x.z = fmaf(rv.z, rs.z, x.z); x.w = fmaf(rv.w, rs.w, x.w);
-    }
-    r[j] = x.x; r[j + 1] = x.y; r[j + 2] = x.z; r[j + 3] = x.w;
   }
 }
 // row `row` of a [128 x 32] fp32 block into the SWIZZLE_128B box layout (128-byte rows)
@@ -197,11 +220,19 @@ __device__ __forceinline__ void mbar_wait_cl(uint32_t bar, uint32_t parity) {   
   }
 }
 
+// debug-only: wait and report the cycles spent blocked (0 when the barrier was already complete)
+__device__ __forceinline__ long long timed_wait(uint32_t bar, uint32_t parity, bool cl) {
+  const long long t0 = clock64();
+  if (cl) mbar_wait_cl(bar, parity); else mbar_wait(bar, parity);
+  return clock64() - t0;
+}
+
 // PAIR = false: one CTA per 128-token tile.  PAIR = true: thread-block pair (cta_group::2): the pair computes a
 // 256-token x BN tile with M = 256 MMAs issued by the leader; each CTA loads its own A planes and HALF of the weight
 // planes (BN/2 rows), TMA completion of both CTAs is credited to the leader's full barrier, tcgen05.commit is
 // multicast to both CTAs, the drain warps of both CTAs release the leader's TMEM-empty barrier.
-template <bool PAIR>
+// NB = 32-column blocks per drain group and tile: 2 for BN <= 128 (64 accumulator registers), 4 up to BN = 256
+template <bool PAIR, bool DBG, int NB>
 __device__ __forceinline__ void gemm_f16x3_body(const CUtensorMap& map_ah, const CUtensorMap& map_al, const CUtensorMap& map_bh,
                                                 const CUtensorMap& map_bl, const CUtensorMap& map_o32, const CUtensorMap& map_oh,
                                                 const CUtensorMap& map_ol, const CUtensorMap& map_oha, const CUtensorMap& map_ola,
@@ -270,11 +301,13 @@ __device__ __forceinline__ void gemm_f16x3_body(const CUtensorMap& map_ah, const
       // ===================== TMA producer =====================
       int stage = 0;
       uint32_t phase = 0;
+      long long w_empty = 0;
       for (int t = unit; t < p.total_tiles; t += nunits) {
         int b, y0, x0, n0;
         tile_coords(t, b, y0, x0, n0);
         for (int kb = 0; kb < p.KB; ++kb) {
-          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+          if (DBG) w_empty += timed_wait(smem_u32(&empty_bar[stage]), phase ^ 1, false);
+          else mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
           const uint32_t sbase = smem0 + stage * p.stage_bytes;
           const uint32_t fb = smem_u32(&full_bar[stage]);
           const int tap = kb / p.cblk_per_tap;
@@ -298,22 +331,28 @@ __device__ __forceinline__ void gemm_f16x3_body(const CUtensorMap& map_ah, const
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
+      if (DBG) p.dbg[blockIdx.x * 16 + 0] = (unsigned long long)w_empty;
     } else if (warp == 1 && lane == 0 && leader) {
       // ===================== MMA issuer (the leader CTA of a pair) =====================
       // D = F32 (bit 4), A = B = F16 (format 0), K-major, N >> 3 at bit 17, M >> 4 at bit 24
       const uint32_t idesc = (1u << 4) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(((PAIR ? 2 : 1) * BM) >> 4) << 24);
       int stage = 0;
       uint32_t phase = 0, gchunk = 0;
+      long long w_full = 0, w_tmem = 0, n_kb = 0, n_tiles = 0;
+      const long long t_start = clock64();
       for (int t = unit; t < p.total_tiles; t += nunits) {
+        ++n_tiles;
         for (int ck = 0; ck < n_chunks; ++ck, ++gchunk) {
           const uint32_t buf = gchunk & 1;
-          if (PAIR) mbar_wait_cl(smem_u32(&tmem_empty_bar[buf]), ((gchunk >> 1) & 1) ^ 1);
+          if (DBG) w_tmem += timed_wait(smem_u32(&tmem_empty_bar[buf]), ((gchunk >> 1) & 1) ^ 1, PAIR);
+          else if (PAIR) mbar_wait_cl(smem_u32(&tmem_empty_bar[buf]), ((gchunk >> 1) & 1) ^ 1);
           else mbar_wait(smem_u32(&tmem_empty_bar[buf]), ((gchunk >> 1) & 1) ^ 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t tmem_acc = tmem_base + buf * (uint32_t)p.BN;
           const int kb_end = min(p.KB, (ck + 1) * p.chunk_kb);
           for (int kb = ck * p.chunk_kb; kb < kb_end; ++kb) {
-            if (PAIR) mbar_wait_cl(smem_u32(&full_bar[stage]), phase);
+            if (DBG) { w_full += timed_wait(smem_u32(&full_bar[stage]), phase, PAIR); ++n_kb; }
+            else if (PAIR) mbar_wait_cl(smem_u32(&full_bar[stage]), phase);
             else mbar_wait(smem_u32(&full_bar[stage]), phase);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t sbase = smem0 + stage * p.stage_bytes;
@@ -339,6 +378,11 @@ __device__ __forceinline__ void gemm_f16x3_body(const CUtensorMap& map_ah, const
           if (PAIR) mma_commit_2sm(smem_u32(&tmem_full_bar[buf])); else mma_commit(smem_u32(&tmem_full_bar[buf]));
         }
       }
+      if (DBG) {
+        unsigned long long* d = p.dbg + blockIdx.x * 16;
+        d[1] = (unsigned long long)w_full; d[2] = (unsigned long long)w_tmem; d[3] = (unsigned long long)(clock64() - t_start);
+        d[4] = (unsigned long long)n_kb; d[5] = (unsigned long long)n_tiles;
+      }
     }
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_DRAIN));
@@ -346,23 +390,39 @@ __device__ __forceinline__ void gemm_f16x3_body(const CUtensorMap& map_ah, const
     const int quarter = warp & 3;
     const int half = (warp - 4) >> 2;
     uint32_t gchunk = 0;
+    long long w_acc = 0, t_drain = 0, t_epi = 0, t_fin = 0, t_rd = 0, t_st = 0, t_b2 = 0;
+    const long long t_start = clock64();
     for (int t = unit; t < p.total_tiles; t += nunits) {
       EpiTile et;
       tile_coords(t, et.b, et.y0, et.x0, et.n0);
       et.B = p.B; et.h = p.h; et.w = p.w; et.tw_shift = p.tw_shift; et.N = p.N; et.BN = p.BN; et.dbg = 0;
-      float acc[EPI_BLOCKS * 32];
+      float acc[NB * 32];
+      float bias_l[NB], rs_l[NB];          // column (block g, lane) of bias / res_scale, see finalize_block
+#pragma unroll
+      for (int g = 0; g < NB; ++g) {
+        const int n = et.n0 + (2 * g + half) * 32 + lane;
+        const bool ok = (2 * g + half) * 32 < p.BN && n < p.N;
+        bias_l[g] = (p.e.bias && ok) ? __ldg(p.e.bias + n) : 0.f;
+        rs_l[g] = (p.e.residual && p.e.res_scale && ok) ? __ldg(p.e.res_scale + n) : 1.f;
+      }
       for (int ck = 0; ck < n_chunks; ++ck, ++gchunk) {
         const uint32_t buf = gchunk & 1;
-        mbar_wait(smem_u32(&tmem_full_bar[buf]), (gchunk >> 1) & 1);
+        if (DBG) w_acc += timed_wait(smem_u32(&tmem_full_bar[buf]), (gchunk >> 1) & 1, false);
+        else mbar_wait(smem_u32(&tmem_full_bar[buf]), (gchunk >> 1) & 1);
+        const long long td0 = DBG ? clock64() : 0;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        drain_chunk(acc, tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * (uint32_t)p.BN, half, p.BN, ck == 0);
+        drain_chunk<NB>(acc, tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * (uint32_t)p.BN, half, p.BN, ck == 0);
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         if (PAIR) mbar_arrive_cluster(smem_u32(&tmem_empty_bar[buf]), 0); else mbar_arrive(smem_u32(&tmem_empty_bar[buf]));
+        if (DBG) t_drain += clock64() - td0;
       }
-#pragma unroll
-      for (int i = 0; i < EPI_BLOCKS * 32; ++i) acc[i] *= p.descale;     // exact: power of two
+      const long long te0 = DBG ? clock64() : 0;
       if (p.dbg_nostore) continue;
       // ---- epilogue: registers -> swizzled staging -> TMA tensor store, one 32-column block at a time ----
+      // A ROLLED loop with one copy of the body.  Fully unrolled (4 blocks x 3 activations x 3 outputs) the kernel was
+      // 350 KB of straight-line SASS that each warp runs once per tile: instruction fetch, not arithmetic, set the
+      // epilogue time (every phase measured 10-20x its instruction count; DCAE_F16_DBG counters).  The accumulator
+      // registers need static indices, so the block's 32 values are selected into r[] first.
       const dcae_epilogue& e = p.e;
       const int act_cols = (e.act_cols <= 0 || e.act_cols > p.N) ? p.N : e.act_cols;
       const int row = quarter * 32 + lane;
@@ -371,57 +431,62 @@ __device__ __forceinline__ void gemm_f16x3_body(const CUtensorMap& map_ah, const
       const int64_t token = ((int64_t)et.b * p.h + yy) * p.w + xx;
       const uint32_t stg = stg_base + (uint32_t)half * STG_BYTES;
       const bool issuer = quarter == 0 && lane == 0;
-#pragma unroll
-      for (int g = 0; g < EPI_BLOCKS; ++g) {
+#pragma unroll 1
+      for (int g = 0; g < NB; ++g) {
         const int blk = 2 * g + half;
-        if (blk * 32 < p.BN && et.n0 + blk * 32 < p.N) {        // uniform over the group; ragged last N tile
-          const int nb0 = et.n0 + blk * 32;
-          const int act = (nb0 < act_cols) ? e.act : DCAE_ACT_NONE;
-          float* r = acc + g * 32;
-          if (act == DCAE_ACT_GELU) finalize_block<DCAE_ACT_GELU>(r, e, row_ok, token, nb0);
-          else if (act == DCAE_ACT_HALF_TANH) finalize_block<DCAE_ACT_HALF_TANH>(r, e, row_ok, token, nb0);
-          else finalize_block<DCAE_ACT_NONE>(r, e, row_ok, token, nb0);
-          if (p.has_o32) {
-            if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the previous store has read the buffer
-            named_bar_sync(1 + half, 128);
-            stage_f32(r, row, stg);
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            named_bar_sync(1 + half, 128);
-            if (issuer) {
-              tma_store_4d(&map_o32, stg + STG_O32, nb0, et.x0, et.y0, et.b);
-              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            }
-          }
-          if (p.has_o16) {
-            if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-            named_bar_sync(1 + half, 128);
-            stage_f16(r, row, stg);
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            named_bar_sync(1 + half, 128);
-            if (issuer) {
-              tma_store_4d(&map_oh, stg + STG_HI, nb0, et.x0, et.y0, et.b);
-              tma_store_4d(&map_ol, stg + STG_LO, nb0, et.x0, et.y0, et.b);
-              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            }
-          }
-          if (p.has_o16a) {        // planes of act2(result): the next layer's GELU prologue, fused here
-            if (e.act2 == DCAE_ACT_GELU) {
+        const int nb0 = et.n0 + blk * 32;
+        if (blk * 32 >= p.BN || nb0 >= p.N) break;              // uniform over the group; ragged last N tile
+        const int act = (nb0 < act_cols) ? e.act : DCAE_ACT_NONE;
+        // the block to process is always acc[0..32) / bias_l[0]: processed in place, then the queue shifts down
+        // (static register indices in a rolled loop without a second copy of the block)
+        float* r = acc;
+        const float bias_lane = bias_l[0], rs_lane = rs_l[0];
 #pragma unroll
-              for (int j = 0; j < 32; ++j) r[j] = gelu_erf(r[j]);
-            }
-            if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-            named_bar_sync(1 + half, 128);
-            stage_f16(r, row, stg);
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            named_bar_sync(1 + half, 128);
-            if (issuer) {
-              tma_store_4d(&map_oha, stg + STG_HI, nb0, et.x0, et.y0, et.b);
-              tma_store_4d(&map_ola, stg + STG_LO, nb0, et.x0, et.y0, et.b);
-              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            }
+        for (int j = 0; j < 32; ++j) r[j] *= p.descale;          // exact: power of two
+        const long long tf0 = DBG ? clock64() : 0;
+        finalize_block(r, e, act, row_ok, token, nb0, bias_lane, rs_lane);
+        if (DBG) { r[0] += 0.f * __int_as_float(__float_as_int(r[31]) & 0); t_fin += clock64() - tf0; }
+        // output o: 0 = fp32, 1 = fp16 planes, 2 = fp16 planes of act2(result), the next layer's GELU prologue.
+        // One staging round each: wait until the previous store has read the buffer, stage, make the writes visible
+        // to the async proxy, and let one thread issue the bulk store(s).
+#pragma unroll 1
+        for (int o = 0; o < 3; ++o) {
+          if (!(o == 0 ? p.has_o32 : o == 1 ? p.has_o16 : p.has_o16a)) continue;
+          if (o == 2 && e.act2 == DCAE_ACT_GELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) r[j] = gelu_fast(r[j]);
           }
+          long long c0 = DBG ? clock64() : 0, c1;
+          if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          if (DBG) { c1 = clock64(); t_rd += c1 - c0; c0 = c1; }
+          named_bar_sync(1 + half, 128);
+          if (o == 0) stage_f32(r, row, stg); else stage_f16(r, row, stg);
+          if (DBG) { c1 = clock64(); t_st += c1 - c0; c0 = c1; }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          named_bar_sync(1 + half, 128);
+          if (issuer) {
+            if (o == 0) {
+              tma_store_4d(&map_o32, stg + STG_O32, nb0, et.x0, et.y0, et.b);
+            } else {
+              tma_store_4d(o == 1 ? &map_oh : &map_oha, stg + STG_HI, nb0, et.x0, et.y0, et.b);
+              tma_store_4d(o == 1 ? &map_ol : &map_ola, stg + STG_LO, nb0, et.x0, et.y0, et.b);
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+          if (DBG) { c1 = clock64(); t_b2 += c1 - c0; }
         }
+#pragma unroll
+        for (int i = 0; i < (NB - 1) * 32; ++i) acc[i] = acc[i + 32];
+#pragma unroll
+        for (int q = 0; q < NB - 1; ++q) { bias_l[q] = bias_l[q + 1]; rs_l[q] = rs_l[q + 1]; }
       }
+      if (DBG) t_epi += clock64() - te0;
+    }
+    if (DBG && warp == 4 && lane == 0) {
+      unsigned long long* d = p.dbg + blockIdx.x * 16;
+      d[6] = (unsigned long long)w_acc; d[7] = (unsigned long long)t_drain; d[8] = (unsigned long long)t_epi;
+      d[9] = (unsigned long long)(clock64() - t_start); d[10] = (unsigned long long)t_fin; d[11] = (unsigned long long)t_rd;
+      d[13] = (unsigned long long)t_st; d[15] = (unsigned long long)t_b2;
     }
     if (quarter == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all stores landed before exit
   }
@@ -435,22 +500,24 @@ __device__ __forceinline__ void gemm_f16x3_body(const CUtensorMap& map_ah, const
   }
 }
 
+template <bool DBG, int NB>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
                   const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUtensorMap map_bl,
                   const __grid_constant__ CUtensorMap map_o32, const __grid_constant__ CUtensorMap map_oh,
                   const __grid_constant__ CUtensorMap map_ol, const __grid_constant__ CUtensorMap map_oha,
                   const __grid_constant__ CUtensorMap map_ola, const F16Params p) {
-  gemm_f16x3_body<false>(map_ah, map_al, map_bh, map_bl, map_o32, map_oh, map_ol, map_oha, map_ola, p);
+  gemm_f16x3_body<false, DBG, NB>(map_ah, map_al, map_bh, map_bl, map_o32, map_oh, map_ol, map_oha, map_ola, p);
 }
 
+template <bool DBG, int NB>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
 gemm_f16x3_pair_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
                        const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUtensorMap map_bl,
                        const __grid_constant__ CUtensorMap map_o32, const __grid_constant__ CUtensorMap map_oh,
                        const __grid_constant__ CUtensorMap map_ol, const __grid_constant__ CUtensorMap map_oha,
                        const __grid_constant__ CUtensorMap map_ola, const F16Params p) {
-  gemm_f16x3_body<true>(map_ah, map_al, map_bh, map_bl, map_o32, map_oh, map_ol, map_oha, map_ola, p);
+  gemm_f16x3_body<true, DBG, NB>(map_ah, map_al, map_bh, map_bl, map_o32, map_oh, map_ol, map_oha, map_ola, p);
 }
 
 int encode_map_f16(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
@@ -549,6 +616,8 @@ int gemm_tcgen05_f16x3(const dcae_operand* a, const dcae_weight* w, const dcae_e
   if (const char* env = getenv("DCAE_TC_CHUNK")) { const int v = atoi(env); if (v >= 1) p.chunk_kb = v; }
   p.descale = w->descale;
   p.dbg_nostore = getenv("DCAE_TC_NOSTORE") != nullptr;
+  static const bool dbg_on = getenv("DCAE_F16_DBG") != nullptr;
+  p.dbg = nullptr;
   p.b_bytes = (uint32_t)(pair ? p.BN / 2 : p.BN) * BK16 * 2;     // a pair's CTA holds half of the weight rows
   p.stage_bytes = 2 * A16_BYTES + 2 * p.b_bytes;
   p.stages = (int)((SMEM_LIMIT - 2048 - 2 * STG_BYTES) / p.stage_bytes);
@@ -606,20 +675,56 @@ int gemm_tcgen05_f16x3(const dcae_operand* a, const dcae_weight* w, const dcae_e
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(attr_once, [] {
-    attr_err = cudaFuncSetAttribute(gemm_f16x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT - 1024);
-    if (attr_err == cudaSuccess)
-      attr_err = cudaFuncSetAttribute(gemm_f16x3_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT - 1024);
+    const void* kernels[8] = {(const void*)gemm_f16x3_kernel<false, 2>, (const void*)gemm_f16x3_kernel<true, 2>,
+                              (const void*)gemm_f16x3_kernel<false, 4>, (const void*)gemm_f16x3_kernel<true, 4>,
+                              (const void*)gemm_f16x3_pair_kernel<false, 2>, (const void*)gemm_f16x3_pair_kernel<true, 2>,
+                              (const void*)gemm_f16x3_pair_kernel<false, 4>, (const void*)gemm_f16x3_pair_kernel<true, 4>};
+    for (int i = 0; i < 8 && attr_err == cudaSuccess; ++i)
+      attr_err = cudaFuncSetAttribute(kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT - 1024);
   });
   DCAE_CUDA(attr_err);
+  const int n_ctas = pair ? 2 * (p.total_tiles < num_sms() / 2 ? p.total_tiles : num_sms() / 2)
+                          : (p.total_tiles < num_sms() ? p.total_tiles : num_sms());
+  if (dbg_on) {     // debug only: synchronous launch with per-CTA role counters, summary on stderr
+    DCAE_CUDA(cudaMalloc(&p.dbg, (size_t)n_ctas * 16 * sizeof(unsigned long long)));
+    DCAE_CUDA(cudaMemsetAsync(p.dbg, 0, (size_t)n_ctas * 16 * sizeof(unsigned long long), s));
+  }
   if (pair) {
     const int max_pairs = num_sms() / 2;
     const int pairs = p.total_tiles < max_pairs ? p.total_tiles : max_pairs;
-    gemm_f16x3_pair_kernel<<<2 * pairs, NTHREADS, smem, s>>>(map_ah, map_al, map_bh, map_bl, map_o32, map_oh, map_ol, map_oha, map_ola, p);
+#define F16_LAUNCH(KERNEL, GRID)                                                                                      \
+  do {                                                                                                                \
+    if (dbg_on && p.BN <= 128) KERNEL<true, 2><<<GRID, NTHREADS, smem, s>>>(map_ah, map_al, map_bh, map_bl, map_o32, map_oh, map_ol, map_oha, map_ola, p);       \
+    else if (dbg_on) KERNEL<true, 4><<<GRID, NTHREADS, smem, s>>>(map_ah, map_al, map_bh, map_bl, map_o32, map_oh, map_ol, map_oha, map_ola, p);               \
+    else if (p.BN <= 128) KERNEL<false, 2><<<GRID, NTHREADS, smem, s>>>(map_ah, map_al, map_bh, map_bl, map_o32, map_oh, map_ol, map_oha, map_ola, p);         \
+    else KERNEL<false, 4><<<GRID, NTHREADS, smem, s>>>(map_ah, map_al, map_bh, map_bl, map_o32, map_oh, map_ol, map_oha, map_ola, p);                           \
+  } while (0)
+    F16_LAUNCH(gemm_f16x3_pair_kernel, 2 * pairs);
   } else {
     const int ctas = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-    gemm_f16x3_kernel<<<ctas, NTHREADS, smem, s>>>(map_ah, map_al, map_bh, map_bl, map_o32, map_oh, map_ol, map_oha, map_ola, p);
+    F16_LAUNCH(gemm_f16x3_kernel, ctas);
+#undef F16_LAUNCH
   }
   DCAE_LAUNCH_CHECK();
+  if (dbg_on) {
+    std::vector<unsigned long long> hbuf((size_t)n_ctas * 16);
+    DCAE_CUDA(cudaStreamSynchronize(s));
+    DCAE_CUDA(cudaMemcpy(hbuf.data(), p.dbg, hbuf.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    DCAE_CUDA(cudaFree(p.dbg));
+    double sum[16] = {0};
+    int nm = 0;
+    for (int c = 0; c < n_ctas; ++c) {
+      if (hbuf[(size_t)c * 16 + 3] == 0 && pair) continue;        // non-leader CTA of a pair: no MMA thread
+      ++nm;
+      for (int i = 0; i < 16; ++i) sum[i] += (double)hbuf[(size_t)c * 16 + i];
+    }
+    const double inv = nm ? 1.0 / nm : 0.0;
+    fprintf(stderr,
+            "[f16dbg] N=%d K=%d taps=%d BN=%d stages=%d pair=%d outs=%d%d%d | per CTA (cycles): mma_total %.0f wait_full %.0f wait_tmem %.0f "
+            "kblocks %.0f tiles %.1f | producer wait_empty %.0f | drain total %.0f wait_acc %.0f tmem_ld %.0f epilogue %.0f (finalize %.0f wait_read %.0f bar+stage %.0f fence+bar+issue %.0f)\n",
+            p.N, (int)Kp * p.taps, p.taps, p.BN, p.stages, (int)pair, p.has_o32, p.has_o16, p.has_o16a, sum[3] * inv, sum[1] * inv,
+            sum[2] * inv, sum[4] * inv, sum[5] * inv, sum[0] * inv, sum[9] * inv, sum[6] * inv, sum[7] * inv, sum[8] * inv, sum[10] * inv, sum[11] * inv, sum[13] * inv, sum[15] * inv);
+  }
   return DCAE_OK;
 }
 

@@ -206,9 +206,10 @@ __device__ __forceinline__ float epi_act(float v, int act) {
 
 // acc (+)= the chain partial sitting in TMEM at taddr (this warp's lane quarter, start of the chain buffer).
 // Both tcgen05.ld of a 32-column block are in flight per wait (more would spill next to the 128 running sums).
+template <int NB = EPI_BLOCKS>
 __device__ __forceinline__ void drain_chunk(float* acc, uint32_t taddr, int half, int BN, bool first) {
 #pragma unroll
-  for (int gg = 0; gg < EPI_BLOCKS; gg += 1) {
+  for (int gg = 0; gg < NB; gg += 1) {
     uint32_t raw[32];
 #pragma unroll
     for (int g = gg; g < gg + 1; ++g) {

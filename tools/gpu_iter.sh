@@ -15,4 +15,5 @@ run it_ops   400 python -m pytest tests/test_gpu_ops.py -q -m gpu -k "f16x3 or p
 run it_loop  600 python -m pytest tests/test_gpu_slice_loop.py -q -m gpu -k "f16x3 or kodak or config"
 run it_bench 600 python bench.py --no-cpu-baseline
 run it_layers 300 python tools/layer_times.py
+run it_dbg 300 python tools/f16_dbg.py
 exit 0
