@@ -198,7 +198,19 @@ struct dcae_slice_loop {
   void* planes;     // scratch for the split pass of operands that have no producer-written planes
   int64_t planes_bytes;
   int64_t n_part;   // partial sums per slice
+  // planes mode: the cc_scale chain (scale2 -> scale3) runs on a side stream beside the cc_mean chain -- each is
+  // 192 tiles on 148 SMs (a 30%-full second wave); side by side the second kernel's CTAs take the SMs the first frees
+  cudaStream_t side;
+  cudaEvent_t ev_fork, ev_join;
 };
+
+static void free_slice_loop(dcae_slice_loop* p) {
+  if (!p) return;
+  if (p->ev_fork) cudaEventDestroy(p->ev_fork);
+  if (p->ev_join) cudaEventDestroy(p->ev_join);
+  if (p->side) cudaStreamDestroy(p->side);
+  delete p;
+}
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -267,7 +279,7 @@ extern "C" int dcae_slice_loop_create(dcae_slice_loop** out, int32_t B, int32_t 
   const size_t need = carve(p, nullptr);
   if (need > workspace_bytes) {
     set_error("dcae_slice_loop_create: workspace too small (%zu < %zu)", workspace_bytes, need);
-    delete p;
+    free_slice_loop(p);
     return DCAE_E_WORKSPACE;
   }
   carve(p, static_cast<char*>(workspace));
@@ -277,9 +289,12 @@ extern "C" int dcae_slice_loop_create(dcae_slice_loop** out, int32_t B, int32_t 
   if (p->pm) {
     // padded K windows over-read a few never-written plane columns (their weight planes are zero): make them finite
     cudaError_t e = cudaMemset(p->planes_begin, 0, p->planes_total);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming);
     if (e != cudaSuccess) {
-      set_error("dcae_slice_loop_create: cudaMemset failed: %s", cudaGetErrorString(e));
-      delete p;
+      set_error("dcae_slice_loop_create: planes-mode setup failed: %s", cudaGetErrorString(e));
+      free_slice_loop(p);
       return DCAE_E_CUDA;
     }
   }
@@ -287,7 +302,7 @@ extern "C" int dcae_slice_loop_create(dcae_slice_loop** out, int32_t B, int32_t 
   return DCAE_OK;
 }
 
-extern "C" void dcae_slice_loop_destroy(dcae_slice_loop* p) { delete p; }
+extern "C" void dcae_slice_loop_destroy(dcae_slice_loop* p) { free_slice_loop(p); }
 
 // ---- small builders --------------------------------------------------------------------------
 static dcae_planes pl(const PBuf& b, int col = 0) {
@@ -430,10 +445,22 @@ extern "C" int dcae_slice_loop_params(dcae_slice_loop* p, int32_t i, void* s) {
     if (p->pm) e.out16 = pl(p->h1p, 0);
     DCAE_TRY(gemm(p, opnd2(p, p->sup, SUP_LD, p->supp, 0, cs, 9), W.cc1, e, s));
   }
+  // The two chains are independent (dcae.py:649-655) and write disjoint columns / buffers.  In planes mode no split
+  // scratch is shared either, so the scale chain forks onto the side stream and joins before the caller continues.
+  void* s2 = s;
+  if (p->pm && p->side) {
+    s2 = p->side;
+    DCAE_CUDA(cudaEventRecord(p->ev_fork, (cudaStream_t)s));
+    DCAE_CUDA(cudaStreamWaitEvent(p->side, p->ev_fork, 0));
+  }
   DCAE_TRY(gemm(p, opnd2(p, p->h1, 672, p->h1p, 0, 224, 9), W.mean2, epi2(p, W.mean2_b, p->h2.p, 256, p->h2p, 0, DCAE_ACT_GELU), s));
-  DCAE_TRY(gemm(p, opnd2(p, p->h1, 672, p->h1p, 224, 224, 9), W.scale2, epi2(p, W.scale2_b, p->h2.p + 128, 256, p->h2p, 128, DCAE_ACT_GELU), s));
+  DCAE_TRY(gemm(p, opnd2(p, p->h1, 672, p->h1p, 224, 224, 9), W.scale2, epi2(p, W.scale2_b, p->h2.p + 128, 256, p->h2p, 128, DCAE_ACT_GELU), s2));
   DCAE_TRY(gemm(p, opnd2(p, p->h2, 256, p->h2p, 0, 128, 9), W.mean3, epi(W.mean3_b, p->means.p + SL * i, M), s));
-  DCAE_TRY(gemm(p, opnd2(p, p->h2, 256, p->h2p, 128, 128, 9), W.scale3, epi(W.scale3_b, p->scales.p + SL * i, M), s));
+  DCAE_TRY(gemm(p, opnd2(p, p->h2, 256, p->h2p, 128, 128, 9), W.scale3, epi(W.scale3_b, p->scales.p + SL * i, M), s2));
+  if (s2 != s) {
+    DCAE_CUDA(cudaEventRecord(p->ev_join, (cudaStream_t)s2));
+    DCAE_CUDA(cudaStreamWaitEvent((cudaStream_t)s, p->ev_join, 0));
+  }
   return DCAE_OK;
 }
 

@@ -24,7 +24,7 @@ namespace {
 
 constexpr int AT_M = 128;        // tokens per tile
 constexpr int AT_HEADS = 20, AT_HD = 32, AT_ND = 128;
-constexpr int AT_THREADS = 320;
+constexpr int AT_THREADS = 448;   // warps: 0 TMA, 1 MMA, 2-9 softmax (two column halves x four TMEM quarters), 10-13 Q splitters
 constexpr int AT_TILE = AT_M * AT_HD * 4;   // 16 KB: every operand tile of a head has this size
 constexpr int AT_MAX_STAGES = 4;
 // TMEM columns
@@ -49,6 +49,7 @@ dict_attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const _
   __shared__ __align__(8) uint64_t full_bar[AT_MAX_STAGES], ready_bar[AT_MAX_STAGES], empty_bar[AT_MAX_STAGES];
   __shared__ __align__(8) uint64_t s_full, s_free, p_ready, o_full;
   __shared__ uint32_t tmem_base_slot;
+  __shared__ float xm[2][2][AT_M], xl[2][2][AT_M];    // row max / row sum of each column half, double-buffered by head parity
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -60,8 +61,8 @@ dict_attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const _
       mbar_init(smem_u32(&empty_bar[s]), 1);
     }
     mbar_init(smem_u32(&s_full), 1);
-    mbar_init(smem_u32(&s_free), 128);
-    mbar_init(smem_u32(&p_ready), 128);
+    mbar_init(smem_u32(&s_free), 256);
+    mbar_init(smem_u32(&p_ready), 256);
     mbar_init(smem_u32(&o_full), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -154,68 +155,79 @@ dict_attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const _
         mma_commit(smem_u32(&o_full));
       }
     }
-  } else if (warp < 6) {
-    // ===================== softmax warps: one token row per thread =====================
-    const int quarter = warp & 3;
+  } else if (warp < 10) {
+    // ===================== softmax warps: one token row per PAIR of threads =====================
+    // Warp w and w + 4 own the same 32 TMEM lanes (rows); each takes 64 of the 128 dictionary columns, so every
+    // scheduler has two softmax warps to alternate between and the unrolled body is half as long.  Row max and row
+    // sum cross the pair through shared memory with one 64-thread named barrier per head.
+    const int quarter = warp & 3, hf = (warp - 2) >> 2;
     const int r = quarter * 32 + lane;
     const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
+    constexpr int HC = AT_ND / 2;     // columns per thread
+    auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory"); };
     // O(g-1) is read back only after the exponentials of head g are done, so the PV MMAs of head g-1 run
     // underneath the softmax arithmetic of head g (and S(g+1) underneath that of head g, see the MMA warp).
-    auto write_out = [&](int g, float inv) {
+    // Each thread of the pair writes 16 of the head's 32 output columns.
+    auto write_out = [&](int g) {
       const int tile = blockIdx.x + (g / AT_HEADS) * gridDim.x, head = g % AT_HEADS;
+      const float inv = 1.0f / (xl[g & 1][0][r] + xl[g & 1][1][r]);
       mbar_wait(smem_u32(&o_full), g & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      uint32_t o0[16], o1[16];
-      tmem_ld16_nowait(lane_addr + TM_O, o0);
-      tmem_ld16_nowait(lane_addr + TM_O + 16, o1);
+      uint32_t o0[16];
+      tmem_ld16_nowait(lane_addr + TM_O + hf * 16, o0);
       tmem_ld_wait();
       const int64_t token = (int64_t)tile * AT_M + r;
       if (token < p.T) {
-        float4* dst = p.out ? reinterpret_cast<float4*>(p.out + token * p.out_ld + head * AT_HD) : nullptr;
+        const int col = head * AT_HD + hf * 16;
+        float4* dst = p.out ? reinterpret_cast<float4*>(p.out + token * p.out_ld + col) : nullptr;
 #pragma unroll
         for (int j = 0; j < 16; j += 4) {
           const float4 a = make_float4(__uint_as_float(o0[j]) * inv, __uint_as_float(o0[j + 1]) * inv,
                                        __uint_as_float(o0[j + 2]) * inv, __uint_as_float(o0[j + 3]) * inv);
-          const float4 b = make_float4(__uint_as_float(o1[j]) * inv, __uint_as_float(o1[j + 1]) * inv,
-                                       __uint_as_float(o1[j + 2]) * inv, __uint_as_float(o1[j + 3]) * inv);
-          if (dst) { dst[j / 4] = a; dst[4 + j / 4] = b; }
-          if (p.out16.hi) {
-            store_planes4(p.out16, token, head * AT_HD + j, a);
-            store_planes4(p.out16, token, head * AT_HD + 16 + j, b);
-          }
+          if (dst) dst[j / 4] = a;
+          if (p.out16.hi) store_planes4(p.out16, token, col + j, a);
         }
       }
     };
-    float inv_prev = 0.f;
     for (int g = 0; g < total; ++g) {
       const int head = g % AT_HEADS;
-      const float sc = __ldg(p.head_scale + head);
+      // softmax(sim * scale) = 2^(t - max t) / sum with t = sim * (scale * log2 e): one FMUL, one FADD and one MUFU.EX2
+      // per element (ex2.approx: 2^-22 relative); max and sum as 8 independent chains.
+      const float sc = __ldg(p.head_scale + head) * 1.4426950408889634f;
       mbar_wait(smem_u32(&s_full), g & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      float s[AT_ND];
+      float s[HC];
       {
-        uint32_t raw[AT_ND];
+        uint32_t raw[HC];
 #pragma unroll
-        for (int c = 0; c < AT_ND / 16; ++c) tmem_ld16_nowait(lane_addr + TM_S + c * 16, raw + c * 16);   // 8 loads in flight
+        for (int c = 0; c < HC / 16; ++c) tmem_ld16_nowait(lane_addr + TM_S + hf * HC + c * 16, raw + c * 16);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < AT_ND; ++j) s[j] = __uint_as_float(raw[j]) * sc;   // sim * scale (dcae.py:498)
+        for (int j = 0; j < HC; ++j) s[j] = __uint_as_float(raw[j]) * sc;   // sim * scale (dcae.py:498), log2 domain
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive(smem_u32(&s_free));                           // S may be overwritten by head g+1
-      float mx = s[0];
+      float m8[8];
 #pragma unroll
-      for (int j = 1; j < AT_ND; ++j) mx = fmaxf(mx, s[j]);
-      float l = 0.f;
+      for (int j = 0; j < 8; ++j) m8[j] = s[j];
 #pragma unroll
-      for (int j = 0; j < AT_ND; ++j) {
-        s[j] = expf(s[j] - mx);
-        l += s[j];
+      for (int j = 8; j < HC; ++j) m8[j & 7] = fmaxf(m8[j & 7], s[j]);
+      float mx = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])), fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7])));
+      xm[g & 1][hf][r] = mx;
+      pair_sync();                                              // also orders xl(g-1) of the partner before write_out(g-1)
+      mx = fmaxf(mx, xm[g & 1][hf ^ 1][r]);
+      float l8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int j = 0; j < HC; ++j) {
+        float e;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(s[j] - mx));
+        s[j] = e;
+        l8[j & 7] += e;
       }
-      if (g > 0) write_out(g - 1, inv_prev);                   // also guarantees PV(g-1) has finished reading P
-      inv_prev = 1.0f / l;
+      if (g > 0) write_out(g - 1);                              // also guarantees PV(g-1) has finished reading P
+      xl[g & 1][hf][r] = ((l8[0] + l8[1]) + (l8[2] + l8[3])) + ((l8[4] + l8[5]) + (l8[6] + l8[7]));
 #pragma unroll
-      for (int c = 0; c < AT_ND / 16; ++c) {
+      for (int c = 0; c < HC / 16; ++c) {
         uint32_t hi[16], lo[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
@@ -224,18 +236,21 @@ dict_attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const _
           hi[j] = __float_as_uint(h);
           lo[j] = __float_as_uint(tf32_rna(e - h));
         }
-        tmem_st16(lane_addr + TM_PHI + c * 16, hi);
-        if (PASSES == 3) tmem_st16(lane_addr + TM_PLO + c * 16, lo);
+        tmem_st16(lane_addr + TM_PHI + hf * HC + c * 16, hi);
+        if (PASSES == 3) tmem_st16(lane_addr + TM_PLO + hf * HC + c * 16, lo);
       }
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive(smem_u32(&p_ready));
     }
-    if (total > 0) write_out(total - 1, inv_prev);
+    if (total > 0) {
+      pair_sync();
+      write_out(total - 1);
+    }
   } else {
     // ===================== Q splitters (3-pass): q -> (q_hi in place, q_lo) =====================
     if (PASSES == 3) {
-      const int st = threadIdx.x - 192;   // 0..127
+      const int st = threadIdx.x - 320;   // 0..127
       for (int g = 0; g < total; ++g) {
         const int stage = g % p.stages;
         mbar_wait(smem_u32(&full_bar[stage]), (g / p.stages) & 1);

@@ -73,9 +73,12 @@ constexpr int DW_X = 8, DW_ROWS = 4;
 
 // grid = (ceil(C4 / 32), ceil(h / DW_ROWS), B * ceil(w / DW_X)); block = 32 channel groups x DW_ROWS token rows, so the
 // three input rows a thread needs are shared with its neighbours in the block through L1.
+// ACT: 0 none, 1 GELU (erff form, the fp32 path), 2 GELU through gelu_fast (planes-only output, i.e. the tensor-core
+// modes: measured issue-bound on erff, 67% issue utilisation at 25% occupancy, before the switch).
+template <int ACT>
 __global__ void __launch_bounds__(32 * DW_ROWS) dwconv3x3_kernel(const float* __restrict__ x, int64_t x_ld,
                                                         const float* __restrict__ wt, const float* __restrict__ bias,
-                                                        int C4, int B, int h, int w, int act,
+                                                        int C4, int B, int h, int w,
                                                         const float* __restrict__ gate, int64_t gate_ld,
                                                         float* __restrict__ out, int64_t out_ld, const dcae_planes o16) {
   const int xg = (w + DW_X - 1) / DW_X;
@@ -123,7 +126,8 @@ __global__ void __launch_bounds__(32 * DW_ROWS) dwconv3x3_kernel(const float* __
       if (x2 >= w) break;
       const int64_t t = (int64_t)(b * h + yy) * w + x2;
       float4 a = acc[j];
-      if (act == DCAE_ACT_GELU) { a.x = gelu_erf(a.x); a.y = gelu_erf(a.y); a.z = gelu_erf(a.z); a.w = gelu_erf(a.w); }
+      if (ACT == 1) { a.x = gelu_erf(a.x); a.y = gelu_erf(a.y); a.z = gelu_erf(a.z); a.w = gelu_erf(a.w); }
+      if (ACT == 2) { a.x = gelu_fast(a.x); a.y = gelu_fast(a.y); a.z = gelu_fast(a.z); a.w = gelu_fast(a.w); }
       if (gate != nullptr) {
         const float4 g = __ldg(reinterpret_cast<const float4*>(gate + t * gate_ld + c));
         a.x *= g.x; a.y *= g.y; a.z *= g.z; a.w *= g.w;
@@ -338,7 +342,10 @@ extern "C" int dcae_op_dwconv3x3(const float* x, int64_t x_ld, const float* wt, 
   const int xg = (w + DW_X - 1) / DW_X;
   DCAE_REQUIRE((int64_t)B * xg <= 65535 && (h + DW_ROWS - 1) / DW_ROWS <= 65535, "dcae_op_dwconv3x3: token grid too large");
   dim3 grid((unsigned)((C / 4 + 31) / 32), (unsigned)((h + DW_ROWS - 1) / DW_ROWS), (unsigned)(B * xg));
-  dwconv3x3_kernel<<<grid, 32 * DW_ROWS, 0, (cudaStream_t)stream>>>(x, x_ld, wt, bias, C / 4, B, h, w, act, gate, gate_ld, out, out_ld, o16);
+  const int variant = act == DCAE_ACT_NONE ? 0 : (out == nullptr ? 2 : 1);
+  if (variant == 0) dwconv3x3_kernel<0><<<grid, 32 * DW_ROWS, 0, (cudaStream_t)stream>>>(x, x_ld, wt, bias, C / 4, B, h, w, gate, gate_ld, out, out_ld, o16);
+  else if (variant == 1) dwconv3x3_kernel<1><<<grid, 32 * DW_ROWS, 0, (cudaStream_t)stream>>>(x, x_ld, wt, bias, C / 4, B, h, w, gate, gate_ld, out, out_ld, o16);
+  else dwconv3x3_kernel<2><<<grid, 32 * DW_ROWS, 0, (cudaStream_t)stream>>>(x, x_ld, wt, bias, C / 4, B, h, w, gate, gate_ld, out, out_ld, o16);
   DCAE_LAUNCH_CHECK();
   return DCAE_OK;
 }

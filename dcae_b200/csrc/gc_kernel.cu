@@ -20,6 +20,7 @@ struct GcParams {
   int64_t groups;   // rows * inner/4
   uint32_t inner4;
   uint32_t shift;   // log2(inner4) when inner4 is a power of two
+  int32_t n_partials;   // dcae_gc_num_partials(rows, inner): entries past the grid size are written as zero
 };
 
 __device__ __forceinline__ float nan_max(float x, float bound) {
@@ -139,6 +140,8 @@ __global__ void __launch_bounds__(GC_THREADS) gc_fused_kernel(const GcParams p) 
       for (int w = 0; w < GC_THREADS / 32; ++w) t += red[w];
       a.log2_partials[blockIdx.x] = t;
     }
+    if (blockIdx.x == 0)        // the caller reduces dcae_gc_num_partials entries whatever this launch's grid was
+      for (int i = (int)gridDim.x + (int)threadIdx.x; i < p.n_partials; i += GC_THREADS) a.log2_partials[i] = 0.f;
   }
 }
 
@@ -156,17 +159,35 @@ __global__ void reduce_partials_kernel(const float* __restrict__ p, int64_t n, f
   if (threadIdx.x == 0) out[0] = sh[0];
 }
 
-static int64_t gc_blocks(int64_t rows, int64_t inner) {
+// The element loop is grid-stride, so the grid is ONE resident wave: SMs x blocks that fit per SM for this variant
+// (a fixed 148 x 8 was 1.6 waves at 5 resident blocks/SM, i.e. a 40%-occupied second wave).  The partial-sum buffer is
+// sized for the upper bound GC_MAX_BLOCKS, which dcae_gc_num_partials reports.
+static int64_t gc_blocks(int64_t rows, int64_t inner, int resident_per_sm = 8) {
   int64_t groups = rows * (inner / 4);
   int64_t b = (groups + GC_THREADS - 1) / GC_THREADS;
+  const int64_t cap = (int64_t)num_sms() * resident_per_sm;
+  if (b > cap) b = cap;
   if (b > GC_MAX_BLOCKS) b = GC_MAX_BLOCKS;
   if (b < 1) b = 1;
   return b;
 }
 
+template <int MODE, bool LIK, bool IDX, bool POW2>
+static int gc_resident() {
+  static const int n = [] {
+    int v = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, gc_fused_kernel<MODE, LIK, IDX, POW2>, GC_THREADS, 0) != cudaSuccess || v < 1) v = 4;
+    return v;
+  }();
+  return n;
+}
+
 }  // namespace dcae
 
-extern "C" int64_t dcae_gc_num_partials(int64_t rows, int64_t inner) { return dcae::gc_blocks(rows, inner); }
+extern "C" int64_t dcae_gc_num_partials(int64_t rows, int64_t inner) {
+  int64_t b = (rows * (inner / 4) + dcae::GC_THREADS - 1) / dcae::GC_THREADS;     // upper bound of any launch's grid
+  return b < 1 ? 1 : (b > dcae::GC_MAX_BLOCKS ? dcae::GC_MAX_BLOCKS : b);
+}
 
 extern "C" int dcae_gc_fused(const dcae_gc_args* a, void* stream) {
   using namespace dcae;
@@ -194,7 +215,7 @@ extern "C" int dcae_gc_fused(const dcae_gc_args* a, void* stream) {
   p.a = *a;
   p.inner4 = (uint32_t)(a->inner / 4);
   p.groups = a->rows * (a->inner / 4);
-  const int64_t blocks = gc_blocks(a->rows, a->inner);
+  p.n_partials = (int32_t)dcae_gc_num_partials(a->rows, a->inner);
   const int n_tensors = (a->y && a->mode != DCAE_GC_DECODE) + 1 + (a->scale != nullptr) + (a->mode == DCAE_GC_NOISE) +
                         (a->mode == DCAE_GC_DECODE) + (a->y_hat != nullptr) + (a->lik != nullptr) + (a->sym != nullptr) + (a->idx != nullptr);
   ProfileScope prof(DCAE_PROF_GC, 4.0 * n_tensors * (double)a->rows * (double)a->inner, stream);
@@ -203,12 +224,11 @@ extern "C" int dcae_gc_fused(const dcae_gc_args* a, void* stream) {
   while (pow2 && (1u << p.shift) < p.inner4) ++p.shift;
   const bool lik = (a->lik != nullptr || a->log2_partials != nullptr) && a->mode != DCAE_GC_DECODE && a->y != nullptr;
   const bool idx = a->idx != nullptr;
-  const unsigned nb = (unsigned)blocks;
   cudaStream_t st = (cudaStream_t)stream;
-#define GC_LAUNCH(M, L, I)                                                        \
-  do {                                                                            \
-    if (pow2) gc_fused_kernel<M, L, I, true><<<nb, GC_THREADS, 0, st>>>(p);       \
-    else gc_fused_kernel<M, L, I, false><<<nb, GC_THREADS, 0, st>>>(p);           \
+#define GC_LAUNCH(M, L, I)                                                                                            \
+  do {                                                                                                                \
+    if (pow2) gc_fused_kernel<M, L, I, true><<<(unsigned)gc_blocks(a->rows, a->inner, gc_resident<M, L, I, true>()), GC_THREADS, 0, st>>>(p);    \
+    else gc_fused_kernel<M, L, I, false><<<(unsigned)gc_blocks(a->rows, a->inner, gc_resident<M, L, I, false>()), GC_THREADS, 0, st>>>(p);      \
   } while (0)
 #define GC_LAUNCH_MODE(M)                                                         \
   do {                                                                            \

@@ -244,6 +244,12 @@ __device__ __forceinline__ void gemm_f16x3_body(const CUtensorMap& map_ah, const
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const long long t_entry = DBG ? clock64() : 0;
+  if (DBG && threadIdx.x == 32) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    p.dbg[blockIdx.x * 24 + 16] = gt;
+  }
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
   const bool leader = rank == 0;
   const int unit = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;          // which persistent worker (CTA or pair)
@@ -331,7 +337,7 @@ __device__ __forceinline__ void gemm_f16x3_body(const CUtensorMap& map_ah, const
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
-      if (DBG) p.dbg[blockIdx.x * 16 + 0] = (unsigned long long)w_empty;
+      if (DBG) p.dbg[blockIdx.x * 24 + 0] = (unsigned long long)w_empty;
     } else if (warp == 1 && lane == 0 && leader) {
       // ===================== MMA issuer (the leader CTA of a pair) =====================
       // D = F32 (bit 4), A = B = F16 (format 0), K-major, N >> 3 at bit 17, M >> 4 at bit 24
@@ -340,6 +346,7 @@ __device__ __forceinline__ void gemm_f16x3_body(const CUtensorMap& map_ah, const
       uint32_t phase = 0, gchunk = 0;
       long long w_full = 0, w_tmem = 0, n_kb = 0, n_tiles = 0;
       const long long t_start = clock64();
+      if (DBG) p.dbg[blockIdx.x * 24 + 12] = (unsigned long long)(t_start - t_entry);
       for (int t = unit; t < p.total_tiles; t += nunits) {
         ++n_tiles;
         for (int ck = 0; ck < n_chunks; ++ck, ++gchunk) {
@@ -379,7 +386,7 @@ __device__ __forceinline__ void gemm_f16x3_body(const CUtensorMap& map_ah, const
         }
       }
       if (DBG) {
-        unsigned long long* d = p.dbg + blockIdx.x * 16;
+        unsigned long long* d = p.dbg + blockIdx.x * 24;
         d[1] = (unsigned long long)w_full; d[2] = (unsigned long long)w_tmem; d[3] = (unsigned long long)(clock64() - t_start);
         d[4] = (unsigned long long)n_kb; d[5] = (unsigned long long)n_tiles;
       }
@@ -483,7 +490,7 @@ __device__ __forceinline__ void gemm_f16x3_body(const CUtensorMap& map_ah, const
       if (DBG) t_epi += clock64() - te0;
     }
     if (DBG && warp == 4 && lane == 0) {
-      unsigned long long* d = p.dbg + blockIdx.x * 16;
+      unsigned long long* d = p.dbg + blockIdx.x * 24;
       d[6] = (unsigned long long)w_acc; d[7] = (unsigned long long)t_drain; d[8] = (unsigned long long)t_epi;
       d[9] = (unsigned long long)(clock64() - t_start); d[10] = (unsigned long long)t_fin; d[11] = (unsigned long long)t_rd;
       d[13] = (unsigned long long)t_st; d[15] = (unsigned long long)t_b2;
@@ -497,6 +504,12 @@ __device__ __forceinline__ void gemm_f16x3_body(const CUtensorMap& map_ah, const
   if (warp == 1) {
     if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
     else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+  }
+  if (DBG && threadIdx.x == 32) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    p.dbg[blockIdx.x * 24 + 17] = gt;
+    p.dbg[blockIdx.x * 24 + 14] = (unsigned long long)(clock64() - t_entry);
   }
 }
 
@@ -686,8 +699,8 @@ int gemm_tcgen05_f16x3(const dcae_operand* a, const dcae_weight* w, const dcae_e
   const int n_ctas = pair ? 2 * (p.total_tiles < num_sms() / 2 ? p.total_tiles : num_sms() / 2)
                           : (p.total_tiles < num_sms() ? p.total_tiles : num_sms());
   if (dbg_on) {     // debug only: synchronous launch with per-CTA role counters, summary on stderr
-    DCAE_CUDA(cudaMalloc(&p.dbg, (size_t)n_ctas * 16 * sizeof(unsigned long long)));
-    DCAE_CUDA(cudaMemsetAsync(p.dbg, 0, (size_t)n_ctas * 16 * sizeof(unsigned long long), s));
+    DCAE_CUDA(cudaMalloc(&p.dbg, (size_t)n_ctas * 24 * sizeof(unsigned long long)));
+    DCAE_CUDA(cudaMemsetAsync(p.dbg, 0, (size_t)n_ctas * 24 * sizeof(unsigned long long), s));
   }
   if (pair) {
     const int max_pairs = num_sms() / 2;
@@ -707,23 +720,32 @@ int gemm_tcgen05_f16x3(const dcae_operand* a, const dcae_weight* w, const dcae_e
   }
   DCAE_LAUNCH_CHECK();
   if (dbg_on) {
-    std::vector<unsigned long long> hbuf((size_t)n_ctas * 16);
+    std::vector<unsigned long long> hbuf((size_t)n_ctas * 24);
     DCAE_CUDA(cudaStreamSynchronize(s));
     DCAE_CUDA(cudaMemcpy(hbuf.data(), p.dbg, hbuf.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     DCAE_CUDA(cudaFree(p.dbg));
     double sum[16] = {0};
     int nm = 0;
+    unsigned long long g0 = ~0ull, g1 = 0, g0max = 0, g1min = ~0ull;
     for (int c = 0; c < n_ctas; ++c) {
-      if (hbuf[(size_t)c * 16 + 3] == 0 && pair) continue;        // non-leader CTA of a pair: no MMA thread
+      const unsigned long long a0 = hbuf[(size_t)c * 24 + 16], a1 = hbuf[(size_t)c * 24 + 17];
+      if (a0 && a0 < g0) g0 = a0;
+      if (a0 > g0max) g0max = a0;
+      if (a1 > g1) g1 = a1;
+      if (a1 && a1 < g1min) g1min = a1;
+    }
+    for (int c = 0; c < n_ctas; ++c) {
+      if (hbuf[(size_t)c * 24 + 3] == 0 && pair) continue;        // non-leader CTA of a pair: no MMA thread
       ++nm;
-      for (int i = 0; i < 16; ++i) sum[i] += (double)hbuf[(size_t)c * 16 + i];
+      for (int i = 0; i < 16; ++i) sum[i] += (double)hbuf[(size_t)c * 24 + i];
     }
     const double inv = nm ? 1.0 / nm : 0.0;
     fprintf(stderr,
             "[f16dbg] N=%d K=%d taps=%d BN=%d stages=%d pair=%d outs=%d%d%d | per CTA (cycles): mma_total %.0f wait_full %.0f wait_tmem %.0f "
-            "kblocks %.0f tiles %.1f | producer wait_empty %.0f | drain total %.0f wait_acc %.0f tmem_ld %.0f epilogue %.0f (finalize %.0f wait_read %.0f bar+stage %.0f fence+bar+issue %.0f)\n",
+            "kblocks %.0f tiles %.1f | producer wait_empty %.0f | drain total %.0f wait_acc %.0f tmem_ld %.0f epilogue %.0f (finalize %.0f wait_read %.0f bar+stage %.0f fence+bar+issue %.0f) | prologue %.0f cta_total %.0f | grid span %.1f us, entry skew %.1f us, exit skew %.1f us\n",
             p.N, (int)Kp * p.taps, p.taps, p.BN, p.stages, (int)pair, p.has_o32, p.has_o16, p.has_o16a, sum[3] * inv, sum[1] * inv,
-            sum[2] * inv, sum[4] * inv, sum[5] * inv, sum[0] * inv, sum[9] * inv, sum[6] * inv, sum[7] * inv, sum[8] * inv, sum[10] * inv, sum[11] * inv, sum[13] * inv, sum[15] * inv);
+            sum[2] * inv, sum[4] * inv, sum[5] * inv, sum[0] * inv, sum[9] * inv, sum[6] * inv, sum[7] * inv, sum[8] * inv, sum[10] * inv, sum[11] * inv, sum[13] * inv, sum[15] * inv, sum[12] * inv, sum[14] * inv,
+            (double)(g1 - g0) * 1e-3, (double)(g0max - g0) * 1e-3, (double)(g1 - g1min) * 1e-3);
   }
   return DCAE_OK;
 }

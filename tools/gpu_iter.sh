@@ -11,7 +11,7 @@ run() { local name=$1 t=$2; shift 2
 }
 : > gpurun_out/iter_summary.txt
 run it_gc    300 python -m pytest tests/test_gpu_gc.py -q -x -m gpu
-run it_ops   400 python -m pytest tests/test_gpu_ops.py -q -m gpu -k "f16x3 or planes"
+run it_ops   600 python -m pytest tests/test_gpu_ops.py -q -m gpu
 run it_loop  600 python -m pytest tests/test_gpu_slice_loop.py -q -m gpu -k "f16x3 or kodak or config"
 run it_bench 600 python bench.py --no-cpu-baseline
 run it_layers 300 python tools/layer_times.py
