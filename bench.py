@@ -154,7 +154,9 @@ def main():
     ap.add_argument("--batch", type=int, default=16, help="images per GPU per step (config #2: 16)")
     ap.add_argument("--cpu-images", type=int, default=2, help="images per step of the CPU reference arm")
     ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--lanes", type=int, default=2, help="sub-batches run on separate streams by EntropySliceLoop.forward")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-clock-sampler", action="store_true", help="diagnostic: do not poll NVML during the timed region")
     ap.add_argument("--gc-micro-mb", type=int, default=1024, help="footprint of the kernel-3 HBM microbenchmark")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -177,7 +179,7 @@ def main():
 
     B, h, w = args.batch, H_IMG // 16, W_IMG // 16
     T = B * h * w
-    eng = EntropySliceLoop(init_entropy_params(0, "lively"), device=dev, math=args.math)
+    eng = EntropySliceLoop(init_entropy_params(0, "lively"), device=dev, math=args.math, lanes=args.lanes)
     host_in = synth_latents(B, h, w, seed=1234 + rank, pin=True)
     dev_in = [t.to(dev) for t in host_in]
     lib = _lib.load()
@@ -215,7 +217,7 @@ def main():
         return float(ms) / steps, out
 
     # the sampler starts BEFORE the warm-up (NVML start-up must not land inside the timed region)
-    sampler = ClockSampler(local) if rank == 0 else None
+    sampler = ClockSampler(local) if rank == 0 and not args.no_clock_sampler else None
     for _ in range(max(args.warmup, 3)):
         step_resident()
     torch.cuda.synchronize()
@@ -287,7 +289,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": "DCAE entropy-model forward (slice loop), batch 16 synthetic Kodak-shaped 768x512 images per GPU (BASELINE config #2)",
                        "batch_per_gpu": B, "tokens_per_gpu": T, "math": args.math, "weights": "random-init (seeded, lively profile)",
-                       "l2": "no flush needed: per-step working set 1.8 GB >> 126 MB L2", "parallelism": f"{world} independent image shards"},
+                       "l2": "no flush needed: per-step working set 1.8 GB >> 126 MB L2", "parallelism": f"{world} independent image shards", "lanes_per_gpu": args.lanes},
             "e2e": {"value": imgs / (ms_e2e * 1e-3), "unit": "images/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": pipe.h2d_bytes, "d2h_bytes_per_step": pipe.d2h_bytes,
                     "how": "dcae_b200.HostPipeline: pinned host tensors in and out, H2D / compute / D2H of consecutive batches overlapped on 3 streams (wall clock over the K steps, last result on the host)"},

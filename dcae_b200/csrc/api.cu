@@ -288,7 +288,9 @@ extern "C" int dcae_slice_loop_create(dcae_slice_loop** out, int32_t B, int32_t 
   p->n_part = dcae_gc_num_partials(p->T, SL);
   if (p->pm) {
     // padded K windows over-read a few never-written plane columns (their weight planes are zero): make them finite
+    // (the memset runs on the legacy stream; the plan may be used on any non-blocking stream right after create)
     cudaError_t e = cudaMemset(p->planes_begin, 0, p->planes_total);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming);

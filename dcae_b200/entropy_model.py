@@ -50,10 +50,15 @@ class _Plan:
 
 class EntropySliceLoop:
     """params: reference state dict (hot-path keys).
-    math: 'f16x3' (default: fp16 hi/lo planes, fp32-level accuracy) | 'tf32x3' | 'fp32' (FFMA) | 'tf32' (reduced)."""
+    math: 'f16x3' (default: fp16 hi/lo planes, fp32-level accuracy) | 'tf32x3' | 'fp32' (FFMA) | 'tf32' (reduced).
+    lanes: images are independent, so `forward` splits the batch into this many sub-batches, each with its
+    own plan on its own stream.  Every kernel of the loop is a persistent grid with a partly filled last wave (960
+    tiles on 148 SMs; 192 for the small conv layers) and the loop is one dependent chain, so a lone lane leaves SMs
+    idle at every kernel boundary; with two lanes the other lane's kernels take those SMs.  Per-image results do not
+    depend on the split (tests: batch invariance)."""
 
     def __init__(self, params: Dict[str, torch.Tensor], device="cuda:0", math: str = "f16x3",
-                 scale_table: Optional[torch.Tensor] = None):
+                 scale_table: Optional[torch.Tensor] = None, lanes: int = 2):
         if math not in _lib.MATH:
             raise ValueError(f"math must be one of {list(_lib.MATH)}")
         self.device = torch.device(device)
@@ -69,13 +74,28 @@ class EntropySliceLoop:
         self.scale_table = scale_table.to(self.device, torch.float32).contiguous()
         self._plans: Dict[tuple, _Plan] = {}
         self.last_launches = 0
+        self.lanes = max(1, int(lanes))
+        with torch.cuda.device(self.device):
+            self._lane_streams = [torch.cuda.Stream(self.device) for _ in range(self.lanes)] if self.lanes > 1 else []
 
     # ---- plumbing -------------------------------------------------------------------------------
-    def _plan(self, B, h, w) -> _Plan:
-        key = (B, h, w)
+    def _plan(self, B, h, w, lane: int = -1) -> _Plan:
+        key = (B, h, w, lane)
         if key not in self._plans:
             self._plans[key] = _Plan(self, B, h, w)
         return self._plans[key]
+
+    def _lane_split(self, B):
+        """[(lane, first image, images)] of a batch of B images (one entry when lanes do not apply)."""
+        n = min(self.lanes, B)
+        if n <= 1:
+            return [(-1, 0, B)]
+        base, extra, out, b0 = B // n, B % n, [], 0
+        for lane in range(n):
+            nb = base + (1 if lane < extra else 0)
+            out.append((lane, b0, nb))
+            b0 += nb
+        return out
 
     def _check_in(self, name, t, B=None, C_=M_LATENT):
         if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float32 and t.dim() == 4):
@@ -103,7 +123,7 @@ class EntropySliceLoop:
             raise ValueError("y, latent_scales and latent_means must have the same shape")
         if noise is not None:
             noise = self._check_in("noise", noise)
-        plan, lib, s = self._plan(B, h, w), self.lib, self._stream()
+        lib, s = self.lib, self._stream()
         sym = idx = None
         if out is None:
             out = {k: torch.empty_like(y) for k in ("y_hat", "means", "scales", "likelihoods")}
@@ -117,24 +137,60 @@ class EntropySliceLoop:
             sym, idx = out["symbols"], out["indexes"]
         if B == 0 or h == 0 or w == 0:
             return out
-        with torch.cuda.device(self.device):
-            if noise is None:
-                _lib.check(lib.dcae_slice_loop_forward(plan.handle, y.data_ptr(), ls.data_ptr(), lm.data_ptr(),
-                                                       out["y_hat"].data_ptr(), out["means"].data_ptr(),
-                                                       out["scales"].data_ptr(), out["likelihoods"].data_ptr(),
-                                                       _lib.ptr(sym), _lib.ptr(idx), out["log2_lik_sum"].data_ptr(), s),
-                           "dcae_slice_loop_forward")
-            else:
-                _lib.check(lib.dcae_slice_loop_load(plan.handle, y.data_ptr(), ls.data_ptr(), lm.data_ptr(), s), "load")
-                for i, nz in enumerate(noise.chunk(NUM_SLICES, 1)):
-                    nz = nz.contiguous()
-                    _lib.check(lib.dcae_slice_loop_params(plan.handle, i, s), "params")
-                    _lib.check(lib.dcae_slice_loop_encode(plan.handle, i, _lib.GC_NOISE, nz.data_ptr(), s), "encode")
-                _lib.check(lib.dcae_slice_loop_store(plan.handle, out["y_hat"].data_ptr(), out["means"].data_ptr(),
-                                                     out["scales"].data_ptr(), out["likelihoods"].data_ptr(),
-                                                     _lib.ptr(sym), _lib.ptr(idx), out["log2_lik_sum"].data_ptr(), s), "store")
+        split = self._lane_split(B)
+        self._last_call_lanes = len(split) > 1
+        if len(split) == 1:
+            with torch.cuda.device(self.device):
+                self._run_forward(self._plan(B, h, w), s, y, ls, lm, noise, out, sym, idx, out["log2_lik_sum"])
+        else:
+            cur = torch.cuda.current_stream(self.device)
+            fork = torch.cuda.Event()
+            fork.record(cur)
+            sums = torch.empty(len(split), device=self.device)
+            lane_sym = []
+            with torch.cuda.device(self.device):
+                for lane, b0, nb in split:
+                    st = self._lane_streams[lane]
+                    st.wait_event(fork)
+                    sl = slice(b0, b0 + nb)
+                    lo = {k: out[k][sl] for k in ("y_hat", "means", "scales", "likelihoods")}
+                    ssym = sidx = None
+                    if want_symbols:          # [5, nb, 64, h, w] per lane, copied into the coder-order tensor below
+                        ssym = torch.empty(NUM_SLICES, nb, SLICE_CH, h, w, dtype=torch.int32, device=self.device)
+                        sidx = torch.empty_like(ssym)
+                        lane_sym.append((sl, ssym, sidx))
+                    with torch.cuda.stream(st):
+                        self._run_forward(self._plan(nb, h, w, lane), st.cuda_stream, y[sl], ls[sl], lm[sl],
+                                          None if noise is None else noise[sl], lo, ssym, sidx, sums[lane:lane + 1])
+                    done = torch.cuda.Event()
+                    done.record(st)
+                    cur.wait_event(done)
+                for sl, ssym, sidx in lane_sym:
+                    sym[:, sl].copy_(ssym)
+                    idx[:, sl].copy_(sidx)
+                _lib.check(lib.dcae_reduce_partials(sums.data_ptr(), len(split), out["log2_lik_sum"].data_ptr(), s),
+                           "dcae_reduce_partials")
         self.last_launches = int(lib.dcae_launch_count())
         return out
+
+    def _run_forward(self, plan, s, y, ls, lm, noise, out, sym, idx, log2_sum):
+        """One plan, one stream: the slice loop for the (sub-)batch whose NCHW tensors are given (contiguous views)."""
+        lib = self.lib
+        if noise is None:
+            _lib.check(lib.dcae_slice_loop_forward(plan.handle, y.data_ptr(), ls.data_ptr(), lm.data_ptr(),
+                                                   out["y_hat"].data_ptr(), out["means"].data_ptr(),
+                                                   out["scales"].data_ptr(), out["likelihoods"].data_ptr(),
+                                                   _lib.ptr(sym), _lib.ptr(idx), log2_sum.data_ptr(), s),
+                       "dcae_slice_loop_forward")
+        else:
+            _lib.check(lib.dcae_slice_loop_load(plan.handle, y.data_ptr(), ls.data_ptr(), lm.data_ptr(), s), "load")
+            for i, nz in enumerate(noise.chunk(NUM_SLICES, 1)):
+                nz = nz.contiguous()
+                _lib.check(lib.dcae_slice_loop_params(plan.handle, i, s), "params")
+                _lib.check(lib.dcae_slice_loop_encode(plan.handle, i, _lib.GC_NOISE, nz.data_ptr(), s), "encode")
+            _lib.check(lib.dcae_slice_loop_store(plan.handle, out["y_hat"].data_ptr(), out["means"].data_ptr(),
+                                                 out["scales"].data_ptr(), out["likelihoods"].data_ptr(),
+                                                 _lib.ptr(sym), _lib.ptr(idx), log2_sum.data_ptr(), s), "store")
 
     # ---- DCAE.compress slice loop ---------------------------------------------------------------
     def compress(self, y, latent_scales, latent_means, with_likelihoods: bool = False):
@@ -154,6 +210,7 @@ class EntropySliceLoop:
         lm = self._check_in("latent_means", latent_means)
         B, _, h, w = ls.shape
         plan, lib, s = self._plan(B, h, w), self.lib, self._stream()
+        self._last_call_lanes = False
         y_hat = torch.empty_like(ls)
         idx_all = torch.empty(NUM_SLICES, B, SLICE_CH, h, w, dtype=torch.int32, device=self.device)
         with torch.cuda.device(self.device):
@@ -171,8 +228,13 @@ class EntropySliceLoop:
 
     # ---- debugging / stage-wise parity (the reference's debug_save pattern, dcae_5_fixed.py:29-34) ---
     def tap(self, name: str, B: int, h: int, w: int) -> torch.Tensor:
-        """Copy of a named token-major intermediate [T, cols] of the most recent call."""
-        plan = self._plan(B, h, w)
+        """Copy of a named token-major intermediate [T, cols] of the most recent call (`forward` lanes concatenated)."""
+        split = self._lane_split(B) if getattr(self, "_last_call_lanes", False) else [(-1, 0, B)]
+        if len(split) > 1:
+            return torch.cat([self._tap_plan(self._plan(nb, h, w, lane), name, nb, h, w) for lane, _, nb in split])
+        return self._tap_plan(self._plan(B, h, w), name, B, h, w)
+
+    def _tap_plan(self, plan, name, B, h, w):
         p, cols, ld = C.c_void_p(), C.c_int32(), C.c_int64()
         _lib.check(self.lib.dcae_slice_loop_tap(plan.handle, name.encode(), C.byref(p), C.byref(cols), C.byref(ld)), "tap")
         T = B * h * w
@@ -186,7 +248,13 @@ class EntropySliceLoop:
 
 def _tap16(self, name: str, B: int, h: int, w: int) -> torch.Tensor:
     """f16x3 mode: a planes-only intermediate [T, cols] reconstructed as fp32 (hi + lo)."""
-    plan = self._plan(B, h, w)
+    split = self._lane_split(B) if getattr(self, "_last_call_lanes", False) else [(-1, 0, B)]
+    if len(split) > 1:
+        return torch.cat([_tap16_plan(self, self._plan(nb, h, w, lane), name, nb, h, w) for lane, _, nb in split])
+    return _tap16_plan(self, self._plan(B, h, w), name, B, h, w)
+
+
+def _tap16_plan(self, plan, name, B, h, w):
     pl, cols = _lib.Planes(), C.c_int32()
     _lib.check(self.lib.dcae_slice_loop_tap16(plan.handle, name.encode(), C.byref(pl), C.byref(cols)), "tap16")
     T, ld = B * h * w, int(pl.ld)

@@ -167,6 +167,29 @@ def test_batch_invariance_and_determinism(lively_params):
     assert torch.equal(a["symbols"][:, 1:], one["symbols"]) and torch.equal(a["indexes"][:, 1:], one["indexes"])
 
 
+@pytest.mark.parametrize("math", ["f16x3", "fp32"])
+def test_lanes_do_not_change_any_output_bit(math, lively_params):
+    """`forward` splits the batch over two plans / streams (lanes=2); every per-element output must be identical to
+    the single-plan run, for an odd batch too, and the bpp numerator must agree to float rounding."""
+    from dcae_b200 import EntropySliceLoop
+    gen = torch.Generator().manual_seed(77)
+    B, h, w = 3, 8, 12
+    y = (4 * torch.randn(B, 320, h, w, generator=gen)).cuda()
+    ls, lm = torch.randn(B, 320, h, w, generator=gen).cuda(), torch.randn(B, 320, h, w, generator=gen).cuda()
+    one = EntropySliceLoop(lively_params, device="cuda:0", math=math, lanes=1)
+    two = EntropySliceLoop(lively_params, device="cuda:0", math=math, lanes=2)
+    a = one.compress(y, ls, lm, with_likelihoods=True)
+    b = two.compress(y, ls, lm, with_likelihoods=True)
+    for k in ("means", "scales", "y_hat", "likelihoods", "symbols", "indexes"):
+        assert torch.equal(a[k], b[k]), k
+    assert abs(float(a["log2_lik_sum"]) - float(b["log2_lik_sum"])) <= 1e-5 * abs(float(a["log2_lik_sum"]))
+    nz = (torch.rand(B, 320, h, w, generator=gen) - 0.5).cuda()
+    a, b = one.forward(y, ls, lm, noise=nz), two.forward(y, ls, lm, noise=nz)
+    for k in ("means", "scales", "y_hat", "likelihoods"):
+        assert torch.equal(a[k], b[k]), k
+    assert torch.equal(one.tap("x2", B, h, w), two.tap("x2", B, h, w))
+
+
 def test_training_noise_forward_vs_oracle(lively_params):
     g = load_golden("slice_loop_b2_7x9")
     eng = engine(lively_params, "fp32")

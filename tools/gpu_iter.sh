@@ -12,8 +12,9 @@ run() { local name=$1 t=$2; shift 2
 : > gpurun_out/iter_summary.txt
 run it_gc    300 python -m pytest tests/test_gpu_gc.py -q -x -m gpu
 run it_ops   600 python -m pytest tests/test_gpu_ops.py -q -m gpu
-run it_loop  600 python -m pytest tests/test_gpu_slice_loop.py -q -m gpu -k "f16x3 or kodak or config"
+run it_loop  900 python -m pytest tests/test_gpu_slice_loop.py -q -m gpu
 run it_bench 600 python bench.py --no-cpu-baseline
+run it_bench1 600 python bench.py --no-cpu-baseline --lanes 1
 run it_layers 300 python tools/layer_times.py
 run it_dbg 300 python tools/f16_dbg.py
 exit 0
