@@ -47,6 +47,7 @@ ProfileScope::ProfileScope(int family, double work, void* s) : slot(-1), stream(
 ProfileScope::~ProfileScope() {
   if (slot >= 0) cudaEventRecord(g_prof[slot].b, (cudaStream_t)stream);
 }
+bool profiling_on() { return g_prof_on; }
 
 }  // namespace dcae
 
@@ -450,7 +451,7 @@ extern "C" int dcae_slice_loop_params(dcae_slice_loop* p, int32_t i, void* s) {
   // The two chains are independent (dcae.py:649-655) and write disjoint columns / buffers.  In planes mode no split
   // scratch is shared either, so the scale chain forks onto the side stream and joins before the caller continues.
   void* s2 = s;
-  if (p->pm && p->side) {
+  if (p->pm && p->side && !profiling_on()) {     // an instrumented step times every kernel ALONE (dcae_profile_start)
     s2 = p->side;
     DCAE_CUDA(cudaEventRecord(p->ev_fork, (cudaStream_t)s));
     DCAE_CUDA(cudaStreamWaitEvent(p->side, p->ev_fork, 0));

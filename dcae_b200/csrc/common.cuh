@@ -130,6 +130,8 @@ struct ProfileScope {
   void* stream;
 };
 
+bool profiling_on();
+
 // internal cross-file entry points
 int gemm_simt(const dcae_operand* a, const dcae_weight* w, const dcae_epilogue* e, cudaStream_t s);
 int gemm_tcgen05(const dcae_operand* a, const dcae_weight* w, const dcae_epilogue* e, int passes, cudaStream_t s);

@@ -7,7 +7,7 @@ import torch
 from dcae_b200.entropy_model import EntropySliceLoop
 from dcae_b200.params import init_entropy_params
 B, h, w = 16, 32, 48
-eng = EntropySliceLoop(init_entropy_params(0, "lively"), math="f16x3")
+eng = EntropySliceLoop(init_entropy_params(0, "lively"), math="f16x3", lanes=1)
 g = torch.Generator().manual_seed(1)
 x = [4 * torch.randn(B, 320, h, w, generator=g).cuda(), torch.randn(B, 320, h, w, generator=g).cuda(), torch.randn(B, 320, h, w, generator=g).cuda()]
 sys.stderr.write("=== step 1 (cold)\n")
