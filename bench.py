@@ -211,6 +211,8 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if os.environ.get("DCAE_BENCH_DEBUG"):
+            print(f"[rank {rank}] timed region {float(ms) / steps:.3f} ms/step", file=sys.stderr, flush=True)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         barrier()
@@ -218,9 +220,13 @@ def main():
 
     # the sampler starts BEFORE the warm-up (NVML start-up must not land inside the timed region)
     sampler = ClockSampler(local) if rank == 0 and not args.no_clock_sampler else None
-    for _ in range(max(args.warmup, 3)):
+    # warm-up: W steps (>= 3), and keep going until the device has been busy for ~1.5 s -- a fresh box needs that long
+    # to page in, ramp its clocks and settle under the power cap (three 15 ms steps do not)
+    n_warm, t_warm = 0, time.perf_counter()
+    while n_warm < max(args.warmup, 3) or time.perf_counter() - t_warm < 1.5:
         step_resident()
-    torch.cuda.synchronize()
+        torch.cuda.synchronize()
+        n_warm += 1
     if sampler:
         sampler.mark()
     ms_step, out = timed(step_resident, args.steps)
@@ -296,7 +302,8 @@ def main():
             "data": "synthetic",
             "config": {"workload": "DCAE entropy-model forward (slice loop), batch 16 synthetic Kodak-shaped 768x512 images per GPU (BASELINE config #2)",
                        "batch_per_gpu": B, "tokens_per_gpu": T, "math": args.math, "weights": "random-init (seeded, lively profile)",
-                       "l2": "no flush needed: per-step working set 1.8 GB >> 126 MB L2", "parallelism": f"{world} independent image shards", "lanes_per_gpu": args.lanes},
+                       "l2": "no flush needed: per-step working set 1.8 GB >> 126 MB L2", "parallelism": f"{world} independent image shards", "lanes_per_gpu": args.lanes,
+                       "warmup_steps_run": n_warm},
             "e2e": {"value": imgs / (ms_e2e * 1e-3), "unit": "images/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": pipe.h2d_bytes, "d2h_bytes_per_step": pipe.d2h_bytes,
                     "how": "dcae_b200.HostPipeline: pinned host tensors in and out, H2D / compute / D2H of consecutive batches overlapped on 3 streams (wall clock over the K steps, last result on the host)"},
