@@ -138,11 +138,7 @@ __device__ __forceinline__ void stage_f16(const float* v, int row, uint32_t stg)
     uint32_t hw[4], lw[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      unsigned short h0, l0, h1, l1;
-      f16_split(v[8 * c + 2 * q], h0, l0);
-      f16_split(v[8 * c + 2 * q + 1], h1, l1);
-      hw[q] = (uint32_t)h0 | ((uint32_t)h1 << 16);
-      lw[q] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+      f16_split2(v[8 * c + 2 * q], v[8 * c + 2 * q + 1], hw[q], lw[q]);
     }
     const uint32_t off = (uint32_t)((c ^ ((row >> 1) & 3)) << 4);
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(bh + off), "r"(hw[0]), "r"(hw[1]), "r"(hw[2]), "r"(hw[3]) : "memory");
