@@ -62,7 +62,9 @@ class Weight(C.Structure):
 
 class DictKV(C.Structure):
     _fields_ = [("Kh", c_f32p), ("Vh", c_f32p), ("Kh_hi", c_f32p), ("Kh_lo", c_f32p),
-                ("Vt_hi", c_f32p), ("Vt_lo", c_f32p), ("head_scale", c_f32p)]
+                ("Vt_hi", c_f32p), ("Vt_lo", c_f32p), ("head_scale", c_f32p),
+                ("K16_hi", C.c_void_p), ("K16_lo", C.c_void_p), ("Vt16_hi", C.c_void_p), ("Vt16_lo", C.c_void_p),
+                ("k_descale", C.c_float), ("v_descale", C.c_float)]
 
 
 class SliceWeights(C.Structure):
@@ -117,7 +119,7 @@ SIGNATURES = {
     "dcae_op_gelu": (C.c_int, [_P, _I64, _I32, _I64, _P, _I64, C.POINTER(Planes), _P]),
     "dcae_op_dwconv3x3": (C.c_int, [_P, _I64, _P, _P, _I32, _I32, _I32, _I32, _I32, _P, _I64, _P, _I64, C.POINTER(Planes), _P]),
     "dcae_op_spatial_gate": (C.c_int, [_P, _I64, _P, _I64, _P, _P, _I32, _I32, _I32, _I32, _P, _P, _I64, _P]),
-    "dcae_op_dict_attention": (C.c_int, [_P, _I64, C.POINTER(DictKV), _I64, _P, _I64, C.POINTER(Planes), C.c_int, _P]),
+    "dcae_op_dict_attention": (C.c_int, [_P, _I64, C.POINTER(Planes), C.POINTER(DictKV), _I64, _P, _I64, C.POINTER(Planes), C.c_int, _P]),
     "dcae_op_nchw_to_tokens": (C.c_int, [_P, _I32, _I32, _I64, _P, _I64, C.POINTER(Planes), _P]),
     "dcae_op_tokens_to_nchw": (C.c_int, [_P, _I64, _I32, _I32, _I64, _P, _P]),
     "dcae_op_tokens_to_nchw_i32": (C.c_int, [_P, _I64, _I32, _I32, _I64, _P, _P]),

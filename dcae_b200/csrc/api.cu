@@ -140,19 +140,22 @@ extern "C" int dcae_op_gemm(const dcae_operand* a, const dcae_weight* w, const d
   return DCAE_E_INVALID;
 }
 
-extern "C" int dcae_op_dict_attention(const float* q, int64_t q_ld, const dcae_dict_kv* kv, int64_t T, float* out,
-                                      int64_t out_ld, const dcae_planes* out16, int math, void* stream) {
+extern "C" int dcae_op_dict_attention(const float* q, int64_t q_ld, const dcae_planes* q16, const dcae_dict_kv* kv, int64_t T,
+                                      float* out, int64_t out_ld, const dcae_planes* out16, int math, void* stream) {
   const dcae_planes o16 = planes_or_null(out16);
-  DCAE_REQUIRE(q && kv && kv->Kh && kv->Vh && kv->head_scale && (out || o16.hi) && planes_ok(out16), "dcae_op_dict_attention: null pointer / bad planes");
+  const bool f16 = math == DCAE_MATH_F16X3;
+  DCAE_REQUIRE((f16 || q) && kv && kv->Kh && kv->Vh && kv->head_scale && (out || o16.hi) && planes_ok(out16) && planes_ok(q16),
+               "dcae_op_dict_attention: null pointer / bad planes");
   DCAE_REQUIRE(math != DCAE_MATH_FP32_SIMT || (out && !o16.hi), "dcae_op_dict_attention(fp32): fp16 planes are a tcgen05-path feature");
-  DCAE_REQUIRE(aligned16(q) && aligned16(out) && aligned16(kv->Kh) && aligned16(kv->Vh) && q_ld % 4 == 0 && out_ld % 4 == 0 && q_ld >= 640 && (!out || out_ld >= 640),
+  DCAE_REQUIRE(aligned16(q) && aligned16(out) && aligned16(kv->Kh) && aligned16(kv->Vh) && (f16 || (q_ld % 4 == 0 && q_ld >= 640)) &&
+                   out_ld % 4 == 0 && (!out || out_ld >= 640),
                "dcae_op_dict_attention: 16-byte alignment and ld >= 640 required");
   DCAE_REQUIRE(T >= 0 && T < (1ll << 31), "dcae_op_dict_attention: bad token count");
   ProfileScope prof(DCAE_PROF_ATTN, 327680.0 * (double)T, stream);
   switch (math) {
     case DCAE_MATH_FP32_SIMT:
       return dict_attention_simt(q, q_ld, kv->Kh, kv->Vh, kv->head_scale, T, out, out_ld, (cudaStream_t)stream);
-    case DCAE_MATH_F16X3:   // the attention core keeps the 3xTF32 formulation (2 % of the module's flops)
+    case DCAE_MATH_F16X3: return dict_attention_tcgen05_f16(q16, kv, T, out, out_ld, o16, (cudaStream_t)stream);
     case DCAE_MATH_TF32X3: return dict_attention_tcgen05(q, q_ld, kv, T, out, out_ld, o16, 3, (cudaStream_t)stream);
     case DCAE_MATH_TF32: return dict_attention_tcgen05(q, q_ld, kv, T, out, out_ld, o16, 1, (cudaStream_t)stream);
   }
@@ -406,10 +409,15 @@ static int run_dca(dcae_slice_loop* p, int i, void* s) {
   DCAE_TRY(dcae_op_spatial_gate(p->so.p, D, p->x0.p, D, W.res_scale_1, W.spatial_w7, D, p->B, p->h, p->w, p->stats.p, p->x1.p, D, s));
   // q = q_trans(lnx(x)); attention against the dictionary                    dcae.py:486-501
   DCAE_TRY(dcae_op_layernorm(p->x1.p, D, W.lnx_g, W.lnx_b, D, T, ln32, D, &lnp, s));
-  DCAE_TRY(gemm(p, opnd2(p, p->ln, D, p->lnp, 0, D, 1), W.q_trans, epi(W.q_trans_b, p->q.p, D), s));
+  {
+    dcae_epilogue e = epi(W.q_trans_b, p->q.p, D);
+    if (pm) { e.out = nullptr; e.out16 = pl(p->gap); }     // planes mode: q as fp16 planes in the (idle) GELU buffer
+    DCAE_TRY(gemm(p, opnd2(p, p->ln, D, p->lnp, 0, D, 1), W.q_trans, e, s));
+  }
   {
     const dcae_planes aop = pm ? pl(p->aop) : none;
-    DCAE_TRY(dcae_op_dict_attention(p->q.p, D, &W.kv, T, pm ? nullptr : p->ao.p, D, &aop, p->math, s));
+    const dcae_planes qp = pm ? pl(p->gap) : none;
+    DCAE_TRY(dcae_op_dict_attention(pm ? nullptr : p->q.p, D, &qp, &W.kv, T, pm ? nullptr : p->ao.p, D, &aop, p->math, s));
   }
   // output = linear(output) + res_scale_2(shortcut)                          dcae.py:503
   {

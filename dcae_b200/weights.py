@@ -171,4 +171,9 @@ class PackedWeights:
             self._keep += [hi, lo]
             setattr(kv, hi_name, hi.data_ptr())
             setattr(kv, lo_name, lo.data_ptr())
+        # fp16 planes for the f16x3 attention kernel: K as the [128, 640] matrix itself, V transposed [640, 128]
+        k_hi, k_lo, _, kv.k_descale = f16_weight_planes(lib, k.contiguous(), 1, s)
+        v_hi, v_lo, _, kv.v_descale = f16_weight_planes(lib, d.t().contiguous(), 1, s)
+        kv.K16_hi, kv.K16_lo, kv.Vt16_hi, kv.Vt16_lo = k_hi.data_ptr(), k_lo.data_ptr(), v_hi.data_ptr(), v_lo.data_ptr()
+        self._keep += [k_hi, k_lo, v_hi, v_lo]
         return kv

@@ -190,14 +190,21 @@ int dcae_op_spatial_gate(const float* s_out, int64_t s_ld, const float* x0, int6
  *   Kh, Vh            [20, 128, 32] fp32  (K = k(LN(dt)) and V = LN(dt), split per head)
  *   Kh_hi, Kh_lo      TF32 split of Kh                      (tcgen05 paths)
  *   Vt_hi, Vt_lo      TF32 split of Vh transposed per head, [20, 32, 128]
- * math FP32_SIMT = FFMA kernel; TF32X3 / TF32 = kernel 1 (tcgen05 + TMEM, softmax in registers). */
+ *   K16_hi, K16_lo    fp16 planes of K * 2^e as the [128, 640] matrix k(LN(dt)) itself (columns = (head, dim)),
+ *                     k_descale = 2^-e                       (DCAE_MATH_F16X3)
+ *   Vt16_hi, Vt16_lo  fp16 planes of LN(dt)^T * 2^e', [640, 128], v_descale = 2^-e'
+ * math FP32_SIMT = FFMA kernel; TF32X3 / TF32 = kernel 1 (tcgen05 + TMEM, softmax in registers) on the fp32 query;
+ * F16X3 = kernel 1 on fp16 planes: the query is read from q16 (q may be NULL), e.g. the q_trans GEMM's out16. */
 typedef struct {
   const float* Kh; const float* Vh;
   const float* Kh_hi; const float* Kh_lo;
   const float* Vt_hi; const float* Vt_lo;
   const float* head_scale;     /* [20] learned per-head scale (dcae.py:457,498) */
+  const void* K16_hi; const void* K16_lo;
+  const void* Vt16_hi; const void* Vt16_lo;
+  float k_descale, v_descale;
 } dcae_dict_kv;
-int dcae_op_dict_attention(const float* q, int64_t q_ld, const dcae_dict_kv* kv, int64_t T, float* out,
+int dcae_op_dict_attention(const float* q, int64_t q_ld, const dcae_planes* q16, const dcae_dict_kv* kv, int64_t T, float* out,
                            int64_t out_ld, const dcae_planes* out16, int math, void* stream);
 /* 'b c h w -> (b h w) c' and back, for a channel window of the token-major buffer. */
 int dcae_op_nchw_to_tokens(const float* src, int32_t B, int32_t C, int64_t HW, float* dst, int64_t dst_ld,

@@ -109,9 +109,24 @@ def dict_attention(q, Kh, Vh, head_scale, math="fp32", planes=False):
     vhi, vlo = split_weight(Vt)
     kv = _lib.DictKV(Kh.data_ptr(), Vh.data_ptr(), khi.data_ptr(), klo.data_ptr(), vhi.data_ptr(), vlo.data_ptr(),
                      head_scale.data_ptr())
+    q16 = keep = None
+    if math == "f16x3":          # the f16x3 kernel reads fp16 planes: q, K as [128, 640], V^T as [640, 128]
+        from dcae_b200.weights import f16_weight_planes
+        s = _s(q.device)
+        k2d = Kh.permute(1, 0, 2).reshape(Kh.shape[1], -1).contiguous()                 # 'e n c -> n (e c)'
+        vt2d = Vh.permute(0, 2, 1).reshape(-1, Vh.shape[1]).contiguous()                # 'e n c -> (e c) n'
+        k_hi, k_lo, _, kv.k_descale = f16_weight_planes(lib, k2d, 1, s)
+        v_hi, v_lo, _, kv.v_descale = f16_weight_planes(lib, vt2d, 1, s)
+        kv.K16_hi, kv.K16_lo, kv.Vt16_hi, kv.Vt16_lo = k_hi.data_ptr(), k_lo.data_ptr(), v_hi.data_ptr(), v_lo.data_ptr()
+        q_hi = q.half()
+        q_lo = (q - q_hi.float()).half()
+        q16 = _lib.Planes(q_hi.data_ptr(), q_lo.data_ptr(), q_hi.stride(0))
+        keep = (k_hi, k_lo, v_hi, v_lo, q_hi, q_lo)
     p16, hi, lo = _planes(q.shape[0], q.shape[1], q.device) if planes else (None, None, None)
-    _lib.check(lib.dcae_op_dict_attention(q.data_ptr(), q.stride(0), kv, q.shape[0], out.data_ptr(), out.stride(0), p16,
+    _lib.check(lib.dcae_op_dict_attention(q.data_ptr(), q.stride(0), q16, kv, q.shape[0], out.data_ptr(), out.stride(0), p16,
                                           _lib.MATH[math], _s(q.device)), "dcae_op_dict_attention")
+    torch.cuda.synchronize()
+    del keep
     return (out, hi, lo) if planes else out
 
 

@@ -131,8 +131,8 @@ def test_spatial_gate():
     assert rel_err(got.cpu(), tok(want)) < 2e-6
 
 
-@pytest.mark.parametrize("math", ["fp32", "tf32x3", "tf32"])
-@pytest.mark.parametrize("T", [300, 128, 4133])
+@pytest.mark.parametrize("math", ["fp32", "tf32x3", "f16x3", "tf32"])
+@pytest.mark.parametrize("T", [300, 128, 4133, 24576])
 def test_dict_attention_core(math, T):
     """dcae.py:489-501.  Logits of a few units so that the softmax is neither flat nor one-hot."""
     q = torch.randn(T, 640, generator=g(31))
@@ -143,7 +143,7 @@ def test_dict_attention_core(math, T):
     sim = torch.einsum("enc,edc->end", qh, Kh) * sc[:, None, None]
     want = torch.einsum("end,edc->enc", torch.softmax(sim, -1), Vh).permute(1, 0, 2).reshape(T, 640)
     got = K.dict_attention(q.cuda(), Kh.cuda(), Vh.cuda(), sc.cuda(), math=math)
-    assert rel_err(got.cpu(), want) < {"fp32": 2e-6, "tf32x3": 1e-5, "tf32": 2e-2}[math]
+    assert rel_err(got.cpu(), want) < {"fp32": 2e-6, "tf32x3": 1e-5, "f16x3": 1e-5, "tf32": 2e-2}[math]
     again = K.dict_attention(q.cuda(), Kh.cuda(), Vh.cuda(), sc.cuda(), math=math)
     assert torch.equal(got, again)
 
@@ -181,8 +181,9 @@ def test_producers_write_fp16_planes():
     assert _planes_close(hi, lo, out) and torch.equal(out.cpu(), tok(xi))
     q = torch.randn(300, 640, generator=g(46))
     Kh, Vh = torch.randn(20, 128, 32, generator=g(47)) * 0.5, torch.randn(20, 128, 32, generator=g(48))
-    out, hi, lo = K.dict_attention(q.cuda(), Kh.cuda(), Vh.cuda(), (torch.rand(20, generator=g(49)) + 0.5).cuda(), math="tf32x3", planes=True)
-    assert _planes_close(hi, lo, out)
+    for math in ("tf32x3", "f16x3"):
+        out, hi, lo = K.dict_attention(q.cuda(), Kh.cuda(), Vh.cuda(), (torch.rand(20, generator=g(49)) + 0.5).cuda(), math=math, planes=True)
+        assert _planes_close(hi, lo, out)
 
 
 def test_f16x3_gemm_reads_and_writes_planes_directly():
