@@ -106,8 +106,13 @@ dict_attention_f16_kernel(const __grid_constant__ CUtensorMap map_qh, const __gr
   // stage (one head pair): [Q_hi | Q_lo | K_hi | K_lo | Vt_hi chunk0, chunk1 | Vt_lo chunk0, chunk1]
   constexpr uint32_t OFF_QL = AF_QK_BYTES, OFF_KH = 2 * AF_QK_BYTES, OFF_KL = 3 * AF_QK_BYTES;
   constexpr uint32_t OFF_VH = 4 * AF_QK_BYTES, OFF_VL = OFF_VH + 2 * AF_V_BYTES;
-  const int my_tiles = (p.tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-  const int total = my_tiles * AF_HEADS;     // (tile, head) work items of this CTA, in order; always even
+  // Work item = one HEAD PAIR of one tile (1 920 items at config #2, 13 per CTA): splitting at tile granularity
+  // leaves 192 tiles on 148 SMs, i.e. 44 CTAs with two tiles and 104 with one.  Item i of this CTA is the global
+  // pair blockIdx.x + i * gridDim.x -> (tile, head pair); the head-step pipeline runs across items unchanged.
+  constexpr int HP = AF_HEADS / 2;
+  const int all_pairs = p.tiles * HP;
+  const int my_pairs = (all_pairs - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int total = my_pairs * 2;            // head steps of this CTA, in order; always even
 
   if (warp == 0) {
     if (lane == 0) {
@@ -115,7 +120,8 @@ dict_attention_f16_kernel(const __grid_constant__ CUtensorMap map_qh, const __gr
       for (int pr = 0; pr < total / 2; ++pr) {
         const int stage = pr % AF_STAGES;
         const uint32_t phase = (pr / AF_STAGES) & 1;
-        const int tile = blockIdx.x + (pr / (AF_HEADS / 2)) * gridDim.x, hp = pr % (AF_HEADS / 2);
+        const int gp = (int)blockIdx.x + pr * (int)gridDim.x;
+        const int tile = gp / HP, hp = gp % HP;
         mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
         const uint32_t sb = smem0 + stage * AF_STAGE;
         const uint32_t fb = smem_u32(&full_bar[stage]);
@@ -186,7 +192,8 @@ dict_attention_f16_kernel(const __grid_constant__ CUtensorMap map_qh, const __gr
     constexpr int HC = AF_ND / 2;     // columns per thread
     auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory"); };
     auto write_out = [&](int g) {
-      const int tile = blockIdx.x + (g / AF_HEADS) * gridDim.x, head = g % AF_HEADS;
+      const int gp = (int)blockIdx.x + (g >> 1) * (int)gridDim.x;
+      const int tile = gp / HP, head = (gp % HP) * 2 + (g & 1);
       const float inv = p.v_descale / (xl[g & 1][0][r] + xl[g & 1][1][r]);
       mbar_wait(smem_u32(&o_full[g & 1]), (g >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -209,7 +216,8 @@ dict_attention_f16_kernel(const __grid_constant__ CUtensorMap map_qh, const __gr
       }
     };
     for (int g = 0; g < total; ++g) {
-      const int head = g % AF_HEADS, b = g & 1;
+      const int b = g & 1;
+      const int head = (((int)blockIdx.x + (g >> 1) * (int)gridDim.x) % HP) * 2 + b;
       // softmax(sim * scale) = 2^(t - max t) / sum, t = acc * (k_descale * scale * log2 e)
       const float sc = __ldg(p.head_scale + head) * p.k_descale * 1.4426950408889634f;
       mbar_wait(smem_u32(&s_full[b]), (g >> 1) & 1);
@@ -320,7 +328,7 @@ int dict_attention_tcgen05_f16(const dcae_planes* q16, const dcae_dict_kv* kv, i
     attr_err = cudaFuncSetAttribute(dict_attention_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AF_STAGES * AF_STAGE + 1024);
   });
   DCAE_CUDA(attr_err);
-  const int ctas = p.tiles < num_sms() ? p.tiles : num_sms();
+  const int ctas = p.tiles * (AF_HEADS / 2) < num_sms() ? p.tiles * (AF_HEADS / 2) : num_sms();
   dict_attention_f16_kernel<<<ctas, AF_THREADS, smem, s>>>(mqh, mql, mkh, mkl, mvh, mvl, p);
   DCAE_LAUNCH_CHECK();
   return DCAE_OK;
