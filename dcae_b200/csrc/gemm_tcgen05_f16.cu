@@ -238,7 +238,7 @@ __device__ __forceinline__ void gemm_f16x3_body(const CUtensorMap& map_ah, const
   __shared__ __align__(8) uint64_t tmem_full_bar[2], tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_slot;
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp: provably uniform
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const long long t_entry = DBG ? clock64() : 0;
   if (DBG && threadIdx.x == 32) {
@@ -246,7 +246,7 @@ __device__ __forceinline__ void gemm_f16x3_body(const CUtensorMap& map_ah, const
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
     p.dbg[blockIdx.x * 24 + 16] = gt;
   }
-  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const uint32_t rank = PAIR ? __shfl_sync(0xffffffffu, cluster_ctarank(), 0) : 0u;
   const bool leader = rank == 0;
   const int unit = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;          // which persistent worker (CTA or pair)
   const int nunits = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
@@ -299,8 +299,8 @@ __device__ __forceinline__ void gemm_f16x3_body(const CUtensorMap& map_ah, const
 
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_CTRL));
-    if (warp == 0 && lane == 0) {
-      // ===================== TMA producer =====================
+    if (warp == 0) {
+      // ===================== TMA producer (warp-uniform; one elected lane issues) =====================
       int stage = 0;
       uint32_t phase = 0;
       long long w_empty = 0;
@@ -316,33 +316,36 @@ __device__ __forceinline__ void gemm_f16x3_body(const CUtensorMap& map_ah, const
           const int c = (kb - tap * p.cblk_per_tap) * BK16;
           int dy = 0, dx = 0;
           if (p.taps == 9) { dy = tap / 3 - 1; dx = tap % 3 - 1; }
-          if (PAIR) {
-            if (leader) mbar_expect_tx(fb, 2 * (2 * A16_BYTES + 2 * p.b_bytes));      // bytes landing in BOTH CTAs
-            const int nrow = n0 + (int)rank * (p.BN >> 1);
-            tma_load_4d_2sm(sbase, &map_ah, fb, c, x0 + dx, y0 + dy, b);
-            tma_load_4d_2sm(sbase + off_al, &map_al, fb, c, x0 + dx, y0 + dy, b);
-            tma_load_2d_2sm(sbase + off_bh, &map_bh, fb, kb * BK16, nrow);
-            tma_load_2d_2sm(sbase + off_bl, &map_bl, fb, kb * BK16, nrow);
-          } else {
-            mbar_expect_tx(fb, 2 * A16_BYTES + 2 * p.b_bytes);
-            tma_load_4d(sbase, &map_ah, fb, c, x0 + dx, y0 + dy, b);
-            tma_load_4d(sbase + off_al, &map_al, fb, c, x0 + dx, y0 + dy, b);
-            tma_load_2d(sbase + off_bh, &map_bh, fb, kb * BK16, n0);
-            tma_load_2d(sbase + off_bl, &map_bl, fb, kb * BK16, n0);
+          const int nrow = n0 + (int)rank * (p.BN >> 1);
+          if (elect_one()) {
+            if (PAIR) {
+              if (leader) mbar_expect_tx(fb, 2 * (2 * A16_BYTES + 2 * p.b_bytes));      // bytes landing in BOTH CTAs
+              tma_load_4d_2sm(sbase, &map_ah, fb, c, x0 + dx, y0 + dy, b);
+              tma_load_4d_2sm(sbase + off_al, &map_al, fb, c, x0 + dx, y0 + dy, b);
+              tma_load_2d_2sm(sbase + off_bh, &map_bh, fb, kb * BK16, nrow);
+              tma_load_2d_2sm(sbase + off_bl, &map_bl, fb, kb * BK16, nrow);
+            } else {
+              mbar_expect_tx(fb, 2 * A16_BYTES + 2 * p.b_bytes);
+              tma_load_4d(sbase, &map_ah, fb, c, x0 + dx, y0 + dy, b);
+              tma_load_4d(sbase + off_al, &map_al, fb, c, x0 + dx, y0 + dy, b);
+              tma_load_2d(sbase + off_bh, &map_bh, fb, kb * BK16, n0);
+              tma_load_2d(sbase + off_bl, &map_bl, fb, kb * BK16, n0);
+            }
           }
+          __syncwarp();
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
-      if (DBG) p.dbg[blockIdx.x * 24 + 0] = (unsigned long long)w_empty;
-    } else if (warp == 1 && lane == 0 && leader) {
-      // ===================== MMA issuer (the leader CTA of a pair) =====================
+      if (DBG && lane == 0) p.dbg[blockIdx.x * 24 + 0] = (unsigned long long)w_empty;
+    } else if (warp == 1 && leader) {
+      // ===================== MMA issuer (the leader CTA of a pair; warp-uniform, one elected lane issues) =====================
       // D = F32 (bit 4), A = B = F16 (format 0), K-major, N >> 3 at bit 17, M >> 4 at bit 24
       const uint32_t idesc = (1u << 4) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(((PAIR ? 2 : 1) * BM) >> 4) << 24);
       int stage = 0;
       uint32_t phase = 0, gchunk = 0;
       long long w_full = 0, w_tmem = 0, n_kb = 0, n_tiles = 0;
       const long long t_start = clock64();
-      if (DBG) p.dbg[blockIdx.x * 24 + 12] = (unsigned long long)(t_start - t_entry);
+      if (DBG && lane == 0) p.dbg[blockIdx.x * 24 + 12] = (unsigned long long)(t_start - t_entry);
       for (int t = unit; t < p.total_tiles; t += nunits) {
         ++n_tiles;
         for (int ck = 0; ck < n_chunks; ++ck, ++gchunk) {
@@ -360,28 +363,34 @@ __device__ __forceinline__ void gemm_f16x3_body(const CUtensorMap& map_ah, const
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t sbase = smem0 + stage * p.stage_bytes;
             const uint32_t first = (kb == ck * p.chunk_kb) ? 0u : 1u;
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < BK16 / UMMA_K16; ++k) {
-              const uint32_t koff = k * UMMA_K16 * 2;
-              const uint64_t a_hi = make_smem_desc(sbase + koff), a_lo = make_smem_desc(sbase + off_al + koff);
-              const uint64_t b_hi = make_smem_desc(sbase + off_bh + koff), b_lo = make_smem_desc(sbase + off_bl + koff);
-              if (PAIR) {
-                mma_f16_2sm(tmem_acc, a_lo, b_hi, idesc, first | (uint32_t)(k != 0));
-                mma_f16_2sm(tmem_acc, a_hi, b_lo, idesc, 1);
-                mma_f16_2sm(tmem_acc, a_hi, b_hi, idesc, 1);
-              } else {
-                mma_f16(tmem_acc, a_lo, b_hi, idesc, first | (uint32_t)(k != 0));
-                mma_f16(tmem_acc, a_hi, b_lo, idesc, 1);
-                mma_f16(tmem_acc, a_hi, b_hi, idesc, 1);
+              for (int k = 0; k < BK16 / UMMA_K16; ++k) {
+                const uint32_t koff = k * UMMA_K16 * 2;
+                const uint64_t a_hi = make_smem_desc(sbase + koff), a_lo = make_smem_desc(sbase + off_al + koff);
+                const uint64_t b_hi = make_smem_desc(sbase + off_bh + koff), b_lo = make_smem_desc(sbase + off_bl + koff);
+                if (PAIR) {
+                  mma_f16_2sm(tmem_acc, a_lo, b_hi, idesc, first | (uint32_t)(k != 0));
+                  mma_f16_2sm(tmem_acc, a_hi, b_lo, idesc, 1);
+                  mma_f16_2sm(tmem_acc, a_hi, b_hi, idesc, 1);
+                } else {
+                  mma_f16(tmem_acc, a_lo, b_hi, idesc, first | (uint32_t)(k != 0));
+                  mma_f16(tmem_acc, a_hi, b_lo, idesc, 1);
+                  mma_f16(tmem_acc, a_hi, b_hi, idesc, 1);
+                }
               }
+              if (PAIR) mma_commit_2sm(smem_u32(&empty_bar[stage])); else mma_commit(smem_u32(&empty_bar[stage]));
             }
-            if (PAIR) mma_commit_2sm(smem_u32(&empty_bar[stage])); else mma_commit(smem_u32(&empty_bar[stage]));
+            __syncwarp();
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
-          if (PAIR) mma_commit_2sm(smem_u32(&tmem_full_bar[buf])); else mma_commit(smem_u32(&tmem_full_bar[buf]));
+          if (elect_one()) {
+            if (PAIR) mma_commit_2sm(smem_u32(&tmem_full_bar[buf])); else mma_commit(smem_u32(&tmem_full_bar[buf]));
+          }
+          __syncwarp();
         }
       }
-      if (DBG) {
+      if (DBG && lane == 0) {
         unsigned long long* d = p.dbg + blockIdx.x * 24;
         d[1] = (unsigned long long)w_full; d[2] = (unsigned long long)w_tmem; d[3] = (unsigned long long)(clock64() - t_start);
         d[4] = (unsigned long long)n_kb; d[5] = (unsigned long long)n_tiles;

@@ -53,6 +53,15 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// One lane of a CONVERGED warp.  The tcgen05 / TMA issue roles run warp-uniform and only the issue instructions sit under
+// this predicate: issued from `if (lane == 0)` instead, every operand of UTCHMMA / UTMALDG (they take uniform registers)
+// goes through a VOTEU / ELECT / R2UR.BROADCAST waterfall loop -- measured 14 SASS instructions per MMA for the lone
+// issuing thread = 84-108 cycles per 64-cycle MMA.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr) {
   // K-major, SWIZZLE_128B: rows of 128 B, 8-row atoms 1024 B apart (SBO), LBO unused (=1), version 1
   uint64_t d = 0;
