@@ -78,7 +78,7 @@ dict_attention_f16_kernel(const __grid_constant__ CUtensorMap map_qh, const __gr
   __shared__ uint32_t tmem_base_slot;
   __shared__ float xm[2][2][AF_M], xl[2][2][AF_M];    // row max / row sum of each column half, double-buffered by head parity
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp: provably uniform
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
 
   if (threadIdx.x == 0) {
@@ -115,8 +115,8 @@ dict_attention_f16_kernel(const __grid_constant__ CUtensorMap map_qh, const __gr
   const int total = my_pairs * 2;            // head steps of this CTA, in order; always even
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ===================== TMA producer: one stage per head pair =====================
+    {
+      // ===================== TMA producer: one stage per head pair (warp-uniform, one elected lane issues) =====================
       for (int pr = 0; pr < total / 2; ++pr) {
         const int stage = pr % AF_STAGES;
         const uint32_t phase = (pr / AF_STAGES) & 1;
@@ -125,21 +125,24 @@ dict_attention_f16_kernel(const __grid_constant__ CUtensorMap map_qh, const __gr
         mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
         const uint32_t sb = smem0 + stage * AF_STAGE;
         const uint32_t fb = smem_u32(&full_bar[stage]);
-        mbar_expect_tx(fb, AF_STAGE);
-        tma_load_2d(sb, &map_qh, fb, hp * 64, tile * AF_M);
-        tma_load_2d(sb + OFF_QL, &map_ql, fb, hp * 64, tile * AF_M);
-        tma_load_2d(sb + OFF_KH, &map_kh, fb, hp * 64, 0);
-        tma_load_2d(sb + OFF_KL, &map_kl, fb, hp * 64, 0);
+        if (elect_one()) {
+          mbar_expect_tx(fb, AF_STAGE);
+          tma_load_2d(sb, &map_qh, fb, hp * 64, tile * AF_M);
+          tma_load_2d(sb + OFF_QL, &map_ql, fb, hp * 64, tile * AF_M);
+          tma_load_2d(sb + OFF_KH, &map_kh, fb, hp * 64, 0);
+          tma_load_2d(sb + OFF_KL, &map_kl, fb, hp * 64, 0);
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {      // V^T rows of the pair, entries 64c .. 64c + 63
-          tma_load_2d(sb + OFF_VH + c * AF_V_BYTES, &map_vh, fb, c * 64, hp * 64);
-          tma_load_2d(sb + OFF_VL + c * AF_V_BYTES, &map_vl, fb, c * 64, hp * 64);
+          for (int c = 0; c < 2; ++c) {      // V^T rows of the pair, entries 64c .. 64c + 63
+            tma_load_2d(sb + OFF_VH + c * AF_V_BYTES, &map_vh, fb, c * 64, hp * 64);
+            tma_load_2d(sb + OFF_VL + c * AF_V_BYTES, &map_vl, fb, c * 64, hp * 64);
+          }
         }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===================== MMA issuer =====================
+    {
+      // ===================== MMA issuer (warp-uniform, one elected lane issues) =====================
       // D = F32 (bit 4), A = B = F16 (format 0), K-major, N >> 3 at bit 17, M >> 4 at bit 24
       const uint32_t idesc_s = (1u << 4) | ((uint32_t)(AF_ND >> 3) << 17) | ((uint32_t)(AF_M >> 4) << 24);
       const uint32_t idesc_o = (1u << 4) | ((uint32_t)(AF_HD >> 3) << 17) | ((uint32_t)(AF_M >> 4) << 24);
@@ -149,16 +152,19 @@ dict_attention_f16_kernel(const __grid_constant__ CUtensorMap map_qh, const __gr
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t sb = smem0 + stage * AF_STAGE;
         const uint32_t d = tmem + TF_SP + (uint32_t)(g & 1) * 128;
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
-          const uint32_t ko = (uint32_t)((g & 1) * 2 + k) * 32;    // this head's 32 dims inside the pair's 128-byte rows
-          const uint64_t q_hi = make_smem_desc(sb + ko), q_lo = make_smem_desc(sb + OFF_QL + ko);
-          const uint64_t k_hi = make_smem_desc(sb + OFF_KH + ko), k_lo = make_smem_desc(sb + OFF_KL + ko);
-          mma_f16_ss(d, q_lo, k_hi, idesc_s, k != 0);
-          mma_f16_ss(d, q_hi, k_lo, idesc_s, 1);
-          mma_f16_ss(d, q_hi, k_hi, idesc_s, 1);
+          for (int k = 0; k < 2; ++k) {
+            const uint32_t ko = (uint32_t)((g & 1) * 2 + k) * 32;    // this head's 32 dims inside the pair's 128-byte rows
+            const uint64_t q_hi = make_smem_desc(sb + ko), q_lo = make_smem_desc(sb + OFF_QL + ko);
+            const uint64_t k_hi = make_smem_desc(sb + OFF_KH + ko), k_lo = make_smem_desc(sb + OFF_KL + ko);
+            mma_f16_ss(d, q_lo, k_hi, idesc_s, k != 0);
+            mma_f16_ss(d, q_hi, k_lo, idesc_s, 1);
+            mma_f16_ss(d, q_hi, k_hi, idesc_s, 1);
+          }
+          mma_commit(smem_u32(&s_full[g & 1]));
         }
-        mma_commit(smem_u32(&s_full[g & 1]));
+        __syncwarp();
       };
       if (total > 0) { issue_s(0); issue_s(1); }
       for (int g = 0; g < total; ++g) {
@@ -169,17 +175,20 @@ dict_attention_f16_kernel(const __grid_constant__ CUtensorMap map_qh, const __gr
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t pa = tmem + TF_SP + (uint32_t)b * 128;                  // P_hi words at +0, P_lo words at +64
         const uint32_t od = tmem + TF_O + (uint32_t)b * 32;
+        if (elect_one()) {
 #pragma unroll
-        for (int j = 0; j < AF_ND / 16; ++j) {
-          // V^T rows of this head: 32 rows = 4 KB into the pair's chunk; k-step j: chunk j >> 2, 32 bytes per step
-          const uint32_t vo = (uint32_t)(j >> 2) * AF_V_BYTES + (uint32_t)b * 4096 + (uint32_t)(j & 3) * 32;
-          const uint64_t v_hi = make_smem_desc(sb + OFF_VH + vo), v_lo = make_smem_desc(sb + OFF_VL + vo);
-          mma_f16_ts(od, pa + 64 + j * 8, v_hi, idesc_o, j != 0);
-          mma_f16_ts(od, pa + j * 8, v_lo, idesc_o, 1);
-          mma_f16_ts(od, pa + j * 8, v_hi, idesc_o, 1);
+          for (int j = 0; j < AF_ND / 16; ++j) {
+            // V^T rows of this head: 32 rows = 4 KB into the pair's chunk; k-step j: chunk j >> 2, 32 bytes per step
+            const uint32_t vo = (uint32_t)(j >> 2) * AF_V_BYTES + (uint32_t)b * 4096 + (uint32_t)(j & 3) * 32;
+            const uint64_t v_hi = make_smem_desc(sb + OFF_VH + vo), v_lo = make_smem_desc(sb + OFF_VL + vo);
+            mma_f16_ts(od, pa + 64 + j * 8, v_hi, idesc_o, j != 0);
+            mma_f16_ts(od, pa + j * 8, v_lo, idesc_o, 1);
+            mma_f16_ts(od, pa + j * 8, v_hi, idesc_o, 1);
+          }
+          mma_commit(smem_u32(&o_full[b]));
+          if (b == 1) mma_commit(smem_u32(&empty_bar[stage]));                 // both heads of the pair are done with the stage
         }
-        mma_commit(smem_u32(&o_full[b]));
-        if (b == 1) mma_commit(smem_u32(&empty_bar[stage]));                   // both heads of the pair are done with the stage
+        __syncwarp();
         if (g + 2 < total) issue_s(g + 2);                                      // overwrites P(g): in order behind PV(g)
       }
     }
