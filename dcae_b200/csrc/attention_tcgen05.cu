@@ -51,7 +51,7 @@ dict_attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const _
   __shared__ uint32_t tmem_base_slot;
   __shared__ float xm[2][2][AT_M], xl[2][2][AT_M];    // row max / row sum of each column half, double-buffered by head parity
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp: provably uniform
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
 
   if (threadIdx.x == 0) {
@@ -85,8 +85,8 @@ dict_attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const _
   const int total = my_tiles * AT_HEADS;     // (tile, head) work items of this CTA, in order
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ===================== TMA producer =====================
+    {
+      // ===================== TMA producer (warp-uniform; one elected lane issues, see elect_one) =====================
       for (int g = 0; g < total; ++g) {
         const int stage = g % p.stages;
         const uint32_t phase = (g / p.stages) & 1;
@@ -94,20 +94,23 @@ dict_attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const _
         mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
         const uint32_t sb = smem0 + stage * p.stage_bytes;
         const uint32_t fb = smem_u32(&full_bar[stage]);
-        mbar_expect_tx(fb, (PASSES == 3 ? 5 : 3) * AT_TILE);
-        tma_load_2d(sb, &map_q, fb, head * AT_HD, tile * AT_M);
-        tma_load_2d(sb + off_khi, &map_khi, fb, 0, head * AT_ND);
-        if (PASSES == 3) tma_load_2d(sb + off_klo, &map_klo, fb, 0, head * AT_ND);
+        if (elect_one()) {
+          mbar_expect_tx(fb, (PASSES == 3 ? 5 : 3) * AT_TILE);
+          tma_load_2d(sb, &map_q, fb, head * AT_HD, tile * AT_M);
+          tma_load_2d(sb + off_khi, &map_khi, fb, 0, head * AT_ND);
+          if (PASSES == 3) tma_load_2d(sb + off_klo, &map_klo, fb, 0, head * AT_ND);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {      // V^T [32 x 128] as four K-major [32 x 32] chunks
-          tma_load_2d(sb + off_vhi + c * 4096, &map_vhi, fb, c * 32, head * AT_HD);
-          if (PASSES == 3) tma_load_2d(sb + off_vlo + c * 4096, &map_vlo, fb, c * 32, head * AT_HD);
+          for (int c = 0; c < 4; ++c) {      // V^T [32 x 128] as four K-major [32 x 32] chunks
+            tma_load_2d(sb + off_vhi + c * 4096, &map_vhi, fb, c * 32, head * AT_HD);
+            if (PASSES == 3) tma_load_2d(sb + off_vlo + c * 4096, &map_vlo, fb, c * 32, head * AT_HD);
+          }
         }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===================== MMA issuer =====================
+    {
+      // ===================== MMA issuer (warp-uniform; one elected lane issues) =====================
       const uint32_t idesc_s = make_idesc_tf32(AT_M, AT_ND);    // S: N = 128
       const uint32_t idesc_o = make_idesc_tf32(AT_M, AT_HD);    // O: N = 32
       auto issue_s = [&](int g) {
@@ -116,20 +119,23 @@ dict_attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const _
         mbar_wait(smem_u32(&s_free), (g & 1) ^ 1);               // softmax warps hold S(g-1) in registers
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t sb = smem0 + stage * p.stage_bytes;
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < AT_HD / 8; ++k) {
-          const uint32_t ko = k * 32;
-          const uint64_t q_hi = make_smem_desc(sb + ko), k_hi = make_smem_desc(sb + off_khi + ko);
-          if (PASSES == 3) {
-            const uint64_t q_lo = make_smem_desc(sb + off_qlo + ko), k_lo = make_smem_desc(sb + off_klo + ko);
-            mma_tf32(tmem + TM_S, q_lo, k_hi, idesc_s, k != 0);
-            mma_tf32(tmem + TM_S, q_hi, k_lo, idesc_s, 1);
-            mma_tf32(tmem + TM_S, q_hi, k_hi, idesc_s, 1);
-          } else {
-            mma_tf32(tmem + TM_S, q_hi, k_hi, idesc_s, k != 0);
+          for (int k = 0; k < AT_HD / 8; ++k) {
+            const uint32_t ko = k * 32;
+            const uint64_t q_hi = make_smem_desc(sb + ko), k_hi = make_smem_desc(sb + off_khi + ko);
+            if (PASSES == 3) {
+              const uint64_t q_lo = make_smem_desc(sb + off_qlo + ko), k_lo = make_smem_desc(sb + off_klo + ko);
+              mma_tf32(tmem + TM_S, q_lo, k_hi, idesc_s, k != 0);
+              mma_tf32(tmem + TM_S, q_hi, k_lo, idesc_s, 1);
+              mma_tf32(tmem + TM_S, q_hi, k_hi, idesc_s, 1);
+            } else {
+              mma_tf32(tmem + TM_S, q_hi, k_hi, idesc_s, k != 0);
+            }
           }
+          mma_commit(smem_u32(&s_full));
         }
-        mma_commit(smem_u32(&s_full));
+        __syncwarp();
       };
       if (total > 0) issue_s(0);
       for (int g = 0; g < total; ++g) {
@@ -138,21 +144,24 @@ dict_attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const _
         const uint32_t sb = smem0 + stage * p.stage_bytes;
         mbar_wait(smem_u32(&p_ready), g & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (elect_one()) {
 #pragma unroll
-        for (int j = 0; j < AT_ND / 8; ++j) {
-          const uint32_t vo = (j >> 2) * 4096 + (j & 3) * 32;
-          const uint64_t v_hi = make_smem_desc(sb + off_vhi + vo);
-          if (PASSES == 3) {
-            const uint64_t v_lo = make_smem_desc(sb + off_vlo + vo);
-            mma_tf32_ts(tmem + TM_O, tmem + TM_PLO + j * 8, v_hi, idesc_o, j != 0);
-            mma_tf32_ts(tmem + TM_O, tmem + TM_PHI + j * 8, v_lo, idesc_o, 1);
-            mma_tf32_ts(tmem + TM_O, tmem + TM_PHI + j * 8, v_hi, idesc_o, 1);
-          } else {
-            mma_tf32_ts(tmem + TM_O, tmem + TM_PHI + j * 8, v_hi, idesc_o, j != 0);
+          for (int j = 0; j < AT_ND / 8; ++j) {
+            const uint32_t vo = (j >> 2) * 4096 + (j & 3) * 32;
+            const uint64_t v_hi = make_smem_desc(sb + off_vhi + vo);
+            if (PASSES == 3) {
+              const uint64_t v_lo = make_smem_desc(sb + off_vlo + vo);
+              mma_tf32_ts(tmem + TM_O, tmem + TM_PLO + j * 8, v_hi, idesc_o, j != 0);
+              mma_tf32_ts(tmem + TM_O, tmem + TM_PHI + j * 8, v_lo, idesc_o, 1);
+              mma_tf32_ts(tmem + TM_O, tmem + TM_PHI + j * 8, v_hi, idesc_o, 1);
+            } else {
+              mma_tf32_ts(tmem + TM_O, tmem + TM_PHI + j * 8, v_hi, idesc_o, j != 0);
+            }
           }
+          mma_commit(smem_u32(&empty_bar[stage]));
+          mma_commit(smem_u32(&o_full));
         }
-        mma_commit(smem_u32(&empty_bar[stage]));
-        mma_commit(smem_u32(&o_full));
+        __syncwarp();
       }
     }
   } else if (warp < 10) {

@@ -82,7 +82,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   __shared__ __align__(8) uint64_t tmem_full_bar[2], tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_slot;
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp: provably uniform
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B atoms need 1024-B alignment
 
   if (threadIdx.x == 0) {
@@ -128,8 +128,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_CTRL));
-    if (warp == 0 && lane == 0) {
-      // ===================== TMA producer =====================
+    if (warp == 0) {
+      // ===================== TMA producer (warp-uniform; one elected lane issues, see elect_one) =====================
       int stage = 0;
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
@@ -139,20 +139,23 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
           const uint32_t sbase = smem0 + stage * p.stage_bytes;
           const uint32_t fb = smem_u32(&full_bar[stage]);
-          mbar_expect_tx(fb, A_BYTES + (PASSES == 3 ? 2 : 1) * p.b_bytes);
           const int tap = kb / p.cblk_per_tap;
           const int c = (kb - tap * p.cblk_per_tap) * BK;
           const int col = (c < p.k0) ? (p.col0 + c) : (p.col1 + (c - p.k0));
           int dy = 0, dx = 0;
           if (p.taps == 9) { dy = tap / 3 - 1; dx = tap % 3 - 1; }
-          tma_load_4d(sbase, &map_a, fb, col, x0 + dx, y0 + dy, b);
-          tma_load_2d(sbase + off_bh, &map_bh, fb, kb * BK, n0);
-          if (PASSES == 3) tma_load_2d(sbase + off_bl, &map_bl, fb, kb * BK, n0);
+          if (elect_one()) {
+            mbar_expect_tx(fb, A_BYTES + (PASSES == 3 ? 2 : 1) * p.b_bytes);
+            tma_load_4d(sbase, &map_a, fb, col, x0 + dx, y0 + dy, b);
+            tma_load_2d(sbase + off_bh, &map_bh, fb, kb * BK, n0);
+            if (PASSES == 3) tma_load_2d(sbase + off_bl, &map_bl, fb, kb * BK, n0);
+          }
+          __syncwarp();
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
-    } else if (warp == 1 && lane == 0) {
-      // ===================== MMA issuer =====================
+    } else if (warp == 1) {
+      // ===================== MMA issuer (warp-uniform; one elected lane issues) =====================
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       int stage = 0;
       uint32_t phase = 0, gchunk = 0;
@@ -168,25 +171,29 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t sbase = smem0 + stage * p.stage_bytes;
             const uint32_t first = (kb == ck * p.chunk_kb) ? 0u : 1u;
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < BK / UMMA_K; ++k) {
-              const uint32_t koff = k * UMMA_K * 4;
-              const uint64_t a_hi = make_smem_desc(sbase + koff);
-              const uint64_t b_hi = make_smem_desc(sbase + off_bh + koff);
-              if (PASSES == 3) {
-                const uint64_t a_lo = make_smem_desc(sbase + off_al + koff);
-                const uint64_t b_lo = make_smem_desc(sbase + off_bl + koff);
-                mma_tf32(tmem_acc, a_lo, b_hi, idesc, first | (uint32_t)(k != 0));
-                mma_tf32(tmem_acc, a_hi, b_lo, idesc, 1);
-                mma_tf32(tmem_acc, a_hi, b_hi, idesc, 1);
-              } else {
-                mma_tf32(tmem_acc, a_hi, b_hi, idesc, first | (uint32_t)(k != 0));
+              for (int k = 0; k < BK / UMMA_K; ++k) {
+                const uint32_t koff = k * UMMA_K * 4;
+                const uint64_t a_hi = make_smem_desc(sbase + koff);
+                const uint64_t b_hi = make_smem_desc(sbase + off_bh + koff);
+                if (PASSES == 3) {
+                  const uint64_t a_lo = make_smem_desc(sbase + off_al + koff);
+                  const uint64_t b_lo = make_smem_desc(sbase + off_bl + koff);
+                  mma_tf32(tmem_acc, a_lo, b_hi, idesc, first | (uint32_t)(k != 0));
+                  mma_tf32(tmem_acc, a_hi, b_lo, idesc, 1);
+                  mma_tf32(tmem_acc, a_hi, b_hi, idesc, 1);
+                } else {
+                  mma_tf32(tmem_acc, a_hi, b_hi, idesc, first | (uint32_t)(k != 0));
+                }
               }
+              mma_commit(smem_u32(&empty_bar[stage]));       // frees the smem slot once these MMAs retire
             }
-            mma_commit(smem_u32(&empty_bar[stage]));       // frees the smem slot once these MMAs retire
+            __syncwarp();
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
-          mma_commit(smem_u32(&tmem_full_bar[buf]));       // this chain is complete
+          if (elect_one()) mma_commit(smem_u32(&tmem_full_bar[buf]));       // this chain is complete
+          __syncwarp();
         }
       }
     }

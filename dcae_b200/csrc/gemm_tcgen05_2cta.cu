@@ -77,8 +77,8 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
   __shared__ __align__(8) uint64_t tmem_full_bar[2], tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_slot;
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp, rank: provably uniform
+  const uint32_t rank = __shfl_sync(0xffffffffu, cluster_ctarank(), 0);
   const bool leader = rank == 0;
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -130,8 +130,8 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
 
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_CTRL));
-    if (warp == 0 && lane == 0) {
-      // ===================== TMA producer (both CTAs) =====================
+    if (warp == 0) {
+      // ===================== TMA producer (both CTAs; warp-uniform, one elected lane issues) =====================
       int stage = 0;
       uint32_t phase = 0;
       for (int pt = pair; pt < p.total_pair_tiles; pt += npairs) {
@@ -146,23 +146,26 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
           int dy = 0, dx = 0;
           if (p.taps == 9) { dy = tap / 3 - 1; dx = tap % 3 - 1; }
           const uint32_t bf = smem_u32(&b_full[stage]);
-          if (PASSES == 3) {
-            const uint32_t af = smem_u32(&a_full[stage]);
-            mbar_expect_tx(af, A_BYTES);
-            tma_load_4d(sbase, &map_a, af, col, x0 + dx, y0 + dy, b);
-            if (leader) mbar_expect_tx(bf, 4 * p.bh_bytes);            // hi + lo halves of both CTAs
-            tma_load_2d_2sm(sbase + off_bh, &map_bh, bf, kb * BK, n0 + (int)rank * half_n);
-            tma_load_2d_2sm(sbase + off_bl, &map_bl, bf, kb * BK, n0 + (int)rank * half_n);
-          } else {
-            if (leader) mbar_expect_tx(bf, 2 * (A_BYTES + p.bh_bytes));
-            tma_load_4d_2sm(sbase, &map_a, bf, col, x0 + dx, y0 + dy, b);
-            tma_load_2d_2sm(sbase + off_bh, &map_bh, bf, kb * BK, n0 + (int)rank * half_n);
+          const uint32_t af = smem_u32(&a_full[stage]);
+          if (elect_one()) {
+            if (PASSES == 3) {
+              mbar_expect_tx(af, A_BYTES);
+              tma_load_4d(sbase, &map_a, af, col, x0 + dx, y0 + dy, b);
+              if (leader) mbar_expect_tx(bf, 4 * p.bh_bytes);            // hi + lo halves of both CTAs
+              tma_load_2d_2sm(sbase + off_bh, &map_bh, bf, kb * BK, n0 + (int)rank * half_n);
+              tma_load_2d_2sm(sbase + off_bl, &map_bl, bf, kb * BK, n0 + (int)rank * half_n);
+            } else {
+              if (leader) mbar_expect_tx(bf, 2 * (A_BYTES + p.bh_bytes));
+              tma_load_4d_2sm(sbase, &map_a, bf, col, x0 + dx, y0 + dy, b);
+              tma_load_2d_2sm(sbase + off_bh, &map_bh, bf, kb * BK, n0 + (int)rank * half_n);
+            }
           }
+          __syncwarp();
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
-    } else if (warp == 1 && lane == 0 && leader) {
-      // ===================== MMA issuer (leader CTA only): M = 256 across the pair =====================
+    } else if (warp == 1 && leader) {
+      // ===================== MMA issuer (leader CTA only; warp-uniform, one elected lane issues): M = 256 across the pair =====================
       const uint32_t idesc = make_idesc_tf32(2 * BM, p.BN);
       int stage = 0;
       uint32_t phase = 0, gchunk = 0;
@@ -179,25 +182,29 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t sbase = smem0 + stage * p.stage_bytes;
             const uint32_t first = (kb == ck * p.chunk_kb) ? 0u : 1u;
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < BK / UMMA_K; ++k) {
-              const uint32_t koff = k * UMMA_K * 4;
-              const uint64_t a_hi = make_smem_desc(sbase + koff);
-              const uint64_t b_hi = make_smem_desc(sbase + off_bh + koff);
-              if (PASSES == 3) {
-                const uint64_t a_lo = make_smem_desc(sbase + off_al + koff);
-                const uint64_t b_lo = make_smem_desc(sbase + off_bl + koff);
-                mma_tf32_2sm(tmem_acc, a_lo, b_hi, idesc, first | (uint32_t)(k != 0));
-                mma_tf32_2sm(tmem_acc, a_hi, b_lo, idesc, 1);
-                mma_tf32_2sm(tmem_acc, a_hi, b_hi, idesc, 1);
-              } else {
-                mma_tf32_2sm(tmem_acc, a_hi, b_hi, idesc, first | (uint32_t)(k != 0));
+              for (int k = 0; k < BK / UMMA_K; ++k) {
+                const uint32_t koff = k * UMMA_K * 4;
+                const uint64_t a_hi = make_smem_desc(sbase + koff);
+                const uint64_t b_hi = make_smem_desc(sbase + off_bh + koff);
+                if (PASSES == 3) {
+                  const uint64_t a_lo = make_smem_desc(sbase + off_al + koff);
+                  const uint64_t b_lo = make_smem_desc(sbase + off_bl + koff);
+                  mma_tf32_2sm(tmem_acc, a_lo, b_hi, idesc, first | (uint32_t)(k != 0));
+                  mma_tf32_2sm(tmem_acc, a_hi, b_lo, idesc, 1);
+                  mma_tf32_2sm(tmem_acc, a_hi, b_hi, idesc, 1);
+                } else {
+                  mma_tf32_2sm(tmem_acc, a_hi, b_hi, idesc, first | (uint32_t)(k != 0));
+                }
               }
+              mma_commit_2sm(smem_u32(&empty_bar[stage]));      // frees the slot in BOTH CTAs
             }
-            mma_commit_2sm(smem_u32(&empty_bar[stage]));      // frees the slot in BOTH CTAs
+            __syncwarp();
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
-          mma_commit_2sm(smem_u32(&tmem_full_bar[buf]));      // chain complete: both CTAs drain their half
+          if (elect_one()) mma_commit_2sm(smem_u32(&tmem_full_bar[buf]));      // chain complete: both CTAs drain their half
+          __syncwarp();
         }
       }
     }
