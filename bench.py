@@ -33,6 +33,26 @@ FLOP_PER_TOKEN = 163.76e6        # whole slice loop, 2*MAC
 GC_BYTES_PER_ELEM = 28           # y, mu, scale in; lik, y_hat, sym, idx out (compress variant)
 
 
+def ncu_traffic(kernel_csv):
+    """Mean DRAM bytes (read + write) per launch from a committed `ncu --set full` summary (tools/ncu_summary.py), or None."""
+    import csv
+    path = os.path.join(ROOT, "profiles", "r01", kernel_csv)
+    try:
+        rows = list(csv.reader(open(path)))
+        hdr, units, data = rows[0], rows[1], rows[2:]
+        mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        tot = []
+        for r in data:
+            b = 0.0
+            for name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                i = hdr.index(name)
+                b += float(r[i]) * mult[units[i]]
+            tot.append(b)
+        return sum(tot) / len(tot) if tot else None
+    except Exception:                                   # noqa: BLE001
+        return None
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -155,6 +175,7 @@ def main():
     ap.add_argument("--cpu-images", type=int, default=2, help="images per step of the CPU reference arm")
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--lanes", type=int, default=2, help="sub-batches run on separate streams by EntropySliceLoop.forward")
+    ap.add_argument("--warmup-seconds", type=float, default=1.5, help="keep warming up until the device has been busy this long (0 under ncu)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-clock-sampler", action="store_true", help="diagnostic: do not poll NVML during the timed region")
     ap.add_argument("--gc-micro-mb", type=int, default=1024, help="footprint of the kernel-3 HBM microbenchmark")
@@ -233,7 +254,7 @@ def main():
     # warm-up: W steps (>= 3), and keep going until the device has been busy for ~1.5 s -- a fresh box needs that long
     # to page in, ramp its clocks and settle under the power cap (three 15 ms steps do not)
     n_warm, t_warm = 0, time.perf_counter()
-    while n_warm < max(args.warmup, 3) or time.perf_counter() - t_warm < 1.5:
+    while n_warm < max(args.warmup, 3) or time.perf_counter() - t_warm < args.warmup_seconds:
         step_resident()
         torch.cuda.synchronize()
         n_warm += 1
@@ -278,7 +299,8 @@ def main():
         "kernel": {"f16x3": "gemm_f16x3_kernel (+ split_f16_planes_kernel)", "tf32x3": "gemm_tcgen05_kernel / gemm_tcgen05_2cta_kernel",
                    "tf32": "gemm_tcgen05_kernel", "fp32": "gemm_simt_kernel"}[args.math],
         "bound": "tensor", "achieved": gemm_tflops, "peak": tc_peak, "unit": "TFLOP/s", "frac": gemm_tflops / tc_peak,
-        "traffic": None,
+        "traffic": ncu_traffic("prof_gemm_final_summary.csv") if args.math == "f16x3" else None,
+        "traffic_note": "mean dram__bytes_read + write per launch over the launches of profiles/r01/prof_gemm_final_summary.csv (ncu --set full, same command); operands are L2-resident between layers, so DRAM traffic is below the algorithmic operand bytes",
         "note": (f"achieved = algorithmic 2*T*N*K flop of all {fam['gemm']['launches_per_step']} dense-layer launches of a step / "
                  f"their summed CUDA-event time; peak = {peaks['src']} sustained dense bf16 (kernel timed inside a long step). "
                  + {"f16x3": "Arithmetic is 3 fp16 MMAs (hi/lo operand planes, fp32 accumulate) per algorithmic MAC: ceiling = 1/3 of this peak; the fp16 plane split of each operand is included in the timed launches.",
@@ -293,7 +315,9 @@ def main():
     if rank == 0:
         roofline_gc = gc_microbench(dev, lib, args.gc_micro_mb, peaks)
         roofline_gc["in_loop"] = {"ms_per_step": fam["gc"]["ms_per_step"], "launches_per_step": fam["gc"]["launches_per_step"],
-                                  "GB/s": fam["gc"]["work_per_step"] / max(fam["gc"]["ms_per_step"], 1e-9) / 1e6}
+                                  "GB/s": fam["gc"]["work_per_step"] / max(fam["gc"]["ms_per_step"], 1e-9) / 1e6,
+                                  "traffic": ncu_traffic("prof_gc_final_summary.csv"),
+                                  "traffic_note": "DRAM bytes per in-loop launch (ncu --set full): the 18.9 MB of inputs; the 25 MB of outputs stay in L2"}
 
     cpu_baseline = None
     if rank == 0 and not args.no_cpu_baseline:
