@@ -148,6 +148,18 @@ def test_dict_attention_core(math, T):
     assert torch.equal(got, again)
 
 
+def test_f16x3_attention_needs_query_planes():
+    """DCAE_MATH_F16X3 reads the query from fp16 planes; without them the call fails loudly (no silent split / fallback)."""
+    from dcae_b200 import _lib
+    lib = _lib.load()
+    q = torch.randn(128, 640, generator=g(60)).cuda()
+    Kh, Vh = torch.randn(20, 128, 32, generator=g(61)).cuda(), torch.randn(20, 128, 32, generator=g(62)).cuda()
+    kv = _lib.DictKV(Kh.data_ptr(), Vh.data_ptr(), None, None, None, None, torch.ones(20).cuda().data_ptr())
+    out = torch.empty_like(q)
+    rc = lib.dcae_op_dict_attention(q.data_ptr(), 640, None, kv, 128, out.data_ptr(), 640, None, _lib.MATH["f16x3"], None)
+    assert rc != 0 and b"q16" in lib.dcae_last_error()
+
+
 def test_transposes_roundtrip():
     x = torch.randn(3, 70, 5, 9, generator=g(35))
     t = K.nchw_to_tokens(x.cuda())
