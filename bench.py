@@ -143,6 +143,35 @@ def cpu_oracle_rate(n_images, steps, warmup, seed=0):
     return n_images / dt, threads, dt
 
 
+def gpu_eager_rate(dev, n_images, steps, warmup, seed=0):
+    """The same oracle port run by eager PyTorch ON THE GPU (fp32, TF32 off as eval.py:3182-3187 sets it): what a user
+    of the reference gets on this B200 without this library.  A baseline leg like cpu_baseline: it only times the
+    checker, nothing of it is on the product path.  Returns (images/s, seconds per step)."""
+    from dcae_b200.params import init_entropy_params
+    from oracle.entropy_model import SliceLoopOracle
+    tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        params = {k: v.to(dev) for k, v in init_entropy_params(seed, "lively").items()}
+        orc = SliceLoopOracle(params, scale_table=None)
+        orc.scale_table = orc.scale_table.to(dev)
+        y, ls, lm = (t.to(dev) for t in synth_latents(n_images, H_IMG // 16, W_IMG // 16))
+        for _ in range(warmup):
+            orc.forward(y, ls, lm)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            orc.forward(y, ls, lm)
+        e1.record()
+        torch.cuda.synchronize()
+        dt = e0.elapsed_time(e1) * 1e-3 / max(steps, 1)
+        return n_images / dt, dt
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
+
+
 def run_reference(args):
     """--impl reference: the reference CPU path on the box's host cores, bounded sample per step."""
     rank = int(os.environ.get("RANK", "0"))
@@ -177,6 +206,7 @@ def main():
     ap.add_argument("--lanes", type=int, default=2, help="sub-batches run on separate streams by EntropySliceLoop.forward")
     ap.add_argument("--warmup-seconds", type=float, default=1.5, help="keep warming up until the device has been busy this long (0 under ncu)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the eager-PyTorch-on-GPU oracle leg")
     ap.add_argument("--no-clock-sampler", action="store_true", help="diagnostic: do not poll NVML during the timed region")
     ap.add_argument("--gc-micro-mb", type=int, default=1024, help="footprint of the kernel-3 HBM microbenchmark")
     args = ap.parse_args()
@@ -325,6 +355,18 @@ def main():
         cpu_baseline = {"value": rate, "unit": "images/s", "cores": threads, "kind": "port",
                         "sample": f"{args.cpu_steps} steps x {args.cpu_images} images of 768x512 (same slice loop, torch-CPU fp32 oracle port)"}
 
+    h2d_bytes, d2h_bytes = pipe.h2d_bytes, pipe.d2h_bytes
+    torch_gpu_baseline = None
+    if rank == 0 and not args.no_gpu_baseline:
+        del eng, pipe, out_buf, out, host_res       # free the plans' workspaces before the eager run needs its temporaries
+        torch.cuda.empty_cache()
+        try:
+            rate, dt = gpu_eager_rate(dev, B, 2, 1)
+            torch_gpu_baseline = {"value": rate, "unit": "images/s", "ms_per_step": dt * 1e3, "kind": "port",
+                                  "sample": f"2 steps x {B} images of 768x512: the oracle port run by eager PyTorch on this GPU (fp32, TF32 off, cuDNN on)"}
+        except Exception as e:                      # noqa: BLE001  (a baseline leg must never take the bench line down)
+            torch_gpu_baseline = {"value": None, "error": repr(e)[:200]}
+
     if rank == 0:
         imgs = B * world
         line = {
@@ -339,7 +381,7 @@ def main():
                        "l2": "no flush needed: per-step working set 1.8 GB >> 126 MB L2", "parallelism": f"{world} independent image shards", "lanes_per_gpu": args.lanes,
                        "warmup_steps_run": n_warm},
             "e2e": {"value": imgs / (ms_e2e * 1e-3), "unit": "images/s", "ms_per_step": ms_e2e,
-                    "h2d_bytes_per_step": pipe.h2d_bytes, "d2h_bytes_per_step": pipe.d2h_bytes,
+                    "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "how": "dcae_b200.HostPipeline: pinned host tensors in and out, H2D / compute / D2H of consecutive batches overlapped on 3 streams (wall clock over the K steps, last result on the host)"},
             "gpu_launches": launches * args.steps,
             "gpu_launches_per_step": launches,
@@ -350,6 +392,7 @@ def main():
             "step_tflops": FLOP_PER_TOKEN * T / (ms_step * 1e-3) / 1e12,
             "bpp": bpp,
             "cpu_baseline": cpu_baseline,
+            "torch_gpu_baseline": torch_gpu_baseline,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -4,6 +4,7 @@ Public surface (mirrors the reference's operator interface for this path only):
   EntropySliceLoop      -- the channel-slice loop of DCAE.forward/compress/decompress
   HostPipeline          -- pinned-host-in / pinned-host-out streaming front end (overlapped copies)
   GaussianConditional   -- compressai-compatible quantise / likelihood / build_indexes (kernel 3)
+  accelerate, DictCrossAttention, ConvStack -- module-level drop-ins for a reference DCAE instance (dcae_b200/modules.py)
   init_entropy_params   -- deterministic random-init weights with the reference's state-dict keys
 """
 from .params import init_entropy_params, entropy_param_shapes  # noqa: F401
@@ -17,6 +18,9 @@ def __getattr__(name):
     if name == "HostPipeline":
         from .pipeline import HostPipeline
         return HostPipeline
+    if name in ("accelerate", "DictCrossAttention", "ConvStack"):
+        from . import modules
+        return getattr(modules, name)
     if name == "GaussianConditional":
         from .gaussian_conditional import GaussianConditional
         return GaussianConditional

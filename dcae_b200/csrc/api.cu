@@ -371,7 +371,7 @@ extern "C" int dcae_slice_loop_load(dcae_slice_loop* p, const float* y, const fl
 }
 
 // dictionary cross-attention module of slice i (dcae.py:479-509) -> support columns [0, 320)
-static int run_dca(dcae_slice_loop* p, int i, void* s) {
+static int run_dca(dcae_slice_loop* p, int i, void* s, bool dict_f32 = false) {   // dict_f32: also keep dict_info in fp32 (module-level call)
   const dcae_slice_weights& W = p->wt[i];
   const int64_t T = p->T;
   const bool pm = p->pm;
@@ -439,8 +439,11 @@ static int run_dca(dcae_slice_loop* p, int i, void* s) {
     DCAE_TRY(gemm(p, opnd2(p, p->g, 2 * D, p->gp, 0, 2 * D, 1), W.fc2, e, s));
   }
   // dict_info = output_trans(output)                                         dcae.py:507
-  DCAE_TRY(gemm(p, opnd2(p, p->x3, D, p->x3p, 0, D, 1), W.output_trans,
-                epi2(p, W.output_trans_b, p->sup.p + SUP_DICT, SUP_LD, p->supp, SUP_DICT), s));
+  {
+    dcae_epilogue e = epi2(p, W.output_trans_b, p->sup.p + SUP_DICT, SUP_LD, p->supp, SUP_DICT);
+    if (dict_f32) { e.out = p->sup.p + SUP_DICT; e.out_ld = SUP_LD; }
+    DCAE_TRY(gemm(p, opnd2(p, p->x3, D, p->x3p, 0, D, 1), W.output_trans, e, s));
+  }
   return DCAE_OK;
 }
 
@@ -473,6 +476,69 @@ extern "C" int dcae_slice_loop_params(dcae_slice_loop* p, int32_t i, void* s) {
     DCAE_CUDA(cudaStreamWaitEvent((cudaStream_t)s, p->ev_join, 0));
   }
   return DCAE_OK;
+}
+
+// ---- module-level entry points (the reference's own nn.Module surfaces) -------------------------
+// One module of slice i on the caller's NCHW tensor, through the plan's buffers (do not interleave with a slice
+// loop in flight on the same plan).  The reference channel order of the inputs is the support-buffer order
+// [latent_scales | latent_means | y_hat_0.. | (dict_info) | (y_hat_slice)], so windows land by column.
+static int load_window(dcae_slice_loop* p, const float* x, int64_t x_channels, int c0, int C, int sup_col, void* s) {
+  for (int b = 0; b < p->B; ++b) {                       // per image: the window's batch stride is the caller's
+    const float* src = x + ((int64_t)b * x_channels + c0) * p->HW;
+    const int64_t row0 = (int64_t)b * p->HW;
+    if (p->pm) {
+      dcae_planes w = pl(p->supp, sup_col);
+      w.hi = static_cast<__half*>(w.hi) + row0 * w.ld;
+      w.lo = static_cast<__half*>(w.lo) + row0 * w.ld;
+      DCAE_TRY(dcae_op_nchw_to_tokens(src, 1, C, p->HW, p->sup.p + row0 * SUP_LD + sup_col, SUP_LD, &w, s));
+    } else {
+      DCAE_TRY(dcae_op_nchw_to_tokens(src, 1, C, p->HW, p->sup.p + row0 * SUP_LD + sup_col, SUP_LD, nullptr, s));
+    }
+  }
+  return DCAE_OK;
+}
+
+extern "C" int dcae_slice_loop_module_dca(dcae_slice_loop* p, int32_t i, const float* x, float* out, void* s) {
+  DCAE_REQUIRE(p && x && out && i >= 0 && i < NS, "dcae_slice_loop_module_dca: bad argument");
+  const int cq = 2 * M + SL * i;
+  DCAE_TRY(load_window(p, x, cq, 0, cq, SUP_LS, s));
+  DCAE_TRY(run_dca(p, i, s, true));
+  return dcae_op_tokens_to_nchw(p->sup.p + SUP_DICT, SUP_LD, p->B, M, p->HW, out, s);
+}
+
+// which: 0 = cc_mean_transforms[i], 1 = cc_scale_transforms[i] (x: [B, 960 + 64 i, h, w]), 2 = lrp_transforms[i]
+// (x: [B, 1024 + 64 i, h, w], the RAW conv stack: the caller applies 0.5 tanh as dcae.py:663 does).
+extern "C" int dcae_slice_loop_module_conv(dcae_slice_loop* p, int32_t i, int32_t which, const float* x, float* out, void* s) {
+  DCAE_REQUIRE(p && x && out && i >= 0 && i < NS && which >= 0 && which <= 2, "dcae_slice_loop_module_conv: bad argument");
+  const dcae_slice_weights& W = p->wt[i];
+  const int cq = 2 * M + SL * i, cs = 3 * M + SL * i, cx = cs + (which == 2 ? SL : 0);
+  DCAE_TRY(load_window(p, x, cx, 0, cq, SUP_LS, s));
+  DCAE_TRY(load_window(p, x, cx, cq, M, SUP_DICT, s));
+  if (which == 2) DCAE_TRY(load_window(p, x, cx, cs, SL, SUP_PRE, s));
+  {
+    dcae_epilogue e = epi(W.cc1_b, p->h1.p, 672, DCAE_ACT_GELU);       // the fused first layer of all three stacks
+    e.act_cols = 448;
+    if (p->pm) e.out16 = pl(p->h1p, 0);
+    DCAE_TRY(gemm(p, opnd2(p, p->sup, SUP_LD, p->supp, 0, cs, 9), W.cc1, e, s));
+  }
+  float* res = nullptr;
+  if (which == 0) {
+    DCAE_TRY(gemm(p, opnd2(p, p->h1, 672, p->h1p, 0, 224, 9), W.mean2, epi2(p, W.mean2_b, p->h2.p, 256, p->h2p, 0, DCAE_ACT_GELU), s));
+    res = p->means.p + SL * i;
+    DCAE_TRY(gemm(p, opnd2(p, p->h2, 256, p->h2p, 0, 128, 9), W.mean3, epi(W.mean3_b, res, M), s));
+  } else if (which == 1) {
+    DCAE_TRY(gemm(p, opnd2(p, p->h1, 672, p->h1p, 224, 224, 9), W.scale2, epi2(p, W.scale2_b, p->h2.p + 128, 256, p->h2p, 128, DCAE_ACT_GELU), s));
+    res = p->scales.p + SL * i;
+    DCAE_TRY(gemm(p, opnd2(p, p->h2, 256, p->h2p, 128, 128, 9), W.scale3, epi(W.scale3_b, res, M), s));
+  } else {
+    dcae_epilogue e = epi2(p, W.lrp1_b, p->l1.p, 224, p->l1p, 0, DCAE_ACT_GELU);
+    e.addend = p->h1.p + 448; e.addend_ld = 672;
+    DCAE_TRY(gemm(p, opnd2(p, p->sup, SUP_LD, p->supp, SUP_PRE, SL, 9), W.lrp1y, e, s));
+    DCAE_TRY(gemm(p, opnd2(p, p->l1, 224, p->l1p, 0, 224, 9), W.lrp2, epi2(p, W.lrp2_b, p->l2.p, 128, p->l2p, 0, DCAE_ACT_GELU), s));
+    res = p->lik.p + SL * i;                                           // scratch window: raw lrp stack output
+    DCAE_TRY(gemm(p, opnd2(p, p->l2, 128, p->l2p, 0, 128, 9), W.lrp3, epi(W.lrp3_b, res, M), s));
+  }
+  return dcae_op_tokens_to_nchw(res, M, p->B, SL, p->HW, out, s);
 }
 
 // LRP of slice i (dcae.py:661-664): y_hat_i = y_hat_pre + 0.5 tanh(lrp(cat(support, y_hat_pre)))

@@ -226,6 +226,30 @@ class EntropySliceLoop:
         self.last_launches = int(lib.dcae_launch_count())
         return {"y_hat": y_hat, "indexes": idx_all}
 
+    # ---- module-level calls (dcae_b200/modules.py: drop-ins for the reference's own sub-modules) -------
+    def module_dca(self, i: int, x: torch.Tensor) -> torch.Tensor:
+        """dt_cross_attention[i](x, dt): x [B, 640 + 64 i, h, w] -> dict_info [B, 320, h, w]  (dcae.py:479-509)."""
+        x = self._check_in("x", x, C_=2 * M_LATENT + SLICE_CH * i)
+        B, _, h, w = x.shape
+        out = torch.empty(B, M_LATENT, h, w, device=self.device)
+        self._last_call_lanes = False
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.dcae_slice_loop_module_dca(self._plan(B, h, w).handle, i, x.data_ptr(), out.data_ptr(),
+                                                           self._stream()), "dcae_slice_loop_module_dca")
+        return out
+
+    def module_conv(self, i: int, which: int, x: torch.Tensor) -> torch.Tensor:
+        """which 0 / 1 / 2 = cc_mean_transforms[i] / cc_scale_transforms[i] / lrp_transforms[i] (raw conv stack):
+        x [B, 960 + 64 i (+ 64 for lrp), h, w] -> [B, 64, h, w]  (dcae.py:584-611)."""
+        x = self._check_in("x", x, C_=3 * M_LATENT + SLICE_CH * i + (SLICE_CH if which == 2 else 0))
+        B, _, h, w = x.shape
+        out = torch.empty(B, SLICE_CH, h, w, device=self.device)
+        self._last_call_lanes = False
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.dcae_slice_loop_module_conv(self._plan(B, h, w).handle, i, which, x.data_ptr(), out.data_ptr(),
+                                                            self._stream()), "dcae_slice_loop_module_conv")
+        return out
+
     # ---- debugging / stage-wise parity (the reference's debug_save pattern, dcae_5_fixed.py:29-34) ---
     def tap(self, name: str, B: int, h: int, w: int) -> torch.Tensor:
         """Copy of a named token-major intermediate [T, cols] of the most recent call (`forward` lanes concatenated)."""

@@ -281,6 +281,17 @@ int dcae_slice_loop_decode(dcae_slice_loop* p, int32_t i, const int32_t* symbols
  * coder order, dcae.py:742-743).  log2_lik_sum: 1 float = sum log2(lik) (deterministic). */
 int dcae_slice_loop_store(dcae_slice_loop* p, float* y_hat, float* means, float* scales, float* lik,
                           int32_t* symbols, int32_t* indexes, float* log2_lik_sum, void* stream);
+/* Module-level calls, for callers that keep the reference's loop text and swap single modules: one
+ * module of slice i on the caller's NCHW fp32 tensors, through the plan's buffers -- do not interleave with a slice
+ * loop in flight on the same plan.
+ *   _module_dca : net.dt_cross_attention[i](x, dt)            dcae.py:479-509, called at :646, :730, :881
+ *                 x [B, 640 + 64 i, h, w] = cat(latent_scales, latent_means, y_hat_0..) -> out [B, 320, h, w];
+ *                 the dictionary is the one packed into the plan's weights (K = k(LN(dt)), V = LN(dt)).
+ *   _module_conv: which 0 = cc_mean_transforms[i], 1 = cc_scale_transforms[i]   (dcae.py:649-655; x [B, 960 + 64 i, h, w])
+ *                 which 2 = lrp_transforms[i]                  (dcae.py:661-662; x [B, 1024 + 64 i, h, w]); the RAW conv
+ *                 stack, the caller applies 0.5 tanh (dcae.py:663)            -> out [B, 64, h, w] */
+int dcae_slice_loop_module_dca(dcae_slice_loop* p, int32_t i, const float* x, float* out, void* stream);
+int dcae_slice_loop_module_conv(dcae_slice_loop* p, int32_t i, int32_t which, const float* x, float* out, void* stream);
 /* load + 5 x (params, encode) + store. */
 int dcae_slice_loop_forward(dcae_slice_loop* p, const float* y, const float* latent_scales,
                             const float* latent_means, float* y_hat, float* means, float* scales,
