@@ -83,3 +83,22 @@ def test_param_spec_covers_reference_hot_path_keys():
     want = {k: tuple(v.shape) for k, v in net.state_dict().items() if k.split(".")[0] in hot}
     got = dict(P.entropy_param_shapes())
     assert want == got
+
+
+def test_accelerate_swaps_exactly_the_attributes_the_reference_loop_calls():
+    """dcae_b200.modules.accelerate() replaces ModuleList entries and `gaussian_conditional` of a DCAE instance: the real
+    reference class must have them with the shapes the drop-ins assume (the swap itself needs a GPU: test_gpu_modules)."""
+    import inspect
+    ref = load_reference_dcae_module()
+    net = ref.DCAE()
+    for name in ("dt_cross_attention", "cc_mean_transforms", "cc_scale_transforms", "lrp_transforms"):
+        ml = getattr(net, name)
+        assert isinstance(ml, torch.nn.ModuleList) and len(ml) == 5, name
+    assert hasattr(net, "gaussian_conditional") and tuple(net.dt.shape) == (128, 640)
+    src = inspect.getsource(ref.DCAE.forward)
+    for call in ("self.dt_cross_attention[slice_index](query, dt)", "self.cc_mean_transforms[slice_index](support)",
+                 "self.cc_scale_transforms[slice_index](support)", "self.lrp_transforms[slice_index](lrp_support)",
+                 "self.gaussian_conditional(y_slice, scale, mu)"):
+        assert call in src, call
+    sig = inspect.signature(type(net.dt_cross_attention[0]).forward)
+    assert list(sig.parameters)[:3] == ["self", "x", "dt"]
