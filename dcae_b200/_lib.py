@@ -135,6 +135,7 @@ SIGNATURES = {
     "dcae_slice_loop_store": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "dcae_slice_loop_module_dca": (C.c_int, [_P, C.c_int32, _P, _P, _P]),
     "dcae_slice_loop_module_conv": (C.c_int, [_P, C.c_int32, C.c_int32, _P, _P, _P]),
+    "dcae_pack_symbols": (C.c_int, [_P, _P, _I64, _P, _P, _P, _P]),
     "dcae_slice_loop_forward": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "dcae_slice_loop_tap": (C.c_int, [_P, C.c_char_p, C.POINTER(_P), C.POINTER(_I32), C.POINTER(_I64)]),
     "dcae_slice_loop_tap16": (C.c_int, [_P, C.c_char_p, C.POINTER(Planes), C.POINTER(_I32)]),

@@ -420,6 +420,38 @@ extern "C" int dcae_op_nchw_to_tokens_i32(const int32_t* src, int32_t B, int32_t
   return transpose_in<int32_t>(src, B, C, HW, dst, dst_ld, stream);
 }
 
+// ---- coder hand-off: int32 symbols / indexes -> int16 / uint8, 16 bytes in, 6 bytes out per 4 elements ----
+// Symbols outside int16 saturate and are counted (the coder's bypass path needs the int32 value: the caller falls back
+// to the int32 tensor when the count is not zero); indexes are < 256 by construction (table size <= 256).
+__global__ void __launch_bounds__(256) pack_symbols_kernel(const int4* __restrict__ sym, const int4* __restrict__ idx, int64_t n4,
+                                                           short4* __restrict__ sym16, uchar4* __restrict__ idx8,
+                                                           unsigned long long* __restrict__ overflow) {
+  unsigned int bad = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int4 v = __ldg(sym + i), j = __ldg(idx + i);
+    bad += (v.x < -32768 || v.x > 32767) + (v.y < -32768 || v.y > 32767) + (v.z < -32768 || v.z > 32767) + (v.w < -32768 || v.w > 32767);
+    sym16[i] = make_short4((short)max(-32768, min(32767, v.x)), (short)max(-32768, min(32767, v.y)),
+                           (short)max(-32768, min(32767, v.z)), (short)max(-32768, min(32767, v.w)));
+    idx8[i] = make_uchar4((unsigned char)j.x, (unsigned char)j.y, (unsigned char)j.z, (unsigned char)j.w);
+  }
+  bad = (unsigned int)__reduce_add_sync(0xffffffffu, bad);
+  if ((threadIdx.x & 31) == 0 && bad) atomicAdd(overflow, (unsigned long long)bad);
+}
+
+extern "C" int dcae_pack_symbols(const int32_t* symbols, const int32_t* indexes, int64_t n, int16_t* symbols16, uint8_t* indexes8,
+                                 unsigned long long* overflow_count, void* stream) {
+  DCAE_REQUIRE(symbols && indexes && symbols16 && indexes8 && overflow_count && n >= 0 && n % 4 == 0, "dcae_pack_symbols: bad arguments (n must be a multiple of 4)");
+  DCAE_REQUIRE(aligned16(symbols) && aligned16(indexes) && (reinterpret_cast<uintptr_t>(symbols16) & 7u) == 0 && (reinterpret_cast<uintptr_t>(indexes8) & 3u) == 0,
+               "dcae_pack_symbols: alignment");
+  ProfileScope prof(DCAE_PROF_OTHER, 0.0, stream);
+  DCAE_CUDA(cudaMemsetAsync(overflow_count, 0, sizeof(unsigned long long), (cudaStream_t)stream));
+  if (n == 0) return DCAE_OK;
+  pack_symbols_kernel<<<grid_for(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const int4*>(symbols), reinterpret_cast<const int4*>(indexes), n / 4,
+                                                                           reinterpret_cast<short4*>(symbols16), reinterpret_cast<uchar4*>(indexes8), overflow_count);
+  DCAE_LAUNCH_CHECK();
+  return DCAE_OK;
+}
+
 extern "C" int dcae_split_tf32(const float* w, float* w_hi, float* w_lo, int64_t n, void* stream) {
   DCAE_REQUIRE(w && w_hi && w_lo && n >= 0, "dcae_split_tf32: bad arguments");
   if (n == 0) return DCAE_OK;

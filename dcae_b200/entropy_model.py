@@ -201,6 +201,31 @@ class EntropySliceLoop:
             out.pop("likelihoods", None)
         return out
 
+    def compress_to_host(self, y, latent_scales, latent_means):
+        """The GPU -> coder hand-off: compress(), then ONE packed device->host copy instead of the
+        reference's ten `.tolist()` round trips (dcae.py:742-743).  Returns dict(symbols, indexes: pinned host tensors
+        in coder order, flat; int16 / uint8 unless a symbol left the int16 range, then int32 / uint8; overflow: int,
+        y_hat: device tensor).  `symbols.numpy()` / `indexes.numpy()` are zero-copy views for the rANS coder."""
+        out = self.compress(y, latent_scales, latent_means)
+        sym, idx = out["symbols"], out["indexes"]
+        n = sym.numel()
+        s16 = torch.empty(n, dtype=torch.int16, device=self.device)
+        i8 = torch.empty(n, dtype=torch.uint8, device=self.device)
+        ovf = torch.zeros(1, dtype=torch.int64, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.dcae_pack_symbols(sym.data_ptr(), idx.data_ptr(), n, s16.data_ptr(), i8.data_ptr(), ovf.data_ptr(),
+                                                  self._stream()), "dcae_pack_symbols")
+        h16 = torch.empty(n, dtype=torch.int16).pin_memory()
+        h8 = torch.empty(n, dtype=torch.uint8).pin_memory()
+        hov = torch.empty(1, dtype=torch.int64).pin_memory()
+        h16.copy_(s16, non_blocking=True)
+        h8.copy_(i8, non_blocking=True)
+        hov.copy_(ovf, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()          # the one host sync of the hand-off
+        overflow = int(hov[0])
+        symbols = h16 if overflow == 0 else sym.flatten().cpu()
+        return {"symbols": symbols, "indexes": h8, "overflow": overflow, "y_hat": out["y_hat"]}
+
     # ---- DCAE.decompress slice loop -------------------------------------------------------------
     def decompress(self, latent_scales, latent_means,
                    decode_slice: Callable[[int, torch.Tensor], torch.Tensor]):

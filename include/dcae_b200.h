@@ -213,6 +213,13 @@ int dcae_op_tokens_to_nchw(const float* src, int64_t src_ld, int32_t B, int32_t 
 int dcae_op_tokens_to_nchw_i32(const int32_t* src, int64_t src_ld, int32_t B, int32_t C, int64_t HW, int32_t* dst, void* stream);
 int dcae_op_nchw_to_tokens_i32(const int32_t* src, int32_t B, int32_t C, int64_t HW, int32_t* dst, int64_t dst_ld, void* stream);
 
+/* Coder hand-off (replaces the per-slice `.tolist()` of dcae.py:742-743 on the device side): the int32
+ * symbols / indexes of a compress() call, in coder order, packed to int16 / uint8 for one small D2H copy.  Symbols
+ * outside int16 saturate and are counted in *overflow_count (device scalar): when it is not zero the caller must
+ * use the int32 tensor (the coder's bypass path needs the exact value).  n must be a multiple of 4. */
+int dcae_pack_symbols(const int32_t* symbols, const int32_t* indexes, int64_t n, int16_t* symbols16, uint8_t* indexes8,
+                      unsigned long long* overflow_count, void* stream);
+
 /* --------------------------------------------------------------------------------------------
  * The channel-slice loop (dcae.py:638-670 forward, :713-753 compress, :878-906 decompress).
  * Packed weights of one slice i.  Dense weights are dcae_weight (row-major [N, K]); packing rules

@@ -190,6 +190,27 @@ def test_lanes_do_not_change_any_output_bit(math, lively_params):
     assert torch.equal(one.tap("x2", B, h, w), two.tap("x2", B, h, w))
 
 
+def test_packed_coder_handoff_equals_the_int32_tensors(lively_params):
+    """one packed D2H (int16 symbols, uint8 indexes, coder order) carries exactly what the reference's
+    per-slice `.tolist()` lists carry (dcae.py:742-743); a symbol outside int16 is detected and the int32 path is used."""
+    g = load_golden("slice_loop_b2_7x9")
+    eng = engine(lively_params, "f16x3")
+    y, ls, lm = (g[k].cuda() for k in ("y", "latent_scales", "latent_means"))
+    enc = eng.compress(y, ls, lm)
+    host = eng.compress_to_host(y, ls, lm)
+    assert host["overflow"] == 0 and host["symbols"].dtype == torch.int16 and host["symbols"].is_pinned()
+    # the reference's list order: slice-major, then reshape(-1) of [B, 64, h, w]
+    want_sym = torch.cat([enc["symbols"][i].reshape(-1) for i in range(5)]).cpu()
+    want_idx = torch.cat([enc["indexes"][i].reshape(-1) for i in range(5)]).cpu()
+    assert torch.equal(host["symbols"].int(), want_sym) and torch.equal(host["indexes"].int(), want_idx)
+    big = y.clone()
+    big[0, 3, 2, 2] = 1.0e5                       # a symbol that does not fit int16: flagged, int32 returned
+    host = eng.compress_to_host(big, ls, lm)
+    enc = eng.compress(big, ls, lm)
+    assert host["overflow"] >= 1 and host["symbols"].dtype == torch.int32
+    assert torch.equal(host["symbols"], enc["symbols"].flatten().cpu())
+
+
 def test_training_noise_forward_vs_oracle(lively_params):
     g = load_golden("slice_loop_b2_7x9")
     eng = engine(lively_params, "fp32")
