@@ -51,10 +51,38 @@ struct F16Params {
   float descale;
   int dbg_nostore;
   int has_o32, has_o16, has_o16a;
+  int fuse_b;                // single CTA, BN <= 128: one N = 2 BN MMA covers a_hi x [b_hi; b_lo], see the MMA issuer
   uint32_t stage_bytes, b_bytes;
   unsigned long long* dbg;   // DCAE_F16_DBG=1: per-CTA role counters (16 u64 each), see dump in the host wrapper
 };
 
+
+// drain of one chunk; FUSED: the accumulator of block blk is the sum of columns blk*32 (a_hi b_hi + a_lo b_hi) and
+// BN + blk*32 (a_hi b_lo)
+template <int NB>
+__device__ __forceinline__ void drain_chunk_f16(float* acc, uint32_t taddr, int half, int BN, bool first, bool fused_rt) {
+  const bool fused = (NB == 2) && fused_rt;     // BN <= 128 only: the NB = 4 instantiation never carries the second range
+#pragma unroll
+  for (int g = 0; g < NB; ++g) {
+    const int blk = 2 * g + half;
+    if (blk * 32 < BN) {                      // warp-uniform
+      uint32_t raw[32], raw2[32];
+      tmem_ld16_nowait(taddr + blk * 32, raw);
+      tmem_ld16_nowait(taddr + blk * 32 + 16, raw + 16);
+      if (fused) {
+        tmem_ld16_nowait(taddr + BN + blk * 32, raw2);
+        tmem_ld16_nowait(taddr + BN + blk * 32 + 16, raw2 + 16);
+      }
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float v = __uint_as_float(raw[j]);
+        if (fused) v = __fadd_rn(v, __uint_as_float(raw2[j]));
+        acc[g * 32 + j] = first ? v : __fadd_rn(acc[g * 32 + j], v);
+      }
+    }
+  }
+}
 
 __device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -341,6 +369,7 @@ __device__ __forceinline__ void gemm_f16x3_body(const CUtensorMap& map_ah, const
       // ===================== MMA issuer (the leader CTA of a pair; warp-uniform, one elected lane issues) =====================
       // D = F32 (bit 4), A = B = F16 (format 0), K-major, N >> 3 at bit 17, M >> 4 at bit 24
       const uint32_t idesc = (1u << 4) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(((PAIR ? 2 : 1) * BM) >> 4) << 24);
+      const uint32_t idesc2 = (1u << 4) | ((uint32_t)((2 * p.BN) >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);   // fuse_b: N = 2 BN
       int stage = 0;
       uint32_t phase = 0, gchunk = 0;
       long long w_full = 0, w_tmem = 0, n_kb = 0, n_tiles = 0;
@@ -354,7 +383,7 @@ __device__ __forceinline__ void gemm_f16x3_body(const CUtensorMap& map_ah, const
           else if (PAIR) mbar_wait_cl(smem_u32(&tmem_empty_bar[buf]), ((gchunk >> 1) & 1) ^ 1);
           else mbar_wait(smem_u32(&tmem_empty_bar[buf]), ((gchunk >> 1) & 1) ^ 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t tmem_acc = tmem_base + buf * (uint32_t)p.BN;
+          const uint32_t tmem_acc = tmem_base + buf * (uint32_t)(p.fuse_b ? 2 * p.BN : p.BN);
           const int kb_end = min(p.KB, (ck + 1) * p.chunk_kb);
           for (int kb = ck * p.chunk_kb; kb < kb_end; ++kb) {
             if (DBG) { w_full += timed_wait(smem_u32(&full_bar[stage]), phase, PAIR); ++n_kb; }
@@ -373,6 +402,11 @@ __device__ __forceinline__ void gemm_f16x3_body(const CUtensorMap& map_ah, const
                   mma_f16_2sm(tmem_acc, a_lo, b_hi, idesc, first | (uint32_t)(k != 0));
                   mma_f16_2sm(tmem_acc, a_hi, b_lo, idesc, 1);
                   mma_f16_2sm(tmem_acc, a_hi, b_hi, idesc, 1);
+                } else if (p.fuse_b) {
+                  // b_lo sits right behind b_hi in the stage, so ONE N = 2 BN instruction computes a_hi x [b_hi; b_lo]
+                  // into columns [0, BN) | [BN, 2 BN): the A tile is read from shared memory twice per k-step, not 3 times
+                  mma_f16(tmem_acc, a_hi, b_hi, idesc2, first | (uint32_t)(k != 0));
+                  mma_f16(tmem_acc, a_lo, b_hi, idesc, 1);
                 } else {
                   mma_f16(tmem_acc, a_lo, b_hi, idesc, first | (uint32_t)(k != 0));
                   mma_f16(tmem_acc, a_hi, b_lo, idesc, 1);
@@ -423,7 +457,7 @@ __device__ __forceinline__ void gemm_f16x3_body(const CUtensorMap& map_ah, const
         else mbar_wait(smem_u32(&tmem_full_bar[buf]), (gchunk >> 1) & 1);
         const long long td0 = DBG ? clock64() : 0;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        drain_chunk<NB>(acc, tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * (uint32_t)p.BN, half, p.BN, ck == 0);
+        drain_chunk_f16<NB>(acc, tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * (uint32_t)(p.fuse_b ? 2 * p.BN : p.BN), half, p.BN, ck == 0, p.fuse_b != 0);
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         if (PAIR) mbar_arrive_cluster(smem_u32(&tmem_empty_bar[buf]), 0); else mbar_arrive(smem_u32(&tmem_empty_bar[buf]));
         if (DBG) t_drain += clock64() - td0;
@@ -607,28 +641,36 @@ int gemm_tcgen05_f16x3(const dcae_operand* a, const dcae_weight* w, const dcae_e
   while ((1 << p.tw_shift) < p.TW) ++p.tw_shift;
   p.tiles_x = (a->w + p.TW - 1) / p.TW;
   p.tiles_y = (a->h + p.TH - 1) / p.TH;
+  const int m_tiles = p.tiles_x * p.tiles_y * a->B;
+  // thread-block pairs (cta_group::2): DCAE_F16_PAIR = 1 / 0 forces it on / off, default = heuristic below
+  static const int pair_mode = [] { const char* v = getenv("DCAE_F16_PAIR"); return v ? atoi(v) : -1; }();
+  static const int fuse_mode = [] { const char* v = getenv("DCAE_F16_FUSEB"); return v ? atoi(v) : 1; }();
+  // A/B sweeps (profiles/r01/gemm_f16_pair_ab.jsonl, layer_times_bn_pair_sweep3.log): pairs win where the mainloop is
+  // long or wide (cc1, proj, fc1, the K = 2 016 conv layers); everything else runs single-CTA with BN <= 128 so that
+  // the fused [b_hi; b_lo] MMA applies (N = 320 -> 128 + 128 + 64 ragged beats 2 x 160 by 20 %, N = 224 likewise).
+  const bool pair_heur = (int64_t)a->taps * Kp >= 2048 || w->N >= 2048;
+  // The arithmetic (fused or three-MMA accumulation order) follows want_pair, a function of the layer shape only, so
+  // that a result never depends on the batch size (a 1-tile problem cannot pair but keeps the pair path's order).
+  const bool want_pair = pair_mode == 1 || (pair_mode == -1 && pair_heur);
+  const bool pair = want_pair && m_tiles >= 2;
   p.BN = 0;
   if (const char* env = getenv("DCAE_TC_BN")) {        // tuning override; BN need not divide N (ragged last tile)
     const int bn = atoi(env);
     if (bn >= 32 && bn <= 256 && bn % 32 == 0) p.BN = bn;
   }
+  if (p.BN == 0 && !want_pair && fuse_mode != 0) p.BN = w->N >= 128 ? 128 : w->N;
   if (p.BN == 0) {
-    // 256 and 128 first: with the 32 KB of epilogue staging, 128 keeps three 64 KB stages in flight (N = 640: 128 beats
-    // 160, which only fits two); then the largest divisor (672 -> 224, 320 -> 160).  profiles/r01/gemm_f16_sweep.jsonl
+    // 256 and 128 first: with the 32 KB of epilogue staging, 128 keeps three 64 KB stages in flight; then the largest
+    // divisor (672 -> 224).  profiles/r01/gemm_f16_sweep.jsonl
     static const int order[] = {256, 128, 224, 192, 160, 96, 64, 32};
     for (int bn : order)
       if (w->N % bn == 0) { p.BN = bn; break; }
   }
-  DCAE_REQUIRE(p.BN > 0, "gemm(f16x3): N=%d must be a multiple of 32", w->N);
-  p.tmem_cols = 2 * p.BN <= 64 ? 64 : 2 * p.BN <= 128 ? 128 : 2 * p.BN <= 256 ? 256 : 512;
+  DCAE_REQUIRE(p.BN > 0 && p.BN % 32 == 0, "gemm(f16x3): N=%d must be a multiple of 32", w->N);
   p.n_tiles_n = (w->N + p.BN - 1) / p.BN;      // a ragged last tile reads zero-filled weight rows and stores clipped
-  const int m_tiles = p.tiles_x * p.tiles_y * a->B;
-  // thread-block pairs (cta_group::2): DCAE_F16_PAIR = 1 / 0 forces it on / off, default = heuristic below
-  static const int pair_mode = [] { const char* v = getenv("DCAE_F16_PAIR"); return v ? atoi(v) : -1; }();
-  // A/B sweep (profiles/r01/gemm_f16_pair_ab.jsonl): pairs win where the mainloop is long or wide (cc1 +15 %, proj +15 %,
-  // fc1 +11 %) and are neutral or slightly worse on the short 640x640 and the small-N conv layers.
-  const bool pair_heur = (int64_t)a->taps * Kp >= 2048 || w->N >= 2048;
-  const bool pair = m_tiles >= 2 && p.BN % 32 == 0 && (pair_mode == 1 || (pair_mode == -1 && pair_heur));
+  p.fuse_b = (fuse_mode != 0 && !want_pair && p.BN <= 128) ? 1 : 0;
+  const int acc_cols = 2 * (p.fuse_b ? 2 * p.BN : p.BN);          // two chunk buffers
+  p.tmem_cols = acc_cols <= 64 ? 64 : acc_cols <= 128 ? 128 : acc_cols <= 256 ? 256 : 512;
   p.total_tiles = p.n_tiles_n * (pair ? (m_tiles + 1) / 2 : m_tiles);
   p.chunk_kb = CHUNK_MMAS / 12;
   if (const char* env = getenv("DCAE_TC_CHUNK")) { const int v = atoi(env); if (v >= 1) p.chunk_kb = v; }

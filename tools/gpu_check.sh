@@ -16,7 +16,8 @@ run gc        300 python -m pytest tests/test_gpu_gc.py -q -x -m gpu
 run ops_simt  400 python -m pytest tests/test_gpu_ops.py -q -m gpu -k "not tf32"
 run loop_fp32 600 python -m pytest tests/test_gpu_slice_loop.py -q -m gpu -s -k "fp32 or training or validation"
 run ops_tc    400 python -m pytest tests/test_gpu_ops.py -q -m gpu -k "tf32 or f16x3"
-run loop_tc   600 python -m pytest tests/test_gpu_slice_loop.py -q -m gpu -s -k "tf32 or f16x3 or invariance or bpp or kodak or pipeline"
+run loop_tc   600 python -m pytest tests/test_gpu_slice_loop.py -q -m gpu -s -k "not (fp32 or training or validation)"
+run modules   300 python -m pytest tests/test_gpu_modules.py -q -m gpu
 run smoke     300 python -c "import __graft_entry__ as g; g.smoke()"
 run bench_tc  600 python bench.py
 run bench_fp32 600 python bench.py --steps 2 --warmup 3 --math fp32 --no-cpu-baseline
