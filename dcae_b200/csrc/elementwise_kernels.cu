@@ -65,9 +65,10 @@ __global__ void __launch_bounds__(256) gelu_kernel(const float* __restrict__ x, 
 // ---------------------------------------------------------------------------------------------
 // Depthwise 3x3 (stride 1, zero pad 1) on the token grid; weights tap-major [9, C].
 // out = act(dw(x) + bias) * gate
-// Each thread owns 4 channels of DW_X horizontally adjacent tokens: a 3 x (DW_X + 2) input patch is read
-// once (3.75 float4 loads per output instead of 9), consecutive threads take consecutive channel
-// groups so every load/store is a coalesced 16-byte access.
+// Each thread owns 4 channels of DX horizontally adjacent tokens: a 3 x (DX + 2) input patch is read
+// once (4.5 float4 loads per output at DX = 4 instead of 9), consecutive threads take consecutive channel
+// groups so every load/store is a coalesced 16-byte access.  DX = 4 (72 registers) measured 8 % / 23 % faster than
+// DX = 8 (104 registers, 25 % occupancy) on the 640- / 1280-channel GLU launch, DX = 2 slower again (DCAE_DW_X).
 // ---------------------------------------------------------------------------------------------
 constexpr int DW_X = 8, DW_ROWS = 4;
 
@@ -75,18 +76,18 @@ constexpr int DW_X = 8, DW_ROWS = 4;
 // three input rows a thread needs are shared with its neighbours in the block through L1.
 // ACT: 0 none, 1 GELU (erff form, the fp32 path), 2 GELU through gelu_fast (planes-only output, i.e. the tensor-core
 // modes: measured issue-bound on erff, 67% issue utilisation at 25% occupancy, before the switch).
-template <int ACT>
+template <int ACT, int DX>
 __global__ void __launch_bounds__(32 * DW_ROWS) dwconv3x3_kernel(const float* __restrict__ x, int64_t x_ld,
                                                         const float* __restrict__ wt, const float* __restrict__ bias,
                                                         int C4, int B, int h, int w,
                                                         const float* __restrict__ gate, int64_t gate_ld,
                                                         float* __restrict__ out, int64_t out_ld, const dcae_planes o16) {
-  const int xg = (w + DW_X - 1) / DW_X;
+  const int xg = (w + DX - 1) / DX;
   const int C = C4 * 4;
   const int c4 = blockIdx.x * 32 + (threadIdx.x & 31);
   const int yy = blockIdx.y * DW_ROWS + (threadIdx.x >> 5);
   const int b = blockIdx.z / xg;
-  const int x0 = (blockIdx.z - b * xg) * DW_X;
+  const int x0 = (blockIdx.z - b * xg) * DX;
   if (c4 >= C4 || yy >= h) return;
   {
     const int c = c4 * 4;
@@ -94,23 +95,23 @@ __global__ void __launch_bounds__(32 * DW_ROWS) dwconv3x3_kernel(const float* __
 #pragma unroll
     for (int t = 0; t < 9; ++t) k[t] = __ldg(reinterpret_cast<const float4*>(wt + t * C + c));
     const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + c));
-    float4 acc[DW_X];
+    float4 acc[DX];
 #pragma unroll
-    for (int j = 0; j < DW_X; ++j) acc[j] = bv;
+    for (int j = 0; j < DX; ++j) acc[j] = bv;
 #pragma unroll
     for (int dy = -1; dy <= 1; ++dy) {
       const int y2 = yy + dy;
       if ((unsigned)y2 >= (unsigned)h) continue;
       const float* row = x + ((int64_t)(b * h + y2) * w) * x_ld + c;
-      float4 p[DW_X + 2];
+      float4 p[DX + 2];
 #pragma unroll
-      for (int j = 0; j < DW_X + 2; ++j) {
+      for (int j = 0; j < DX + 2; ++j) {
         const int x2 = x0 - 1 + j;
         p[j] = ((unsigned)x2 < (unsigned)w) ? __ldg(reinterpret_cast<const float4*>(row + (int64_t)x2 * x_ld))
                                             : make_float4(0.f, 0.f, 0.f, 0.f);
       }
 #pragma unroll
-      for (int j = 0; j < DW_X; ++j) {
+      for (int j = 0; j < DX; ++j) {
 #pragma unroll
         for (int dx = 0; dx < 3; ++dx) {
           const float4 kk = k[(dy + 1) * 3 + dx];
@@ -121,7 +122,7 @@ __global__ void __launch_bounds__(32 * DW_ROWS) dwconv3x3_kernel(const float* __
       }
     }
 #pragma unroll
-    for (int j = 0; j < DW_X; ++j) {
+    for (int j = 0; j < DX; ++j) {
       const int x2 = x0 + j;
       if (x2 >= w) break;
       const int64_t t = (int64_t)(b * h + yy) * w + x2;
@@ -339,13 +340,16 @@ extern "C" int dcae_op_dwconv3x3(const float* x, int64_t x_ld, const float* wt, 
   DCAE_REQUIRE(aligned16(x) && aligned16(wt) && aligned16(bias) && aligned16(out) && aligned16(gate), "dcae_op_dwconv3x3: 16-byte alignment required");
   DCAE_REQUIRE(act == DCAE_ACT_NONE || act == DCAE_ACT_GELU, "dcae_op_dwconv3x3: act must be NONE or GELU");
   if ((int64_t)B * h * w == 0) return DCAE_OK;
-  const int xg = (w + DW_X - 1) / DW_X;
+  static const int dw_x = [] { const char* v = getenv("DCAE_DW_X"); const int x = v ? atoi(v) : 4; return (x == 2 || x == 4 || x == 8) ? x : 4; }();
+  const int xg = (w + dw_x - 1) / dw_x;
   DCAE_REQUIRE((int64_t)B * xg <= 65535 && (h + DW_ROWS - 1) / DW_ROWS <= 65535, "dcae_op_dwconv3x3: token grid too large");
   dim3 grid((unsigned)((C / 4 + 31) / 32), (unsigned)((h + DW_ROWS - 1) / DW_ROWS), (unsigned)(B * xg));
   const int variant = act == DCAE_ACT_NONE ? 0 : (out == nullptr ? 2 : 1);
-  if (variant == 0) dwconv3x3_kernel<0><<<grid, 32 * DW_ROWS, 0, (cudaStream_t)stream>>>(x, x_ld, wt, bias, C / 4, B, h, w, gate, gate_ld, out, out_ld, o16);
-  else if (variant == 1) dwconv3x3_kernel<1><<<grid, 32 * DW_ROWS, 0, (cudaStream_t)stream>>>(x, x_ld, wt, bias, C / 4, B, h, w, gate, gate_ld, out, out_ld, o16);
-  else dwconv3x3_kernel<2><<<grid, 32 * DW_ROWS, 0, (cudaStream_t)stream>>>(x, x_ld, wt, bias, C / 4, B, h, w, gate, gate_ld, out, out_ld, o16);
+#define DW_LAUNCH(A, X) dwconv3x3_kernel<A, X><<<grid, 32 * DW_ROWS, 0, (cudaStream_t)stream>>>(x, x_ld, wt, bias, C / 4, B, h, w, gate, gate_ld, out, out_ld, o16)
+  if (dw_x == 4) { if (variant == 0) DW_LAUNCH(0, 4); else if (variant == 1) DW_LAUNCH(1, 4); else DW_LAUNCH(2, 4); }
+  else if (dw_x == 2) { if (variant == 0) DW_LAUNCH(0, 2); else if (variant == 1) DW_LAUNCH(1, 2); else DW_LAUNCH(2, 2); }
+  else { if (variant == 0) DW_LAUNCH(0, 8); else if (variant == 1) DW_LAUNCH(1, 8); else DW_LAUNCH(2, 8); }
+#undef DW_LAUNCH
   DCAE_LAUNCH_CHECK();
   return DCAE_OK;
 }
