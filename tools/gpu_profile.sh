@@ -3,7 +3,7 @@
 # One lane and a short warm-up so that launch indices are predictable: 6 steps (1 buffer + 2 pipeline + 3 warm-up)
 # precede the 2 timed ones; a step is 110 GEMM, 5 attention, 5 kernel-3 and 47 element-wise launches.
 mkdir -p gpurun_out; cd "$(dirname "$0")/.."
-CMD="python bench.py --steps 2 --warmup 3 --warmup-seconds 0 --no-cpu-baseline --gc-micro-mb 256 --lanes 1"
+CMD="python bench.py --steps 2 --warmup 3 --warmup-seconds 0 --no-cpu-baseline --no-gpu-baseline --gc-micro-mb 256 --lanes 1"
 $CMD > gpurun_out/plain.log 2>&1 || { tail -5 gpurun_out/plain.log; exit 1; }
 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/launches_all.csv $CMD > gpurun_out/ncu_launches.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:gemm_f16x3 -s 700 -c 6 -o gpurun_out/prof_gemm $CMD > gpurun_out/ncu_gemm.log 2>&1
