@@ -305,3 +305,20 @@ def test_baseline_config_shapes(name, B, h, w, lively_params):
     assert torch.equal(sym, enc["symbols"])
     dec = eng.decompress(lsc, lmc, lambda i, idx: enc["symbols"][i])
     assert torch.equal(dec["indexes"], enc["indexes"]) and torch.equal(dec["y_hat"], enc["y_hat"])
+
+
+@pytest.mark.parametrize("B,h,w", [(1, 5, 17), (3, 13, 6), (2, 1, 1), (1, 24, 40), (5, 9, 9)])
+@pytest.mark.parametrize("math", ["f16x3", "tf32x3"])
+def test_ragged_shapes_against_the_oracle(B, h, w, math, lively_params):
+    """Token grids that are not multiples of the 8x16 / 128-token tiles, odd batches (lanes of unequal size), a single
+    token: slice 0 against the CPU oracle (nothing has cascaded yet) + round trip of the whole loop."""
+    eng = engine(lively_params, math)
+    gen = torch.Generator().manual_seed(100 * B + 10 * h + w)
+    y = 4 * torch.randn(B, 320, h, w, generator=gen)
+    ls, lm = torch.randn(B, 320, h, w, generator=gen), torch.randn(B, 320, h, w, generator=gen)
+    enc = eng.compress(y.cuda(), ls.cuda(), lm.cuda(), with_likelihoods=True)
+    _, mu0, sc0 = SliceLoopOracle(lively_params).slice_params(0, ls, lm, [])
+    assert rel_err(enc["means"][:, :64].cpu(), mu0) < FP32_TOL and rel_err(enc["scales"][:, :64].cpu(), sc0) < FP32_TOL
+    assert bool(torch.isfinite(enc["y_hat"]).all()) and bool(((enc["likelihoods"] >= 1e-9) & (enc["likelihoods"] <= 1)).all())
+    dec = eng.decompress(ls.cuda(), lm.cuda(), lambda i, idx: enc["symbols"][i])
+    assert torch.equal(dec["indexes"], enc["indexes"]) and torch.equal(dec["y_hat"], enc["y_hat"])
