@@ -672,7 +672,7 @@ int gemm_tcgen05_f16x3(const dcae_operand* a, const dcae_weight* w, const dcae_e
   const int acc_cols = 2 * (p.fuse_b ? 2 * p.BN : p.BN);          // two chunk buffers
   p.tmem_cols = acc_cols <= 64 ? 64 : acc_cols <= 128 ? 128 : acc_cols <= 256 ? 256 : 512;
   p.total_tiles = p.n_tiles_n * (pair ? (m_tiles + 1) / 2 : m_tiles);
-  p.chunk_kb = CHUNK_MMAS / 12;
+  p.chunk_kb = CHUNK_MMAS / (p.fuse_b ? 8 : 12);      // accumulation chain per column: 2 (fused) or 3 MMAs per K = 16 step, 4 steps per k-block
   if (const char* env = getenv("DCAE_TC_CHUNK")) { const int v = atoi(env); if (v >= 1) p.chunk_kb = v; }
   p.descale = w->descale;
   p.dbg_nostore = getenv("DCAE_TC_NOSTORE") != nullptr;

@@ -178,6 +178,7 @@ def test_lanes_do_not_change_any_output_bit(math, lively_params):
     ls, lm = torch.randn(B, 320, h, w, generator=gen).cuda(), torch.randn(B, 320, h, w, generator=gen).cuda()
     one = EntropySliceLoop(lively_params, device="cuda:0", math=math, lanes=1)
     two = EntropySliceLoop(lively_params, device="cuda:0", math=math, lanes=2)
+    two.LANE_MIN_TOKENS = 0           # lanes normally engage from 8 192 tokens per step; force them for this small case
     a = one.compress(y, ls, lm, with_likelihoods=True)
     b = two.compress(y, ls, lm, with_likelihoods=True)
     for k in ("means", "scales", "y_hat", "likelihoods", "symbols", "indexes"):
@@ -322,3 +323,24 @@ def test_ragged_shapes_against_the_oracle(B, h, w, math, lively_params):
     assert bool(torch.isfinite(enc["y_hat"]).all()) and bool(((enc["likelihoods"] >= 1e-9) & (enc["likelihoods"] <= 1)).all())
     dec = eng.decompress(ls.cuda(), lm.cuda(), lambda i, idx: enc["symbols"][i])
     assert torch.equal(dec["indexes"], enc["indexes"]) and torch.equal(dec["y_hat"], enc["y_hat"])
+
+
+def test_cuda_graph_replay_equals_stream_launches(lively_params):
+    """`capture()`: the whole step (both lanes, the side stream, 173 launches) as one CUDA graph; inputs by address."""
+    eng = engine(lively_params, "f16x3")
+    gen = torch.Generator().manual_seed(9)
+    y = (4 * torch.randn(2, 320, 16, 16, generator=gen)).cuda()
+    ls, lm = torch.randn(2, 320, 16, 16, generator=gen).cuda(), torch.randn(2, 320, 16, 16, generator=gen).cuda()
+    replay, out = eng.capture(y, ls, lm, want_symbols=True)
+    want = {k: v.clone() for k, v in eng.forward(y, ls, lm, want_symbols=True).items()}
+    for v in out.values():
+        v.zero_()
+    replay()
+    torch.cuda.synchronize()
+    for k in ("y_hat", "means", "scales", "likelihoods", "symbols", "indexes"):
+        assert torch.equal(out[k], want[k]), k
+    y.mul_(0.5)                                   # new data at the same addresses
+    replay()
+    torch.cuda.synchronize()
+    again = eng.forward(y, ls, lm, want_symbols=True)
+    assert torch.equal(out["symbols"], again["symbols"]) and torch.equal(out["y_hat"], again["y_hat"])

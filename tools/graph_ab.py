@@ -5,10 +5,9 @@ sys.path.insert(0, ROOT)
 import torch
 from dcae_b200.entropy_model import EntropySliceLoop
 from dcae_b200.params import init_entropy_params
-B, h, w = 16, 32, 48
+SHAPES = [(16, 32, 48), (1, 16, 16), (1, 88, 128), (4, 16, 16)]
 params = init_entropy_params(0, "lively")
 g = torch.Generator().manual_seed(1)
-x = [4 * torch.randn(B, 320, h, w, generator=g).cuda(), torch.randn(B, 320, h, w, generator=g).cuda(), torch.randn(B, 320, h, w, generator=g).cuda()]
 def timeit(fn, n=10):
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -16,7 +15,11 @@ def timeit(fn, n=10):
     for _ in range(n): fn()
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n
-for lanes in (1, 2):
+import itertools
+for (B, h, w), lanes in itertools.product(SHAPES, (1, 2)):
+    if lanes == 2 and B == 1:
+        continue
+    x = [4 * torch.randn(B, 320, h, w, generator=g).cuda(), torch.randn(B, 320, h, w, generator=g).cuda(), torch.randn(B, 320, h, w, generator=g).cuda()]
     eng = EntropySliceLoop(params, math="f16x3", lanes=lanes)
     out = eng.forward(*x)
     for _ in range(20): eng.forward(*x, out=out)
@@ -30,4 +33,4 @@ for lanes in (1, 2):
     same = all(torch.equal(out[k], ref[k]) for k in ("y_hat", "means", "scales", "likelihoods"))
     a = [timeit(lambda: eng.forward(*x, out=out)) for _ in range(5)]
     b = [timeit(gr.replay) for _ in range(5)]
-    print(f"lanes={lanes}: stream {statistics.median(a):.3f} ms  graph {statistics.median(b):.3f} ms  identical={same}")
+    print(f"B={B} {h}x{w} lanes={lanes}: stream {statistics.median(a):.3f} ms  graph {statistics.median(b):.3f} ms  identical={same}")
