@@ -51,6 +51,7 @@ struct F16Params {
   float descale;
   int dbg_nostore;
   int has_o32, has_o16, has_o16a;
+  int pdl;                   // launched with programmatic stream serialization: see griddepcontrol below
   int fuse_b;                // single CTA, BN <= 128: one N = 2 BN MMA covers a_hi x [b_hi; b_lo], see the MMA issuer
   uint32_t stage_bytes, b_bytes;
   unsigned long long* dbg;   // DCAE_F16_DBG=1: per-CTA role counters (16 u64 each), see dump in the host wrapper
@@ -310,6 +311,15 @@ __device__ __forceinline__ void gemm_f16x3_body(const CUtensorMap& map_ah, const
   if (PAIR) cluster_sync_all();     // the peer's barriers exist before anything signals them
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_base_slot;
+  // Programmatic dependent launch: this grid may have become resident while the previous kernel of the stream was
+  // still draining (its CTAs leave one by one: 8-10 us of exit skew); barrier init, TMEM allocation and the
+  // tensor-map prefetch above overlapped with that tail.  Nothing before this line touches global memory a
+  // predecessor writes; from here on the predecessor has completed and its writes are visible.  Our own successor
+  // may be scheduled as soon as every CTA has passed this point.
+  if (p.pdl) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  }
 
   // per-stage smem: [A_hi | A_lo | B_hi | B_lo]; the two epilogue staging buffers follow the stages
   const uint32_t off_al = A16_BYTES, off_bh = 2 * A16_BYTES, off_bl = off_bh + p.b_bytes;
@@ -749,21 +759,38 @@ int gemm_tcgen05_f16x3(const dcae_operand* a, const dcae_weight* w, const dcae_e
     DCAE_CUDA(cudaMalloc(&p.dbg, (size_t)n_ctas * 24 * sizeof(unsigned long long)));
     DCAE_CUDA(cudaMemsetAsync(p.dbg, 0, (size_t)n_ctas * 24 * sizeof(unsigned long long), s));
   }
+  // Opt-in (DCAE_F16_PDL=1).  Measured at config #2 (tools/lanes_ab.py, medians of 8 x 10 steps): one lane 13.67 ->
+  // 13.58 ms, two lanes 13.60 -> 13.74 ms -- the early-resident CTAs of the successor hold SMs the other lane's
+  // kernels would have used, and the chip is power-capped either way.
+  static const int pdl_mode = [] { const char* v = getenv("DCAE_F16_PDL"); return v ? atoi(v) : 0; }();
+  p.pdl = (pdl_mode != 0 && !dbg_on) ? 1 : 0;
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(NTHREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute pdl_attr[1];
+  pdl_attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  pdl_attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = pdl_attr;
+  cfg.numAttrs = p.pdl ? 1 : 0;
   if (pair) {
     const int max_pairs = num_sms() / 2;
     const int pairs = p.total_tiles < max_pairs ? p.total_tiles : max_pairs;
+#define F16_LAUNCH_ONE(KERNEL, GRID) DCAE_CUDA(cudaLaunchKernelEx(&cfg, KERNEL, map_ah, map_al, map_bh, map_bl, map_o32, map_oh, map_ol, map_oha, map_ola, p))
 #define F16_LAUNCH(KERNEL, GRID)                                                                                      \
   do {                                                                                                                \
-    if (dbg_on && p.BN <= 128) KERNEL<true, 2><<<GRID, NTHREADS, smem, s>>>(map_ah, map_al, map_bh, map_bl, map_o32, map_oh, map_ol, map_oha, map_ola, p);       \
-    else if (dbg_on) KERNEL<true, 4><<<GRID, NTHREADS, smem, s>>>(map_ah, map_al, map_bh, map_bl, map_o32, map_oh, map_ol, map_oha, map_ola, p);               \
-    else if (p.BN <= 128) KERNEL<false, 2><<<GRID, NTHREADS, smem, s>>>(map_ah, map_al, map_bh, map_bl, map_o32, map_oh, map_ol, map_oha, map_ola, p);         \
-    else KERNEL<false, 4><<<GRID, NTHREADS, smem, s>>>(map_ah, map_al, map_bh, map_bl, map_o32, map_oh, map_ol, map_oha, map_ola, p);                           \
+    cfg.gridDim = dim3((unsigned)(GRID));                                                                             \
+    if (dbg_on && p.BN <= 128) F16_LAUNCH_ONE((KERNEL<true, 2>), GRID);                                               \
+    else if (dbg_on) F16_LAUNCH_ONE((KERNEL<true, 4>), GRID);                                                         \
+    else if (p.BN <= 128) F16_LAUNCH_ONE((KERNEL<false, 2>), GRID);                                                   \
+    else F16_LAUNCH_ONE((KERNEL<false, 4>), GRID);                                                                    \
   } while (0)
     F16_LAUNCH(gemm_f16x3_pair_kernel, 2 * pairs);
   } else {
     const int ctas = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
     F16_LAUNCH(gemm_f16x3_kernel, ctas);
 #undef F16_LAUNCH
+#undef F16_LAUNCH_ONE
   }
   DCAE_LAUNCH_CHECK();
   if (dbg_on) {
