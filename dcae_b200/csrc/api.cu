@@ -65,7 +65,7 @@ extern "C" int dcae_profile_dump(const char* path, double* ms, double* work, int
   g_prof_on = false;
   DCAE_CUDA(cudaDeviceSynchronize());
   FILE* f = path ? fopen(path, "w") : nullptr;
-  if (f) fprintf(f, "index,family,work,ms\n");
+  if (f) fprintf(f, "index,family,work,ms,start_ms\n");
   for (int k = 0; k < DCAE_PROF_FAMILIES; ++k) { ms[k] = 0; work[k] = 0; launches[k] = 0; }
   int i = 0;
   for (const ProfRec& r : g_prof) {
@@ -74,7 +74,11 @@ extern "C" int dcae_profile_dump(const char* path, double* ms, double* work, int
     ms[r.family] += t;
     work[r.family] += r.work;
     launches[r.family] += 1;
-    if (f) fprintf(f, "%d,%d,%.6g,%.6f\n", i, r.family, r.work, t);
+    if (f) {
+      float t0 = 0.f;                                  // start of this op relative to the first recorded one
+      DCAE_CUDA(cudaEventElapsedTime(&t0, g_prof.front().a, r.a));
+      fprintf(f, "%d,%d,%.6g,%.6f,%.6f\n", i, r.family, r.work, t, t0);
+    }
     ++i;
   }
   if (f) fclose(f);

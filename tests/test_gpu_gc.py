@@ -179,3 +179,21 @@ def test_large_input_properties_and_log2_sum():
     # run-to-run determinism
     sym2, idx2, y_hat2, lik2 = gc.fused(yc, sc, mc)
     assert torch.equal(lik, lik2) and torch.equal(sym, sym2) and torch.equal(idx, idx2)
+
+
+def test_kernel3_against_the_plain_c_oracle():
+    """A second, torch-free checker (oracle/gc_oracle.c, glibc erfcf): symbols / indexes / y_hat bit-exact, likelihood
+    within the same 1e-5 relative + 4 ulp(0.5) bar."""
+    import __graft_entry__ as ge
+    ge.build()
+    from oracle import gc_c
+    if not gc_c.available():
+        pytest.skip("oracle/_build/libgc_oracle.so not built (no gcc)")
+    gc = _gc()
+    y, mu, scale = _direct_inputs((2, 64, 24, 40), seed=99)
+    sym, idx, y_hat, lik = gc.fused(y.cuda(), scale.cuda(), mu.cuda())
+    assert torch.equal(sym.cpu(), gc_c.symbols(y, mu))
+    assert torch.equal(idx.cpu(), gc_c.build_indexes(scale, orc.get_scale_table()))
+    want_hat, want_lik = gc_c.forward_eval(y, scale, mu)
+    assert torch.equal(y_hat.cpu(), want_hat)
+    _assert_lik_close(lik.cpu(), want_lik)

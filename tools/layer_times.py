@@ -34,3 +34,9 @@ for sl in (0, 4):
         print(f"{n:13s} {t * 1e3:8.1f} us  {fl / (t * 1e-3) / 1e12 * 3:7.1f} TF-MMA  (N*K = {fl / (2 * T):.0f})")
 others = [r for r in rows if r["family"] == "3"]
 print("other ops (first slice):", [round(float(r["ms"]) * 1e3, 1) for r in others[:20]])
+
+# idle time between consecutive ops of the (single-lane, single-stream) step: start of op i+1 minus end of op i
+gaps = [float(b["start_ms"]) - (float(a["start_ms"]) + float(a["ms"])) for a, b in zip(rows, rows[1:])]
+span = float(rows[-1]["start_ms"]) + float(rows[-1]["ms"])
+print(f"step span {span:.3f} ms, sum of op times {sum(float(r['ms']) for r in rows):.3f} ms, sum of gaps {sum(gaps):.3f} ms "
+      f"(mean {1e3 * sum(gaps) / len(gaps):.2f} us, max {1e3 * max(gaps):.1f} us over {len(gaps)} transitions)")
