@@ -250,56 +250,70 @@ struct EpiTile {
   int dbg;                  // tuning experiments (env DCAE_TC_EPI): 1 = skip transpose, 2 = skip global stores
 };
 
-// Row-per-lane epilogue of one 32-column block held in r[0..32): bias / addend / activation / scaled
-// residual, eight 16-byte stores per thread.  ACT is a compile-time activation: with a run-time switch the
-// compiler if-converts and evaluates erf AND tanh for every element of every layer (measured: that, not the
-// store pattern, was what made the epilogue slower than the single-pass mainloop).
-template <int ACT>
-__device__ __forceinline__ void epi_block(const float* r, const dcae_epilogue& e, int64_t token, int n0) {
+// Row-per-lane epilogue of one 32-column block held in r[0..32): bias / addend / activation / scaled residual, eight
+// 16-byte stores per thread.  One instance with a run-time activation whose branches are disjoint loops (nothing for
+// ptxas to if-convert into "evaluate erf AND tanh for every element"), called from a ROLLED block loop: fully unrolled
+// (4 blocks x 3 activations) the epilogue was straight-line code that every warp ran once per tile, and instruction
+// fetch set its time (kernel 2).
+__device__ __forceinline__ void epi_block(float* r, const dcae_epilogue& e, int act, int64_t token, int n0) {
+  if (e.bias) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 bv = __ldg(reinterpret_cast<const float4*>(e.bias + n0 + j));
+      r[j] += bv.x; r[j + 1] += bv.y; r[j + 2] += bv.z; r[j + 3] += bv.w;
+    }
+  }
+  if (e.addend) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 ad = __ldg(reinterpret_cast<const float4*>(e.addend + token * e.addend_ld + n0 + j));
+      r[j] += ad.x; r[j + 1] += ad.y; r[j + 2] += ad.z; r[j + 3] += ad.w;
+    }
+  }
+  if (act == DCAE_ACT_GELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) r[j] = gelu_fast(r[j]);
+  } else if (act == DCAE_ACT_HALF_TANH) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) r[j] = 0.5f * tanhf(r[j]);
+  }
+  if (e.residual) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 rv = __ldg(reinterpret_cast<const float4*>(e.residual + token * e.residual_ld + n0 + j));
+      float4 rs = make_float4(1.f, 1.f, 1.f, 1.f);
+      if (e.res_scale) rs = __ldg(reinterpret_cast<const float4*>(e.res_scale + n0 + j));
+      r[j] = fmaf(rv.x, rs.x, r[j]); r[j + 1] = fmaf(rv.y, rs.y, r[j + 1]);
+      r[j + 2] = fmaf(rv.z, rs.z, r[j + 2]); r[j + 3] = fmaf(rv.w, rs.w, r[j + 3]);
+    }
+  }
   float* orow = e.out ? e.out + token * e.out_ld + n0 : nullptr;
 #pragma unroll
   for (int j = 0; j < 32; j += 4) {
-    const int n = n0 + j;
-    float4 v = make_float4(r[j], r[j + 1], r[j + 2], r[j + 3]);
-    if (e.bias) {
-      const float4 bv = __ldg(reinterpret_cast<const float4*>(e.bias + n));
-      v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
-    }
-    if (e.addend) {
-      const float4 ad = __ldg(reinterpret_cast<const float4*>(e.addend + token * e.addend_ld + n));
-      v.x += ad.x; v.y += ad.y; v.z += ad.z; v.w += ad.w;
-    }
-    if (ACT == DCAE_ACT_GELU) { v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w); }
-    if (ACT == DCAE_ACT_HALF_TANH) { v.x = 0.5f * tanhf(v.x); v.y = 0.5f * tanhf(v.y); v.z = 0.5f * tanhf(v.z); v.w = 0.5f * tanhf(v.w); }
-    if (e.residual) {
-      const float4 rv = __ldg(reinterpret_cast<const float4*>(e.residual + token * e.residual_ld + n));
-      float4 rs = make_float4(1.f, 1.f, 1.f, 1.f);
-      if (e.res_scale) rs = __ldg(reinterpret_cast<const float4*>(e.res_scale + n));
-      v.x = fmaf(rv.x, rs.x, v.x); v.y = fmaf(rv.y, rs.y, v.y); v.z = fmaf(rv.z, rs.z, v.z); v.w = fmaf(rv.w, rs.w, v.w);
-    }
+    const float4 v = make_float4(r[j], r[j + 1], r[j + 2], r[j + 3]);
     if (orow) *reinterpret_cast<float4*>(orow + j) = v;
-    if (e.out16.hi) store_planes4(e.out16, token, n, v);
+    if (e.out16.hi) store_planes4(e.out16, token, n0 + j, v);
   }
 }
 
 // out = act(acc + bias + addend) + residual * res_scale for this thread's row.  act_cols (columns that get the
-// activation) must be a multiple of 32 when it is smaller than N: a 32-column block is all-or-nothing.
+// activation) must be a multiple of 32 when it is smaller than N: a 32-column block is all-or-nothing.  The
+// accumulator registers need static indices, so the block being processed is always acc[0..32) and the queue
+// shifts down by register moves after each block (acc is consumed).
 __device__ __forceinline__ void epilogue_store(float* acc, const dcae_epilogue& e, const EpiTile& t, int quarter, int half, int lane) {
   const int act_cols = (e.act_cols <= 0 || e.act_cols > t.N) ? t.N : e.act_cols;
   const int row = quarter * 32 + lane;
   const int yy = t.y0 + (row >> t.tw_shift), xx = t.x0 + (row & ((1 << t.tw_shift) - 1));
   if (t.b >= t.B || yy >= t.h || xx >= t.w) return;
   const int64_t token = ((int64_t)t.b * t.h + yy) * t.w + xx;
-#pragma unroll
+#pragma unroll 1
   for (int g = 0; g < EPI_BLOCKS; ++g) {
     const int blk = 2 * g + half;
-    if (blk * 32 < t.BN) {
-      const int nb0 = t.n0 + blk * 32;
-      const int act = (nb0 < act_cols) ? e.act : DCAE_ACT_NONE;   // uniform over the block
-      if (act == DCAE_ACT_GELU) epi_block<DCAE_ACT_GELU>(acc + g * 32, e, token, nb0);
-      else if (act == DCAE_ACT_HALF_TANH) epi_block<DCAE_ACT_HALF_TANH>(acc + g * 32, e, token, nb0);
-      else epi_block<DCAE_ACT_NONE>(acc + g * 32, e, token, nb0);
-    }
+    if (blk * 32 >= t.BN) break;
+    const int nb0 = t.n0 + blk * 32;
+    epi_block(acc, e, (nb0 < act_cols) ? e.act : DCAE_ACT_NONE, token, nb0);
+#pragma unroll
+    for (int i = 0; i < (EPI_BLOCKS - 1) * 32; ++i) acc[i] = acc[i + 32];
   }
 }
 
