@@ -143,15 +143,15 @@ def cpu_oracle_rate(n_images, steps, warmup, seed=0):
     return n_images / dt, threads, dt
 
 
-def gpu_eager_rate(dev, n_images, steps, warmup, seed=0):
+def gpu_eager_rate(dev, n_images, steps, warmup, seed=0, tf32=False):
     """The same oracle port run by eager PyTorch ON THE GPU (fp32, TF32 off as eval.py:3182-3187 sets it): what a user
     of the reference gets on this B200 without this library.  A baseline leg like cpu_baseline: it only times the
     checker, nothing of it is on the product path.  Returns (images/s, seconds per step)."""
     from dcae_b200.params import init_entropy_params
     from oracle.entropy_model import SliceLoopOracle
-    tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
-    torch.backends.cuda.matmul.allow_tf32 = False
-    torch.backends.cudnn.allow_tf32 = False
+    saved = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = tf32
+    torch.backends.cudnn.allow_tf32 = tf32
     try:
         params = {k: v.to(dev) for k, v in init_entropy_params(seed, "lively").items()}
         orc = SliceLoopOracle(params, scale_table=None)
@@ -169,7 +169,7 @@ def gpu_eager_rate(dev, n_images, steps, warmup, seed=0):
         dt = e0.elapsed_time(e1) * 1e-3 / max(steps, 1)
         return n_images / dt, dt
     finally:
-        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = saved
 
 
 def run_reference(args):
@@ -362,8 +362,11 @@ def main():
         torch.cuda.empty_cache()
         try:
             rate, dt = gpu_eager_rate(dev, B, 2, 1)
+            rate_tf32, dt_tf32 = gpu_eager_rate(dev, B, 2, 1, tf32=True)
             torch_gpu_baseline = {"value": rate, "unit": "images/s", "ms_per_step": dt * 1e3, "kind": "port",
-                                  "sample": f"2 steps x {B} images of 768x512: the oracle port run by eager PyTorch on this GPU (fp32, TF32 off, cuDNN on)"}
+                                  "sample": f"2 steps x {B} images of 768x512: the oracle port run by eager PyTorch on this GPU (fp32, TF32 off, cuDNN on)",
+                                  "tf32_on": {"value": rate_tf32, "ms_per_step": dt_tf32 * 1e3,
+                                              "note": "same with allow_tf32 = True for matmul and cuDNN (reduced precision: not the parity setting)"}}
         except Exception as e:                      # noqa: BLE001  (a baseline leg must never take the bench line down)
             torch_gpu_baseline = {"value": None, "error": repr(e)[:200]}
 
