@@ -32,7 +32,8 @@ namespace {
 
 constexpr int AF_M = 128;                         // tokens per tile
 constexpr int AF_HEADS = 20, AF_HD = 32, AF_ND = 128;
-constexpr int AF_THREADS = 320;
+constexpr int AF_SUB = 4;                         // softmax threads per token row (column quarters of 32)
+constexpr int AF_THREADS = 64 + AF_SUB * 128;     // warps 0 TMA, 1 MMA, then AF_SUB x 4 softmax warps
 constexpr int AF_QK_BYTES = AF_M * 128;           // 16 KB: a [128 x 64 halfs] tile (Q or K of a head pair, one plane)
 constexpr int AF_V_BYTES = 64 * 128;              // 8 KB: V^T chunk [64 rows (2 heads x 32 dims) x 64 entries], one plane
 constexpr int AF_STAGE = 4 * AF_QK_BYTES + 4 * AF_V_BYTES;   // 96 KB per head PAIR
@@ -76,7 +77,7 @@ dict_attention_f16_kernel(const __grid_constant__ CUtensorMap map_qh, const __gr
   __shared__ __align__(8) uint64_t full_bar[AF_STAGES], empty_bar[AF_STAGES];
   __shared__ __align__(8) uint64_t s_full[2], p_ready[2], o_full[2], o_free[2];
   __shared__ uint32_t tmem_base_slot;
-  __shared__ float xm[2][2][AF_M], xl[2][2][AF_M];    // row max / row sum of each column half, double-buffered by head parity
+  __shared__ float xm[2][AF_SUB][AF_M], xl[2][AF_SUB][AF_M];    // row max / row sum of each column range, double-buffered by head parity
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp: provably uniform
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -88,9 +89,9 @@ dict_attention_f16_kernel(const __grid_constant__ CUtensorMap map_qh, const __gr
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(smem_u32(&s_full[b]), 1);
-      mbar_init(smem_u32(&p_ready[b]), 256);
+      mbar_init(smem_u32(&p_ready[b]), AF_SUB * 128);
       mbar_init(smem_u32(&o_full[b]), 1);
-      mbar_init(smem_u32(&o_free[b]), 256);
+      mbar_init(smem_u32(&o_free[b]), AF_SUB * 128);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -193,30 +194,36 @@ dict_attention_f16_kernel(const __grid_constant__ CUtensorMap map_qh, const __gr
       }
     }
   } else {
-    // ===================== softmax warps: one token row per PAIR of threads =====================
-    // Warp w and w + 4 own the same 32 TMEM lanes (rows); each takes 64 of the 128 dictionary columns.
-    const int quarter = warp & 3, hf = (warp - 2) >> 2;
+    // ===================== softmax warps: AF_SUB threads per token row =====================
+    // Warps w, w + 4, w + 8, ... own the same 32 TMEM lanes (rows); each takes 128 / AF_SUB dictionary columns, so every
+    // scheduler has AF_SUB softmax warps to alternate between.  Row max and row sum cross the group through shared
+    // memory with one named barrier (AF_SUB x 32 threads) per head.
+    const int quarter = warp & 3, sub = (warp - 2) >> 2;
     const int r = quarter * 32 + lane;
     const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
-    constexpr int HC = AF_ND / 2;     // columns per thread
-    auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory"); };
+    constexpr int HC = AF_ND / AF_SUB;     // columns per thread (32)
+    constexpr int OC = AF_HD / AF_SUB;     // output columns per thread (8)
+    auto row_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(1 + quarter), "n"(AF_SUB * 32) : "memory"); };
     auto write_out = [&](int g) {
       const int gp = (int)blockIdx.x + (g >> 1) * (int)gridDim.x;
       const int tile = gp / HP, head = (gp % HP) * 2 + (g & 1);
-      const float inv = p.v_descale / (xl[g & 1][0][r] + xl[g & 1][1][r]);
+      float l = 0.f;
+#pragma unroll
+      for (int q = 0; q < AF_SUB; ++q) l += xl[g & 1][q][r];
+      const float inv = p.v_descale / l;
       mbar_wait(smem_u32(&o_full[g & 1]), (g >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      uint32_t o0[16];
-      tmem_ld16_nowait(lane_addr + TF_O + (uint32_t)(g & 1) * 32 + hf * 16, o0);
+      uint32_t o0[OC];
+      tmem_ld8_nowait(lane_addr + TF_O + (uint32_t)(g & 1) * 32 + sub * OC, o0);
       tmem_ld_wait();
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive(smem_u32(&o_free[g & 1]));
       const int64_t token = (int64_t)tile * AF_M + r;
       if (token < p.T) {
-        const int col = head * AF_HD + hf * 16;
+        const int col = head * AF_HD + sub * OC;
         float4* dst = p.out ? reinterpret_cast<float4*>(p.out + token * p.out_ld + col) : nullptr;
 #pragma unroll
-        for (int j = 0; j < 16; j += 4) {
+        for (int j = 0; j < OC; j += 4) {
           const float4 a = make_float4(__uint_as_float(o0[j]) * inv, __uint_as_float(o0[j + 1]) * inv,
                                        __uint_as_float(o0[j + 2]) * inv, __uint_as_float(o0[j + 3]) * inv);
           if (dst) dst[j / 4] = a;
@@ -235,7 +242,7 @@ dict_attention_f16_kernel(const __grid_constant__ CUtensorMap map_qh, const __gr
       {
         uint32_t raw[HC];
 #pragma unroll
-        for (int c = 0; c < HC / 16; ++c) tmem_ld16_nowait(lane_addr + TF_SP + (uint32_t)b * 128 + hf * HC + c * 16, raw + c * 16);
+        for (int c = 0; c < HC / 16; ++c) tmem_ld16_nowait(lane_addr + TF_SP + (uint32_t)b * 128 + sub * HC + c * 16, raw + c * 16);
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < HC; ++j) s[j] = __uint_as_float(raw[j]) * sc;
@@ -246,9 +253,11 @@ dict_attention_f16_kernel(const __grid_constant__ CUtensorMap map_qh, const __gr
 #pragma unroll
       for (int j = 8; j < HC; ++j) m8[j & 7] = fmaxf(m8[j & 7], s[j]);
       float mx = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])), fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7])));
-      xm[b][hf][r] = mx;
-      pair_sync();          // both threads hold their S columns in registers now: P may overwrite S; orders xl(g-1) too
-      mx = fmaxf(mx, xm[b][hf ^ 1][r]) - 10.0f;           // P' = 1024 * P
+      xm[b][sub][r] = mx;
+      row_sync();           // every thread of the row holds its S columns in registers now: P may overwrite S; orders xl(g-1) too
+#pragma unroll
+      for (int q = 0; q < AF_SUB; ++q) mx = fmaxf(mx, xm[b][q][r]);
+      mx -= 10.0f;                                         // P' = 1024 * P
       float l8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int j = 0; j < HC; ++j) {
@@ -258,22 +267,21 @@ dict_attention_f16_kernel(const __grid_constant__ CUtensorMap map_qh, const __gr
         l8[j & 7] += e;
       }
       if (g > 0) write_out(g - 1);
-      xl[b][hf][r] = ((l8[0] + l8[1]) + (l8[2] + l8[3])) + ((l8[4] + l8[5]) + (l8[6] + l8[7]));
+      xl[b][sub][r] = ((l8[0] + l8[1]) + (l8[2] + l8[3])) + ((l8[4] + l8[5]) + (l8[6] + l8[7]));
       // packed fp16 pairs: word w = (P'[2w], P'[2w+1]); P_hi at columns [0, 64), P_lo at [64, 128) of the S/P buffer
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
+      {
         uint32_t hi[16], lo[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) f16_split2(s[c * 32 + 2 * j], s[c * 32 + 2 * j + 1], hi[j], lo[j]);
-        tmem_st16(lane_addr + TF_SP + (uint32_t)b * 128 + hf * 32 + c * 16, hi);
-        tmem_st16(lane_addr + TF_SP + (uint32_t)b * 128 + 64 + hf * 32 + c * 16, lo);
+        for (int j = 0; j < 16; ++j) f16_split2(s[2 * j], s[2 * j + 1], hi[j], lo[j]);
+        tmem_st16(lane_addr + TF_SP + (uint32_t)b * 128 + sub * 16, hi);
+        tmem_st16(lane_addr + TF_SP + (uint32_t)b * 128 + 64 + sub * 16, lo);
       }
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive(smem_u32(&p_ready[b]));
     }
     if (total > 0) {
-      pair_sync();
+      row_sync();
       write_out(total - 1);
     }
   }
