@@ -7,7 +7,7 @@ from dcae_b200 import _lib
 from dcae_b200.entropy_model import EntropySliceLoop
 from dcae_b200.params import init_entropy_params
 math = sys.argv[1] if len(sys.argv) > 1 else "f16x3"
-B, h, w = 16, 32, 48
+B, h, w = int(os.environ.get("LT_B", 16)), 32, 48
 eng = EntropySliceLoop(init_entropy_params(0, "lively"), math=math, lanes=1)
 g = torch.Generator().manual_seed(1)
 x = [4 * torch.randn(B, 320, h, w, generator=g).cuda(), torch.randn(B, 320, h, w, generator=g).cuda(), torch.randn(B, 320, h, w, generator=g).cuda()]
