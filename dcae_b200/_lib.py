@@ -125,7 +125,9 @@ SIGNATURES = {
     "dcae_op_tokens_to_nchw_i32": (C.c_int, [_P, _I64, _I32, _I32, _I64, _P, _P]),
     "dcae_op_nchw_to_tokens_i32": (C.c_int, [_P, _I32, _I32, _I64, _P, _I64, _P]),
     "dcae_slice_loop_workspace_bytes": (C.c_size_t, [_I32, _I32, _I32]),
-    "dcae_slice_loop_create": (C.c_int, [C.POINTER(_P), _I32, _I32, _I32, C.POINTER(SliceWeights), _P, _P, C.c_size_t, C.c_int]),
+    "dcae_slice_loop_create": (C.c_int, [C.POINTER(_P), _I32, _I32, _I32, C.POINTER(SliceWeights), _P, _I32, _P, C.c_size_t, C.c_int]),
+    "dcae_slice_loop_check_f16_range": (C.c_int, [_P, _I32, C.POINTER(C.c_ulonglong)]),
+    "dcae_count_f16_clamped": (C.c_int, [C.POINTER(Planes), _I64, _I32, _P, _P]),
     "dcae_slice_loop_destroy": (None, [_P]),
     "dcae_slice_loop_load": (C.c_int, [_P, _P, _P, _P, _P]),
     "dcae_slice_loop_params": (C.c_int, [_P, _I32, _P]),

@@ -210,6 +210,9 @@ struct dcae_slice_loop {
   // 192 tiles on 148 SMs (a 30%-full second wave); side by side the second kernel's CTAs take the SMs the first frees
   cudaStream_t side;
   cudaEvent_t ev_fork, ev_join;
+  int n_table;                       // entries of scale_table (2..256)
+  bool check_range;                  // DCAE_MATH_F16X3: count operand-plane elements that hit the fp16 clamp (see dcae_slice_loop_check_f16_range)
+  unsigned long long* sat_count;     // device counter, part of the workspace
 };
 
 static void free_slice_loop(dcae_slice_loop* p) {
@@ -258,6 +261,8 @@ static size_t carve(dcae_slice_loop* p, char* base) {
   takep(p->supp, SUP_LD); takep(p->lnp, D); takep(p->gap, D); takep(p->t2p, D); takep(p->dcp, 4 * D); takep(p->aop, D);
   takep(p->gp, 2 * D); takep(p->x3p, D); takep(p->h1p, 704); takep(p->h2p, 256); takep(p->l1p, 256); takep(p->l2p, 128);
   p->planes_total = off - off0;
+  p->sat_count = base ? reinterpret_cast<unsigned long long*>(base + off) : nullptr;
+  off = align_up(off + sizeof(unsigned long long), 256);
   return off;
 }
 
@@ -270,11 +275,12 @@ extern "C" size_t dcae_slice_loop_workspace_bytes(int32_t B, int32_t h, int32_t 
 }
 
 extern "C" int dcae_slice_loop_create(dcae_slice_loop** out, int32_t B, int32_t h, int32_t w,
-                                      const dcae_slice_weights* weights, const float* scale_table, void* workspace,
+                                      const dcae_slice_weights* weights, const float* scale_table, int32_t n_table, void* workspace,
                                       size_t workspace_bytes, int math) {
   DCAE_REQUIRE(out && weights && workspace, "dcae_slice_loop_create: null argument");
   DCAE_REQUIRE(B > 0 && h > 0 && w > 0 && (int64_t)B * h * w < (1ll << 31) / 4, "dcae_slice_loop_create: bad shape B=%d h=%d w=%d", B, h, w);
   DCAE_REQUIRE(math >= DCAE_MATH_FP32_SIMT && math <= DCAE_MATH_F16X3, "dcae_slice_loop_create: bad math mode %d", math);
+  DCAE_REQUIRE(scale_table == nullptr || (n_table >= 2 && n_table <= 256), "dcae_slice_loop_create: scale table of %d entries (2..256 supported: indexes travel as uint8)", n_table);
   DCAE_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, "dcae_slice_loop_create: workspace must be 256-byte aligned");
   DCAE_TRY(dcae_device_check());
   dcae_slice_loop* p = new (std::nothrow) dcae_slice_loop;
@@ -293,11 +299,13 @@ extern "C" int dcae_slice_loop_create(dcae_slice_loop** out, int32_t B, int32_t 
   carve(p, static_cast<char*>(workspace));
   memcpy(p->wt, weights, sizeof(dcae_slice_weights) * NS);
   p->scale_table = scale_table;
+  p->n_table = scale_table ? n_table : 0;
   p->n_part = dcae_gc_num_partials(p->T, SL);
   if (p->pm) {
     // padded K windows over-read a few never-written plane columns (their weight planes are zero): make them finite
     // (the memset runs on the legacy stream; the plan may be used on any non-blocking stream right after create)
     cudaError_t e = cudaMemset(p->planes_begin, 0, p->planes_total);
+    if (e == cudaSuccess) e = cudaMemset(p->sat_count, 0, sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming);
@@ -354,8 +362,15 @@ static dcae_epilogue epi2(const dcae_slice_loop* p, const float* bias, float* ou
   if (p->pm) { e.out = nullptr; e.out16 = pl(f16, col16); }
   return e;
 }
+// range check (validation mode): count clamped elements of a freshly written planes window
+static int chk(const dcae_slice_loop* p, const dcae_planes& pl16, int cols, void* s) {
+  if (!p->check_range || !pl16.hi) return DCAE_OK;
+  return dcae_count_f16_clamped(&pl16, p->T, cols, p->sat_count, s);
+}
 static int gemm(const dcae_slice_loop* p, const dcae_operand& a, const dcae_weight& w, const dcae_epilogue& e, void* s) {
-  return dcae_op_gemm(&a, &w, &e, p->math, s);
+  DCAE_TRY(dcae_op_gemm(&a, &w, &e, p->math, s));
+  DCAE_TRY(chk(p, e.out16, w.N, s));
+  return chk(p, e.out16_act, w.N, s);
 }
 
 extern "C" int dcae_slice_loop_load(dcae_slice_loop* p, const float* y, const float* latent_scales,
@@ -367,6 +382,8 @@ extern "C" int dcae_slice_loop_load(dcae_slice_loop* p, const float* y, const fl
     const dcae_planes ls = pl(p->supp, SUP_LS), lm = pl(p->supp, SUP_LM);
     DCAE_TRY(dcae_op_nchw_to_tokens(latent_scales, p->B, M, p->HW, nullptr, 0, &ls, stream));
     DCAE_TRY(dcae_op_nchw_to_tokens(latent_means, p->B, M, p->HW, nullptr, 0, &lm, stream));
+    DCAE_TRY(chk(p, ls, M, stream));
+    DCAE_TRY(chk(p, lm, M, stream));
   } else {
     DCAE_TRY(dcae_op_nchw_to_tokens(latent_scales, p->B, M, p->HW, p->sup.p + SUP_LS, SUP_LD, nullptr, stream));
     DCAE_TRY(dcae_op_nchw_to_tokens(latent_means, p->B, M, p->HW, p->sup.p + SUP_LM, SUP_LD, nullptr, stream));
@@ -387,6 +404,7 @@ static int run_dca(dcae_slice_loop* p, int i, void* s, bool dict_f32 = false) { 
   DCAE_TRY(gemm(p, opnd2(p, p->sup, SUP_LD, p->supp, SUP_LS, cq, 1), W.x_trans, epi(W.x_trans_b, p->x0.p, D), s));
   // msa(ln_scale(x))                                                         dcae.py:484, 435-448
   DCAE_TRY(dcae_op_layernorm(p->x0.p, D, W.ln_scale_g, W.ln_scale_b, D, T, ln32, D, &lnp, s));
+  DCAE_TRY(chk(p, lnp, D, s));
   {
     dcae_epilogue e = epi(W.msa_s_b, p->dc.p, 4 * D);
     if (pm) {   // planes for proj + planes of GELU(.) = the prologue of dense layer 0; no fp32 copy at all
@@ -400,6 +418,7 @@ static int run_dca(dcae_slice_loop* p, int i, void* s, bool dict_f32 = false) { 
     DCAE_TRY(gemm(p, opnd2(p, p->ga, D, p->gap, 0, D, 1), W.dense_in[j], epi(W.dense_in_b[j], p->t1.p, D, DCAE_ACT_GELU), s));
     DCAE_TRY(dcae_op_dwconv3x3(p->t1.p, D, W.dense_dw[j], W.dense_dw_b[j], D, p->B, p->h, p->w, DCAE_ACT_GELU, nullptr, 0,
                                pm ? nullptr : p->t2.p, D, &t2p, s));
+    DCAE_TRY(chk(p, t2p, D, s));
     dcae_epilogue e = epi(W.dense_out_b[j], p->dc.p + D * (j + 1), 4 * D);
     if (pm) {
       e.out = nullptr;
@@ -413,6 +432,7 @@ static int run_dca(dcae_slice_loop* p, int i, void* s, bool dict_f32 = false) { 
   DCAE_TRY(dcae_op_spatial_gate(p->so.p, D, p->x0.p, D, W.res_scale_1, W.spatial_w7, D, p->B, p->h, p->w, p->stats.p, p->x1.p, D, s));
   // q = q_trans(lnx(x)); attention against the dictionary                    dcae.py:486-501
   DCAE_TRY(dcae_op_layernorm(p->x1.p, D, W.lnx_g, W.lnx_b, D, T, ln32, D, &lnp, s));
+  DCAE_TRY(chk(p, lnp, D, s));
   {
     dcae_epilogue e = epi(W.q_trans_b, p->q.p, D);
     if (pm) { e.out = nullptr; e.out16 = pl(p->gap); }     // planes mode: q as fp16 planes in the (idle) GELU buffer
@@ -422,6 +442,7 @@ static int run_dca(dcae_slice_loop* p, int i, void* s, bool dict_f32 = false) { 
     const dcae_planes aop = pm ? pl(p->aop) : none;
     const dcae_planes qp = pm ? pl(p->gap) : none;
     DCAE_TRY(dcae_op_dict_attention(pm ? nullptr : p->q.p, D, &qp, &W.kv, T, pm ? nullptr : p->ao.p, D, &aop, p->math, s));
+    DCAE_TRY(chk(p, aop, D, s));
   }
   // output = linear(output) + res_scale_2(shortcut)                          dcae.py:503
   {
@@ -431,11 +452,13 @@ static int run_dca(dcae_slice_loop* p, int i, void* s, bool dict_f32 = false) { 
   }
   // output = mlp(ln_mlp(output)) + res_scale_3(output)                       dcae.py:505, 312-328
   DCAE_TRY(dcae_op_layernorm(p->x2.p, D, W.ln_mlp_g, W.ln_mlp_b, D, T, ln32, D, &lnp, s));
+  DCAE_TRY(chk(p, lnp, D, s));
   DCAE_TRY(gemm(p, opnd2(p, p->ln, D, p->lnp, 0, D, 1), W.fc1, epi(W.fc1_b, p->f.p, 4 * D), s));
   {
     const dcae_planes gp = pm ? pl(p->gp) : none;
     DCAE_TRY(dcae_op_dwconv3x3(p->f.p, 4 * D, W.mlp_dw, W.mlp_dw_b, 2 * D, p->B, p->h, p->w, DCAE_ACT_GELU, p->f.p + 2 * D, 4 * D,
                                pm ? nullptr : p->g.p, 2 * D, &gp, s));
+    DCAE_TRY(chk(p, gp, 2 * D, s));
   }
   {
     dcae_epilogue e = epi2(p, W.fc2_b, p->x3.p, D, p->x3p, 0);
@@ -495,6 +518,7 @@ static int load_window(dcae_slice_loop* p, const float* x, int64_t x_channels, i
       w.hi = static_cast<__half*>(w.hi) + row0 * w.ld;
       w.lo = static_cast<__half*>(w.lo) + row0 * w.ld;
       DCAE_TRY(dcae_op_nchw_to_tokens(src, 1, C, p->HW, p->sup.p + row0 * SUP_LD + sup_col, SUP_LD, &w, s));
+      if (p->check_range) DCAE_TRY(dcae_count_f16_clamped(&w, p->HW, C, p->sat_count, s));
     } else {
       DCAE_TRY(dcae_op_nchw_to_tokens(src, 1, C, p->HW, p->sup.p + row0 * SUP_LD + sup_col, SUP_LD, nullptr, s));
     }
@@ -568,7 +592,7 @@ static dcae_gc_args gc_base(dcae_slice_loop* p, int i) {
   memset(&a, 0, sizeof(a));
   a.mu = p->means.p + SL * i; a.mu_ld = M;
   a.scale = p->scales.p + SL * i; a.scale_ld = M;
-  a.scale_table = p->scale_table; a.n_table = 64;
+  a.scale_table = p->scale_table; a.n_table = p->n_table;
   a.scale_bound = 0.11f; a.lik_bound = 1e-9f;
   a.rows = p->T; a.inner = SL;
   return a;
@@ -591,6 +615,7 @@ extern "C" int dcae_slice_loop_encode(dcae_slice_loop* p, int32_t i, int32_t gc_
   if (p->scale_table) { a.idx = p->idx + SL * i; a.idx_ld = M; }
   a.log2_partials = p->part.p + (int64_t)i * p->n_part;
   DCAE_TRY(dcae_gc_fused(&a, s));
+  DCAE_TRY(chk(p, a.y_hat16, SL, s));
   return run_lrp(p, i, s);
 }
 
@@ -614,7 +639,19 @@ extern "C" int dcae_slice_loop_decode(dcae_slice_loop* p, int32_t i, const int32
   a.y_hat = p->sup.p + SUP_PRE; a.y_hat_ld = SUP_LD;
   if (p->pm) a.y_hat16 = pl(p->supp, SUP_PRE);
   DCAE_TRY(dcae_gc_fused(&a, s));
+  DCAE_TRY(chk(p, a.y_hat16, SL, s));
   return run_lrp(p, i, s);
+}
+
+extern "C" int dcae_slice_loop_check_f16_range(dcae_slice_loop* p, int32_t enable, unsigned long long* clamped_host) {
+  DCAE_REQUIRE(p, "dcae_slice_loop_check_f16_range: null plan");
+  if (clamped_host) {                                  // read (synchronises the device) and reset
+    DCAE_CUDA(cudaDeviceSynchronize());
+    DCAE_CUDA(cudaMemcpy(clamped_host, p->sat_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  }
+  DCAE_CUDA(cudaMemset(p->sat_count, 0, sizeof(unsigned long long)));
+  p->check_range = enable != 0 && p->pm;
+  return DCAE_OK;
 }
 
 extern "C" int dcae_slice_loop_store(dcae_slice_loop* p, float* y_hat, float* means, float* scales, float* lik,

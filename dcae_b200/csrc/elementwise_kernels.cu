@@ -456,6 +456,30 @@ extern "C" int dcae_pack_symbols(const int32_t* symbols, const int32_t* indexes,
   return DCAE_OK;
 }
 
+// ---- fp16 operand-plane range check (DCAE_MATH_F16X3) -----------------------------------------------------
+// Activations are converted to hi/lo planes with cvt.rn.satfinite: a magnitude above 65504 is silently clamped.
+// This kernel counts the elements of a planes window whose hi half sits at the clamp (|hi| == 0x7bff) or is not
+// finite; the slice loop runs it behind every producer when range checking is on (validation of a new checkpoint).
+__global__ void count_f16_clamped_kernel(const __half* __restrict__ hi, int64_t ld, int64_t rows, int32_t cols, unsigned long long* counter) {
+  unsigned long long n = 0;
+  const int64_t total = rows * cols;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cols;
+    const unsigned short b = __half_as_ushort(hi[r * ld + (i - r * cols)]) & 0x7fffu;
+    n += b >= 0x7bffu;
+  }
+  n = __reduce_add_sync(0xffffffffu, (unsigned)n);
+  if ((threadIdx.x & 31) == 0 && n) atomicAdd(counter, n);
+}
+
+extern "C" int dcae_count_f16_clamped(const dcae_planes* planes, int64_t T, int32_t cols, unsigned long long* counter, void* stream) {
+  DCAE_REQUIRE(planes && planes->hi && counter && T >= 0 && cols >= 0, "dcae_count_f16_clamped: bad arguments");
+  if (T == 0 || cols == 0) return DCAE_OK;
+  count_f16_clamped_kernel<<<grid_for(T * cols, 256), 256, 0, (cudaStream_t)stream>>>(static_cast<const __half*>(planes->hi), planes->ld, T, cols, counter);
+  DCAE_LAUNCH_CHECK();
+  return DCAE_OK;
+}
+
 extern "C" int dcae_split_tf32(const float* w, float* w_hi, float* w_lo, int64_t n, void* stream) {
   DCAE_REQUIRE(w && w_hi && w_lo && n >= 0, "dcae_split_tf32: bad arguments");
   if (n == 0) return DCAE_OK;

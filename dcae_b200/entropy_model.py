@@ -36,7 +36,8 @@ class _Plan:
         base = (self.workspace.data_ptr() + 255) // 256 * 256
         self.handle = C.c_void_p()
         table = eng.scale_table.data_ptr() if eng.scale_table is not None else None
-        _lib.check(lib.dcae_slice_loop_create(C.byref(self.handle), B, h, w, eng.weights.array, table, base,
+        n_table = int(eng.scale_table.numel()) if eng.scale_table is not None else 0
+        _lib.check(lib.dcae_slice_loop_create(C.byref(self.handle), B, h, w, eng.weights.array, table, n_table, base,
                                               nbytes, _lib.MATH[eng.math]), "dcae_slice_loop_create")
         self.lib = lib
 
@@ -69,14 +70,26 @@ class EntropySliceLoop:
         with torch.cuda.device(self.device):
             _lib.check(self.lib.dcae_device_check(), "dcae_device_check")
         self.weights = PackedWeights(params, self.device, split_tf32=True)
+        self.dictionary = params["dt"].detach().to(self.device, torch.float32).clone()     # what K / V were packed from
         if scale_table is None:
             scale_table = get_scale_table()
-        self.scale_table = scale_table.to(self.device, torch.float32).contiguous()
+        self.scale_table = scale_table.detach().to(self.device, torch.float32).contiguous().reshape(-1)
+        if not 2 <= self.scale_table.numel() <= 256:
+            raise ValueError(f"scale_table must have 2..256 entries (got {self.scale_table.numel()}): indexes travel as uint8")
         self._plans: Dict[tuple, _Plan] = {}
         self.last_launches = 0
         self.lanes = max(1, int(lanes))
         with torch.cuda.device(self.device):
             self._lane_streams = [torch.cuda.Stream(self.device) for _ in range(self.lanes)] if self.lanes > 1 else []
+
+    def refresh(self, params: Dict[str, torch.Tensor]) -> None:
+        """Repack the device weights from a new state dict (after `load_state_dict` or an optimizer step).  Plans are
+        rebuilt on the next call; the previous packed tensors are released once no launch uses them any more."""
+        torch.cuda.synchronize(self.device)
+        self._plans.clear()
+        self.weights = PackedWeights(params, self.device, split_tf32=True)
+        self.dictionary = params["dt"].detach().to(self.device, torch.float32).clone()
+        self._dt_checked = False
 
     # ---- plumbing -------------------------------------------------------------------------------
     def _plan(self, B, h, w, lane: int = -1) -> _Plan:
@@ -177,6 +190,29 @@ class EntropySliceLoop:
                            "dcae_reduce_partials")
         self.last_launches = int(lib.dcae_launch_count())
         return out
+
+    def check_f16_range(self, y, latent_scales, latent_means) -> int:
+        """Validation of a checkpoint for the default `f16x3` mode: activations travel as fp16 hi/lo planes written with
+        a saturating convert, so a magnitude above 65504 would be clamped without any signal.  Runs one forward with
+        the library's range check on (one small counting launch behind every producer of operand planes) and returns
+        the number of clamped elements; 0 means the 22-bit operand claim held for these inputs.  Raises if not 0 and
+        `math` is f16x3 -- use `math="tf32x3"` (fp32 operands in HBM, no range limit) for such a checkpoint."""
+        if self.math != "f16x3":
+            return 0
+        y = self._check_in("y", y)
+        B, _, h, w = y.shape
+        plan = self._plan(B, h, w, lane=-2)            # its own plan: the production plans never pay for the check
+        n = C.c_ulonglong(0)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.dcae_slice_loop_check_f16_range(plan.handle, 1, None), "check_f16_range")
+            out = {k: torch.empty_like(y) for k in ("y_hat", "means", "scales", "likelihoods")}
+            self._run_forward(plan, self._stream(), y, self._check_in("latent_scales", latent_scales),
+                              self._check_in("latent_means", latent_means), None, out, None, None, torch.empty(1, device=self.device))
+            _lib.check(self.lib.dcae_slice_loop_check_f16_range(plan.handle, 0, C.byref(n)), "check_f16_range")
+        if n.value:
+            raise _lib.DcaeError(f"f16x3: {n.value} activation elements exceed the fp16 range (|x| > 65504) and were clamped; "
+                                 "run this checkpoint with math='tf32x3'")
+        return int(n.value)
 
     def capture(self, y, latent_scales, latent_means, want_symbols: bool = False):
         """CUDA-graph form of `forward` for launch-bound shapes (a 256x256 image is 173 launches of a few microseconds:

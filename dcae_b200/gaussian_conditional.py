@@ -18,19 +18,55 @@ import torch.nn as nn
 from . import _lib
 
 
+class _Bound(nn.Module):
+    """Key-compatible stand-in for compressai's `LowerBound` sub-module (one buffer, `bound`); the clamp itself
+    happens inside kernel 3."""
+
+    def __init__(self, bound: float):
+        super().__init__()
+        self.register_buffer("bound", torch.Tensor([float(bound)]))
+
+
 class GaussianConditional(nn.Module):
     def __init__(self, scale_table=None, scale_bound: float = 0.11, tail_mass: float = 1e-9,
                  likelihood_bound: float = 1e-9, entropy_coder_precision: int = 16):
         super().__init__()
-        self.scale_bound = float(scale_bound)
         self.tail_mass = float(tail_mass)
-        self.likelihood_bound = float(likelihood_bound)
         self.entropy_coder_precision = int(entropy_coder_precision)
+        # compressai's published module also owns `scale_bound`, `lower_bound_scale.bound` and
+        # `likelihood_lower_bound.bound` (its source is not in /root/reference; the reference itself only touches the four
+        # table buffers, dcae.py:680-685): registered so that a checkpoint saved from the real class loads key for key
+        self.likelihood_lower_bound = _Bound(likelihood_bound)
+        self.lower_bound_scale = _Bound(scale_bound)
         self.register_buffer("_offset", torch.IntTensor())
         self.register_buffer("_quantized_cdf", torch.IntTensor())
         self.register_buffer("_cdf_length", torch.IntTensor())
         self.register_buffer("scale_table", torch.Tensor(tuple(float(s) for s in scale_table))
                              if scale_table is not None else torch.Tensor())
+        self.register_buffer("scale_bound", torch.Tensor([float(scale_bound)]))
+        self._bounds = (float(scale_bound), float(likelihood_bound))     # host copies: kernel arguments, no device read per call
+
+    @property
+    def likelihood_bound(self) -> float:
+        return self._bounds[1]
+
+    _TABLE_BUFFERS = ("_quantized_cdf", "_offset", "_cdf_length", "scale_table")
+
+    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
+        """The coder tables change size with the checkpoint (`update()` / baked tables): resize the four buffers to
+        the incoming shapes first, which is what the reference does with `update_registered_buffers` before it loads
+        (dcae.py:679-687).  Keys of compressai's own state dict that this class does not hold are the caller's
+        business (`strict=False`)."""
+        for name in self._TABLE_BUFFERS:
+            src = state_dict.get(prefix + name)
+            if src is not None:
+                cur = getattr(self, name)
+                if tuple(cur.shape) != tuple(src.shape):
+                    setattr(self, name, torch.empty(src.shape, dtype=cur.dtype, device=cur.device))
+        super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
+        sb, lb = state_dict.get(prefix + "scale_bound"), state_dict.get(prefix + "likelihood_lower_bound.bound")
+        self._bounds = (float(sb) if sb is not None and sb.numel() == 1 else self._bounds[0],
+                        float(lb) if lb is not None and lb.numel() == 1 else self._bounds[1])
 
     offset = property(lambda self: self._offset)
     quantized_cdf = property(lambda self: self._quantized_cdf)
@@ -110,7 +146,7 @@ class GaussianConditional(nn.Module):
             table = table.to(ref.device, torch.float32).contiguous()
             keep.append(table)
             a.scale_table, a.n_table = table.data_ptr(), table.numel()
-        a.scale_bound, a.lik_bound, a.mode = self.scale_bound, self.likelihood_bound, mode
+        a.scale_bound, a.lik_bound, a.mode = self._bounds[0], self._bounds[1], mode
         a.rows, a.inner = n_rows, inner
         outs = {}
         for name, dt in (("y_hat", torch.float32), ("lik", torch.float32), ("sym", torch.int32), ("idx", torch.int32)):
@@ -181,27 +217,7 @@ class GaussianConditional(nn.Module):
 
 
 def _pmf_to_quantized_cdf(pmf, precision: int = 16):
-    """compressai `_CXX.pmf_to_quantized_cdf` (published algorithm): scale to 2^precision, force every
-    symbol to a non-zero frequency by stealing from the cheapest donor."""
-    cdf = [0] * (len(pmf) + 1)
-    for i, p in enumerate(pmf):
-        cdf[i + 1] = int(round(float(p) * (1 << precision)))      # std::round(p * 2^precision)
-    total = sum(cdf)
-    cdf = [((1 << precision) * c) // total for c in cdf]          # integer renormalisation (floor)
-    for i in range(1, len(cdf)):
-        cdf[i] += cdf[i - 1]                                       # std::partial_sum
-    cdf[-1] = 1 << precision
-    for i in range(len(cdf) - 1):
-        if cdf[i] == cdf[i + 1]:
-            best_freq, best_steal = 1 << 32, -1
-            for j in range(len(cdf) - 1):
-                freq = cdf[j + 1] - cdf[j]
-                if 1 < freq < best_freq:
-                    best_freq, best_steal = freq, j
-            if best_steal < i:
-                for j in range(best_steal + 1, i + 1):
-                    cdf[j] -= 1
-            else:
-                for j in range(i + 1, best_steal + 1):
-                    cdf[j] += 1
-    return cdf
+    """compressai `_CXX.pmf_to_quantized_cdf`: native, in libdcae_rans.so next to the coder that consumes the tables
+    (dcae_pmf_to_quantized_cdf, include/dcae_rans.h)."""
+    from .ans import pmf_to_quantized_cdf
+    return pmf_to_quantized_cdf(pmf, precision)

@@ -131,7 +131,7 @@ class PackedWeights:
                          self._conv3x3_to_gemm(scale("0.weight"), perm),
                          self._conv3x3_to_gemm(lrp0[:, :c_sup], perm)], dim=0)
         W.cc1 = self._weight(cc1, taps=9)
-        W.cc1_b = self._vec(torch.cat([mean("0.bias"), scale("0.bias"), torch.zeros(CC_HID1)]))
+        W.cc1_b = self._vec(torch.cat([mean("0.bias"), scale("0.bias"), mean("0.bias").new_zeros(CC_HID1)]))
         W.lrp1y = self._weight(self._conv3x3_to_gemm(lrp0[:, c_sup:]), taps=9)
         W.lrp1_b = self._vec(lrp("0.bias"))
         W.mean2, W.mean2_b = self._weight(self._conv3x3_to_gemm(mean("2.weight")), taps=9), self._vec(mean("2.bias"))

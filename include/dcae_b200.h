@@ -265,9 +265,10 @@ typedef struct {
 typedef struct dcae_slice_loop dcae_slice_loop;
 
 size_t dcae_slice_loop_workspace_bytes(int32_t B, int32_t h, int32_t w);
-/* weights: array of 5; scale_table: device [64]; workspace: device, 256-byte aligned. */
+/* weights: array of 5; scale_table: device [n_table] (the module's buffer, dcae.py:616-621; 2..256 entries, NULL if
+ * update() has not run: indexes are then unavailable); workspace: device, 256-byte aligned. */
 int dcae_slice_loop_create(dcae_slice_loop** out, int32_t B, int32_t h, int32_t w,
-                           const dcae_slice_weights* weights, const float* scale_table,
+                           const dcae_slice_weights* weights, const float* scale_table, int32_t n_table,
                            void* workspace, size_t workspace_bytes, int math);
 void dcae_slice_loop_destroy(dcae_slice_loop* p);
 
@@ -288,6 +289,15 @@ int dcae_slice_loop_decode(dcae_slice_loop* p, int32_t i, const int32_t* symbols
  * coder order, dcae.py:742-743).  log2_lik_sum: 1 float = sum log2(lik) (deterministic). */
 int dcae_slice_loop_store(dcae_slice_loop* p, float* y_hat, float* means, float* scales, float* lik,
                           int32_t* symbols, int32_t* indexes, float* log2_lik_sum, void* stream);
+/* DCAE_MATH_F16X3 range validation.  Activations travel as fp16 hi/lo planes written with a saturating convert, so a
+ * magnitude above 65504 would be clamped silently.  With `enable` != 0 every later call on this plan counts, behind
+ * each producer, the plane elements that sit at the clamp; the call itself returns the count accumulated so far in
+ * *clamped_host (nullable; reading synchronises the device) and resets it.  Meant for validating a checkpoint once
+ * (dcae_b200.EntropySliceLoop.check_f16_range), not for the hot path: it adds one small launch per producer. */
+int dcae_slice_loop_check_f16_range(dcae_slice_loop* p, int32_t enable, unsigned long long* clamped_host);
+/* elements of the [T, cols] window of `planes` whose hi half is at the fp16 clamp or not finite, added to *counter (device). */
+int dcae_count_f16_clamped(const dcae_planes* planes, int64_t T, int32_t cols, unsigned long long* counter, void* stream);
+
 /* Module-level calls, for callers that keep the reference's loop text and swap single modules: one
  * module of slice i on the caller's NCHW fp32 tensors, through the plan's buffers -- do not interleave with a slice
  * loop in flight on the same plan.

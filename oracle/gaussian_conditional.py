@@ -129,7 +129,7 @@ def pmf_to_quantized_cdf(pmf, precision: int = 16):
     """Restatement of compressai's C++ `pmf_to_quantized_cdf` (rans interface)."""
     cdf = [0] * (len(pmf) + 1)
     for i, p in enumerate(pmf):
-        cdf[i + 1] = int(round(float(p) * (1 << precision)))      # std::round(p * 2^precision)
+        cdf[i + 1] = int(math.floor(float(p) * (1 << precision) + 0.5))   # std::round (half away from zero; p >= 0), not Python's half-to-even
     total = sum(cdf)
     cdf = [((1 << precision) * c) // total for c in cdf]          # integer renormalisation (floor)
     for i in range(1, len(cdf)):

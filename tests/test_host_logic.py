@@ -49,7 +49,39 @@ def test_cdf_tables_match_oracle_restatement():
         row = q[i, : int(ln[i])]
         assert int(row[0]) == 0 and int(row[-1]) == 65536 and bool((row.diff() > 0).all())
     sd = gc.state_dict()
-    assert set(sd) == {"_offset", "_quantized_cdf", "_cdf_length", "scale_table"}      # dcae.py:680-685
+    # the four the reference resizes before loading (dcae.py:680-685) + the three scalar buffers of compressai's class
+    assert set(sd) == {"_offset", "_quantized_cdf", "_cdf_length", "scale_table", "scale_bound",
+                       "lower_bound_scale.bound", "likelihood_lower_bound.bound"}
+
+
+def test_state_dict_round_trip_resizes_the_table_buffers():
+    """`strict=False` does not excuse size mismatches; a fresh module (buffers of shape [0]) must load an
+    updated module's tables, a baked checkpoint in the reference layout (export_checkpoint.py:34-42), and shrink again."""
+    src = GaussianConditional(None)
+    src.update_scale_table(ogc.get_scale_table())
+    dst = GaussianConditional(None)
+    assert dst._offset.numel() == 0
+    dst.load_state_dict(src.state_dict(), strict=False)
+    for k in ("_offset", "_quantized_cdf", "_cdf_length", "scale_table"):
+        assert torch.equal(getattr(dst, k), getattr(src, k)), k
+    assert dst.update_scale_table(ogc.get_scale_table()) is False            # already initialised by the load
+    # reference checkpoint layout: keys prefixed inside a parent module, only the four table buffers present
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.gaussian_conditional = GaussianConditional(None)
+    ckpt = {"gaussian_conditional." + k: v.clone() for k, v in src.state_dict().items()
+            if k in ("_offset", "_quantized_cdf", "_cdf_length", "scale_table")}
+    net = Net()
+    missing, unexpected = net.load_state_dict(ckpt, strict=False)
+    assert not unexpected and all("bound" in m for m in missing)
+    assert torch.equal(net.gaussian_conditional.quantized_cdf, src.quantized_cdf)
+    # a different table size (custom levels) replaces the buffers again, and the scalar bounds travel
+    small = GaussianConditional(None, scale_bound=0.2)
+    small.update_scale_table(ogc.get_scale_table(0.2, 64, 16))
+    net.gaussian_conditional.load_state_dict(small.state_dict())
+    assert tuple(net.gaussian_conditional._offset.shape) == (16,)
+    assert abs(net.gaussian_conditional._bounds[0] - 0.2) < 1e-7
 
 
 def test_pmf_to_quantized_cdf_steals_for_zero_bins():
