@@ -28,15 +28,35 @@ sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402
 
-H_IMG, W_IMG = 512, 768          # Kodak
 FLOP_PER_TOKEN = 163.76e6        # whole slice loop, 2*MAC
 GC_BYTES_PER_ELEM = 28           # y, mu, scale in; lik, y_hat, sym, idx out (compress variant)
+
+# BASELINE.json configs that are bench lines (the others are parity-test cases).  #2 is the one the metric is quoted on
+# and the default; #3 and #5 are the "larger images" of the north star.  H x W are padded to multiples of 128 as
+# eval.py:3583-3598 does before the model sees them; tokens = (H_pad / 16) * (W_pad / 16).
+CONFIGS = {
+    1: dict(H=256, W=256, batch=1, mode="forward", tag="256x256",
+            workload="DCAE entropy-model forward (slice loop), one synthetic 256x256 image (BASELINE config #1)"),
+    2: dict(H=512, W=768, batch=16, mode="forward", tag="768x512",
+            workload="DCAE entropy-model forward (slice loop), batch 16 synthetic Kodak-shaped 768x512 images per GPU (BASELINE config #2)"),
+    3: dict(H=1365, W=2048, batch=4, mode="compress", tag="2048x1365",
+            workload="DCAE compress() slice loop (quantize + build_indexes + likelihoods), synthetic CLIC-shaped 2048x1365 images, 4 per GPU per step (BASELINE config #3)"),
+    5: dict(H=2160, W=3840, batch=4, mode="forward", tag="3840x2160",
+            workload="DCAE entropy-model forward (slice loop), synthetic 4K 3840x2160 images, 4 per GPU per step (BASELINE config #5)"),
+}
+
+
+def latent_hw(cfg):
+    pad = lambda v: (v + 127) // 128 * 128
+    return pad(cfg["H"]) // 16, pad(cfg["W"]) // 16
 
 
 def ncu_traffic(kernel_csv):
     """Mean DRAM bytes (read + write) per launch from a committed `ncu --set full` summary (tools/ncu_summary.py), or None."""
     import csv
-    path = os.path.join(ROOT, "profiles", "r01", kernel_csv)
+    path = os.path.join(ROOT, "profiles", "r02", kernel_csv)
+    if not os.path.exists(path):
+        path = os.path.join(ROOT, "profiles", "r01", kernel_csv)
     try:
         rows = list(csv.reader(open(path)))
         hdr, units, data = rows[0], rows[1], rows[2:]
@@ -125,68 +145,111 @@ class ClockSampler:
                 "power_w_max": max((r[1] for r in rows), default=None), "samples": len(rows), "source": "nvml"}
 
 
-def cpu_oracle_rate(n_images, steps, warmup, seed=0):
-    """The reference's CPU implementation of the path (oracle port; /root/reference cannot travel to the
-    GPU box): torch-CPU fp32, all host threads.  Returns (images/s, threads, seconds per step)."""
+class _ReferenceLoop:
+    """The reference's own implementation of the path, for the baseline legs only (never on the product path).
+    kind "reference": the UNMODIFIED classes of /root/reference/models/dcae.py (staged into oracle/_ref/ by build()):
+    `DCAE.forward` / `DCAE.compress` run as written on injected (y, latent_scales, latent_means) -- everything outside
+    the slice loop is replaced by injectors that cost nothing (oracle/reference_loader.py); compressai is absent, so
+    `GaussianConditional` is the oracle restatement and, in compress mode, the rANS encoder is a recorder (the
+    `.tolist()` hand-off of dcae.py:742-743 is part of the reference's path and stays inside the timed region).
+    kind "port": the functional restatement oracle/entropy_model.py, when the reference file is not available."""
+
+    def __init__(self, params, device, mode):
+        from oracle import reference_loader as rl
+        self.mode, self.device = mode, torch.device(device)
+        if rl.reference_available():
+            self.kind = "reference"
+            self.rl = rl
+            self.net = rl.build_reference_net(params).to(self.device)
+        else:
+            from oracle.entropy_model import SliceLoopOracle
+            self.kind = "port"
+            p = {k: v.to(self.device) for k, v in params.items()}
+            self.orc = SliceLoopOracle(p, scale_table=None)
+            self.orc.scale_table = self.orc.scale_table.to(self.device)
+
+    def step(self, y, ls, lm):
+        with torch.no_grad():
+            if self.kind == "port":
+                return self.orc.compress(y, ls, lm) if self.mode == "compress" else self.orc.forward(y, ls, lm)
+            x = self.rl.inject_latents(self.net, y, ls, lm)
+            if self.mode == "forward":
+                return self.net(x)
+            import tempfile
+            cwd = os.getcwd()
+            with tempfile.TemporaryDirectory() as td:           # compress() writes debug dumps to ./output/debug (dcae.py:707, 758)
+                os.makedirs(os.path.join(td, "output", "debug"))
+                os.chdir(td)
+                try:
+                    return self.net.compress(x)
+                finally:
+                    os.chdir(cwd)
+
+
+def cpu_reference_rate(cfg, n_images, steps, warmup, seed=0):
+    """The reference's CPU path on all host threads, `steps` steps of `n_images` images.
+    -> (images/s, threads, seconds per step, kind)."""
     from dcae_b200.params import init_entropy_params
-    from oracle.entropy_model import SliceLoopOracle
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
-    orc = SliceLoopOracle(init_entropy_params(seed, "lively"))
-    y, ls, lm = synth_latents(n_images, H_IMG // 16, W_IMG // 16)
+    h, w = latent_hw(cfg)
+    loop = _ReferenceLoop(init_entropy_params(seed, "lively"), "cpu", cfg["mode"])
+    y, ls, lm = synth_latents(n_images, h, w)
     for _ in range(warmup):
-        orc.forward(y, ls, lm)
+        loop.step(y, ls, lm)
     t0 = time.perf_counter()
     for _ in range(steps):
-        orc.forward(y, ls, lm)
+        loop.step(y, ls, lm)
     dt = (time.perf_counter() - t0) / max(steps, 1)
-    return n_images / dt, threads, dt
+    return n_images / dt, threads, dt, loop.kind
 
 
-def gpu_eager_rate(dev, n_images, steps, warmup, seed=0, tf32=False):
-    """The same oracle port run by eager PyTorch ON THE GPU (fp32, TF32 off as eval.py:3182-3187 sets it): what a user
-    of the reference gets on this B200 without this library.  A baseline leg like cpu_baseline: it only times the
-    checker, nothing of it is on the product path.  Returns (images/s, seconds per step)."""
+def gpu_eager_rate(cfg, dev, n_images, steps, warmup, seed=0, tf32=False):
+    """The same reference classes run by eager PyTorch ON THE GPU with the reference's evaluation flags (TF32 off,
+    cuDNN off: eval.py:3182-3187, 3904): what a user of the reference gets on this B200 without this library.  A
+    baseline leg like cpu_baseline; `tf32=True` is the reduced-precision fair-fight variant (TF32 + cuDNN on).
+    -> (images/s, seconds per step, kind)."""
     from dcae_b200.params import init_entropy_params
-    from oracle.entropy_model import SliceLoopOracle
-    saved = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    saved = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32, torch.backends.cudnn.enabled)
     torch.backends.cuda.matmul.allow_tf32 = tf32
     torch.backends.cudnn.allow_tf32 = tf32
+    torch.backends.cudnn.enabled = tf32
     try:
-        params = {k: v.to(dev) for k, v in init_entropy_params(seed, "lively").items()}
-        orc = SliceLoopOracle(params, scale_table=None)
-        orc.scale_table = orc.scale_table.to(dev)
-        y, ls, lm = (t.to(dev) for t in synth_latents(n_images, H_IMG // 16, W_IMG // 16))
+        h, w = latent_hw(cfg)
+        loop = _ReferenceLoop(init_entropy_params(seed, "lively"), dev, cfg["mode"])
+        y, ls, lm = (t.to(dev) for t in synth_latents(n_images, h, w))
         for _ in range(warmup):
-            orc.forward(y, ls, lm)
+            loop.step(y, ls, lm)
         torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+        t0 = time.perf_counter()                      # wall clock: compress mode has host work (.tolist()) on its path
         for _ in range(steps):
-            orc.forward(y, ls, lm)
-        e1.record()
+            loop.step(y, ls, lm)
         torch.cuda.synchronize()
-        dt = e0.elapsed_time(e1) * 1e-3 / max(steps, 1)
-        return n_images / dt, dt
+        dt = (time.perf_counter() - t0) / max(steps, 1)
+        return n_images / dt, dt, loop.kind
     finally:
-        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = saved
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32, torch.backends.cudnn.enabled = saved
 
 
 def run_reference(args):
-    """--impl reference: the reference CPU path on the box's host cores, bounded sample per step."""
+    """--impl reference: the reference's CPU implementation of the path on the box's host cores; every step is the
+    same batch the GPU arm processes per GPU (same config), same warm-up count."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_img = args.cpu_images
-    rate, threads, dt = cpu_oracle_rate(n_img, args.steps, min(args.warmup, 1))
+    cfg = CONFIGS[args.config]
+    n_img = args.batch or cfg["batch"]
+    warm = max(args.warmup, 3) if args.config == 2 else min(args.warmup, 1)
+    rate, threads, dt, kind = cpu_reference_rate(cfg, n_img, args.steps, warm)
+    what = ("unmodified /root/reference/models/dcae.py classes (DCAE.%s slice loop on injected latents; GaussianConditional = oracle restatement, compressai absent)" % cfg["mode"]
+            if kind == "reference" else "torch-CPU fp32 oracle port of dcae.py:638-670")
     line = {
-        "impl": "reference", "metric": "entropy-model images/sec @768x512", "value": rate, "unit": "images/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3,
+        "impl": "reference", "metric": f"entropy-model images/sec @{cfg['tag']}", "value": rate, "unit": "images/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": warm, "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"DCAE entropy-model slice loop, {n_img} x 768x512 per step on host CPU (bounded sample of config #2)",
-                   "batch_per_step": n_img},
-        "cpu_baseline": {"value": rate, "unit": "images/s", "cores": threads, "kind": "port",
-                         "sample": f"{args.steps} steps x {n_img} images of 768x512, torch-CPU fp32 oracle port of dcae.py:638-670"},
+        "config": {"workload": cfg["workload"], "batch_per_gpu": n_img, "mode": cfg["mode"], "where": "host CPU, torch fp32, all threads"},
+        "cpu_baseline": {"value": rate, "unit": "images/s", "cores": threads, "kind": kind,
+                         "sample": f"{args.steps} steps x {n_img} images of {cfg['tag']}: {what}"},
         "e2e": {"value": rate, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -200,9 +263,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--math", default="f16x3", choices=["f16x3", "tf32x3", "tf32", "fp32"])
-    ap.add_argument("--batch", type=int, default=16, help="images per GPU per step (config #2: 16)")
-    ap.add_argument("--cpu-images", type=int, default=2, help="images per step of the CPU reference arm")
-    ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS), help="BASELINE.json config number (2 = the headline)")
+    ap.add_argument("--mode", default=None, choices=["forward", "compress"], help="override the config's mode")
+    ap.add_argument("--batch", type=int, default=0, help="images per GPU per step (default: the config's)")
+    ap.add_argument("--cpu-steps", type=int, default=2, help="steps of the in-line cpu_baseline leg (same batch as the GPU arm for config #2, one image otherwise)")
+    ap.add_argument("--gpu-baseline-steps", type=int, default=5)
     ap.add_argument("--lanes", type=int, default=2, help="sub-batches run on separate streams by EntropySliceLoop.forward")
     ap.add_argument("--warmup-seconds", type=float, default=1.5, help="keep warming up until the device has been busy this long (0 under ncu)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -210,8 +275,12 @@ def main():
     ap.add_argument("--no-clock-sampler", action="store_true", help="diagnostic: do not poll NVML during the timed region")
     ap.add_argument("--gc-micro-mb", type=int, default=1024, help="footprint of the kernel-3 HBM microbenchmark")
     args = ap.parse_args()
+    if args.mode:
+        CONFIGS[args.config] = dict(CONFIGS[args.config], mode=args.mode)
     if args.impl == "reference":
         return run_reference(args)
+    cfg = CONFIGS[args.config]
+    compress = cfg["mode"] == "compress"
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -228,21 +297,22 @@ def main():
     from dcae_b200.params import init_entropy_params
     from dcae_b200.sharding import max_over_ranks
 
-    B, h, w = args.batch, H_IMG // 16, W_IMG // 16
+    B = args.batch or cfg["batch"]
+    h, w = latent_hw(cfg)
     T = B * h * w
     eng = EntropySliceLoop(init_entropy_params(0, "lively"), device=dev, math=args.math, lanes=args.lanes)
     host_in = synth_latents(B, h, w, seed=1234 + rank, pin=True)
     dev_in = [t.to(dev) for t in host_in]
     lib = _lib.load()
 
-    out_buf = eng.forward(*dev_in)             # outputs are allocated once and overwritten in place (forward(out=...)):
+    out_buf = eng.forward(*dev_in, want_symbols=compress)   # outputs are allocated once and overwritten in place (forward(out=...)):
                                                # a cudaMalloc inside the timed region synchronises the device (measured:
                                                # 150-400 ms in the one step that had to grow the caching allocator's pool)
     def step_resident():
-        return eng.forward(*dev_in, out=out_buf)
+        return eng.forward(*dev_in, want_symbols=compress, out=out_buf)
 
     from dcae_b200.pipeline import HostPipeline
-    pipe = HostPipeline(eng, B, h, w)          # the public host-facing call: pinned host in, pinned host out
+    pipe = HostPipeline(eng, B, h, w, mode=cfg["mode"])      # the public host-facing call: pinned host in, pinned host out
 
     def run_e2e(steps):
         last = None
@@ -301,11 +371,14 @@ def main():
     if world > 1:
         ms_e2e = max_over_ranks(ms_e2e, dev)
     barrier()
-    assert bool(torch.isfinite(host_res["likelihoods"]).all())
+    if compress:
+        assert int(host_res["overflow"][0]) == 0 and int(host_res["indexes8"].max()) <= 63
+    else:
+        assert bool(torch.isfinite(host_res["likelihoods"]).all())
 
     # bpp over all ranks: the only data-path reduction -- one scalar all-reduce
     from dcae_b200.sharding import reduce_bpp
-    bpp = reduce_bpp(out["log2_lik_sum"], B * H_IMG * W_IMG)
+    bpp = reduce_bpp(out["log2_lik_sum"], B * cfg["H"] * cfg["W"])
 
     # per-kernel-family device time of one instrumented step (CUDA events on the launching stream)
     ms = (C.c_double * 4)(); work = (C.c_double * 4)(); cnt = (C.c_int64 * 4)()
@@ -313,11 +386,11 @@ def main():
     # kernels of two sub-batches overlap and per-kernel event times would count each other's SM time)
     eng_prof = eng if args.lanes == 1 else EntropySliceLoop(init_entropy_params(0, "lively"), device=dev, math=args.math, lanes=1)
     for _ in range(2):
-        eng_prof.forward(*dev_in)
+        eng_prof.forward(*dev_in, want_symbols=compress)
     torch.cuda.synchronize()
     lib.dcae_profile_start()
     for _ in range(2):
-        eng_prof.forward(*dev_in)
+        eng_prof.forward(*dev_in, want_symbols=compress)
     lib.dcae_profile_stop(ms, work, cnt)
     del eng_prof
     fam = {n: {"ms_per_step": ms[i] / 2, "launches_per_step": cnt[i] // 2, "work_per_step": work[i] / 2}
@@ -351,9 +424,12 @@ def main():
 
     cpu_baseline = None
     if rank == 0 and not args.no_cpu_baseline:
-        rate, threads, dt = cpu_oracle_rate(args.cpu_images, args.cpu_steps, 1)
-        cpu_baseline = {"value": rate, "unit": "images/s", "cores": threads, "kind": "port",
-                        "sample": f"{args.cpu_steps} steps x {args.cpu_images} images of 768x512 (same slice loop, torch-CPU fp32 oracle port)"}
+        n_cpu = B if args.config == 2 else 1            # bounded sample: ~10-30 s of host work
+        rate, threads, dt, kind = cpu_reference_rate(cfg, n_cpu, args.cpu_steps, 1)
+        cpu_baseline = {"value": rate, "unit": "images/s", "cores": threads, "kind": kind, "ms_per_step": dt * 1e3,
+                        "sample": f"{args.cpu_steps} steps x {n_cpu} images of {cfg['tag']} after 1 warm-up, torch fp32 on all host threads: "
+                                  + ("the unmodified reference classes of models/dcae.py (oracle/_ref), DCAE.%s slice loop on injected latents" % cfg["mode"]
+                                     if kind == "reference" else "oracle port of dcae.py:638-670")}
 
     h2d_bytes, d2h_bytes = pipe.h2d_bytes, pipe.d2h_bytes
     torch_gpu_baseline = None
@@ -361,31 +437,34 @@ def main():
         del eng, pipe, out_buf, out, host_res       # free the plans' workspaces before the eager run needs its temporaries
         torch.cuda.empty_cache()
         try:
-            rate, dt = gpu_eager_rate(dev, B, 2, 1)
-            rate_tf32, dt_tf32 = gpu_eager_rate(dev, B, 2, 1, tf32=True)
-            torch_gpu_baseline = {"value": rate, "unit": "images/s", "ms_per_step": dt * 1e3, "kind": "port",
-                                  "sample": f"2 steps x {B} images of 768x512: the oracle port run by eager PyTorch on this GPU (fp32, TF32 off, cuDNN on)",
+            gs = args.gpu_baseline_steps if not compress else 2
+            rate, dt, kind = gpu_eager_rate(cfg, dev, B, gs, 2)
+            rate_tf32, dt_tf32, _ = gpu_eager_rate(cfg, dev, B, gs, 2, tf32=True)
+            torch_gpu_baseline = {"value": rate, "unit": "images/s", "ms_per_step": dt * 1e3, "kind": kind,
+                                  "sample": f"{gs} steps x {B} images of {cfg['tag']} after 2 warm-ups: the reference's own classes (DCAE.{cfg['mode']} slice loop on injected latents) "
+                                            "run by eager PyTorch on this GPU with the reference's evaluation flags (fp32, TF32 off, cuDNN off: eval.py:3182-3187, 3904)",
                                   "tf32_on": {"value": rate_tf32, "ms_per_step": dt_tf32 * 1e3,
-                                              "note": "same with allow_tf32 = True for matmul and cuDNN (reduced precision: not the parity setting)"}}
+                                              "note": "same with TF32 and cuDNN on (reduced precision: not the parity setting)"}}
         except Exception as e:                      # noqa: BLE001  (a baseline leg must never take the bench line down)
             torch_gpu_baseline = {"value": None, "error": repr(e)[:200]}
 
     if rank == 0:
         imgs = B * world
         line = {
-            "metric": "entropy-model images/sec @768x512", "value": imgs / (ms_step * 1e-3), "unit": "images/s",
+            "metric": f"entropy-model images/sec @{cfg['tag']}", "value": imgs / (ms_step * 1e-3), "unit": "images/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": {"f16x3": "f32 (fp16 hi+lo planes = 22-bit operands, 3-pass tcgen05, fp32 accumulate)",
                       "tf32x3": "f32 (3xTF32 error-compensated tcgen05, fp32 accumulate)", "tf32": "tf32", "fp32": "f32"}[args.math],
             "data": "synthetic",
-            "config": {"workload": "DCAE entropy-model forward (slice loop), batch 16 synthetic Kodak-shaped 768x512 images per GPU (BASELINE config #2)",
+            "config": {"workload": cfg["workload"], "config": args.config, "mode": cfg["mode"],
                        "batch_per_gpu": B, "tokens_per_gpu": T, "math": args.math, "weights": "random-init (seeded, lively profile)",
-                       "l2": "no flush needed: per-step working set 1.8 GB >> 126 MB L2", "parallelism": f"{world} independent image shards", "lanes_per_gpu": args.lanes,
+                       "l2": f"no flush needed: per-step working set {T * 110e3 / 1e9:.1f} GB >> 126 MB L2" if T >= 4096 else "working set is L2-sized at this config (latency-bound single image)", "parallelism": f"{world} independent image shards", "lanes_per_gpu": args.lanes,
                        "warmup_steps_run": n_warm},
             "e2e": {"value": imgs / (ms_e2e * 1e-3), "unit": "images/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
-                    "how": "dcae_b200.HostPipeline: pinned host tensors in and out, H2D / compute / D2H of consecutive batches overlapped on 3 streams (wall clock over the K steps, last result on the host)"},
+                    "how": "dcae_b200.HostPipeline(mode=%r): pinned host tensors in and out, H2D / compute / D2H of consecutive batches overlapped on 3 streams (wall clock over the K steps, last result on the host)" % cfg["mode"]
+                           + ("; results = int16 symbols + uint8 indexes in coder order (what DCAE.compress hands to the range coder), y_hat stays on the device" if compress else "; results = y_hat, means, scales, likelihoods fp32")},
             "gpu_launches": launches * args.steps,
             "gpu_launches_per_step": launches,
             "clocks": clocks,

@@ -279,6 +279,52 @@ class EntropySliceLoop:
         symbols = h16 if overflow == 0 else sym.flatten().cpu()
         return {"symbols": symbols, "indexes": h8, "overflow": overflow, "y_hat": out["y_hat"]}
 
+    # ---- DCAE.compress / decompress with the native range coder (SURVEY 8f N1 + N2) -----------------------------
+    def compress_to_string(self, y, latent_scales, latent_means, gc) -> dict:
+        """dcae.py:713-761 between `(y, latent_scales, latent_means)` and `y_string`: the slice loop, ONE packed
+        device->host copy (int16 symbols, uint8 indexes, coder order) and one call into the native coder
+        (`dcae_b200.ans.BufferedRansEncoder`, libdcae_rans.so) -- instead of ten `.tolist()` syncs, 2 x 320 T Python
+        ints and a 200 k-element table list per call.  `gc`: the model's GaussianConditional (tables: `quantized_cdf`,
+        `cdf_length`, `offset`, dcae.py:718-720).  -> dict(y_string: bytes, y_hat: device tensor, overflow: int)."""
+        from .ans import BufferedRansEncoder
+        h = self.compress_to_host(y, latent_scales, latent_means)
+        enc = BufferedRansEncoder()
+        enc.encode_with_indexes(h["symbols"], h["indexes"], *self._coder_tables(gc))
+        return {"y_string": enc.flush(), "y_hat": h["y_hat"], "overflow": h["overflow"]}
+
+    def decompress_from_string(self, y_string: bytes, latent_scales, latent_means, gc) -> dict:
+        """dcae.py:875-906: per slice, the indexes leave the device in one copy, the native decoder returns the
+        symbols as one int32 array, and they go back in one copy (the reference: `.tolist()`, a Python list of ints,
+        `torch.Tensor(rv)` on the CPU, batch hard-coded to 1 at :894).  -> dict(y_hat, indexes)."""
+        from .ans import RansDecoder
+        dec = RansDecoder()
+        dec.set_stream(y_string)
+        tables = self._coder_tables(gc)
+        B, _, h, w = latent_scales.shape
+        n = B * SLICE_CH * h * w
+        host_idx = torch.empty(n, dtype=torch.int32).pin_memory()
+        host_sym = torch.empty(n, dtype=torch.int32).pin_memory()
+        stream = torch.cuda.current_stream(self.device)
+
+        def decode_slice(i, idx):
+            host_idx.copy_(idx.reshape(-1), non_blocking=True)
+            stream.synchronize()                                  # the decoder needs the indexes: one sync per slice
+            host_sym.numpy()[:] = dec.decode_array(host_idx.numpy(), *tables)
+            return host_sym.to(self.device, non_blocking=True).reshape(B, SLICE_CH, h, w)
+
+        return self.decompress(latent_scales, latent_means, decode_slice)
+
+    def _coder_tables(self, gc):
+        """Host copies of the three coder tables of a GaussianConditional, cached per (object, table version)."""
+        key = (id(gc), gc._quantized_cdf.data_ptr(), gc._quantized_cdf._version)
+        if getattr(self, "_tables_key", None) != key:
+            if gc._quantized_cdf.numel() == 0:
+                raise _lib.DcaeError("the GaussianConditional has no CDF tables: call net.update() / update_scale_table() first")
+            self._tables = (gc.quantized_cdf.detach().cpu().int().contiguous(), gc.cdf_length.detach().cpu().int().reshape(-1).contiguous(),
+                            gc.offset.detach().cpu().int().reshape(-1).contiguous())
+            self._tables_key = key
+        return self._tables
+
     # ---- DCAE.decompress slice loop -------------------------------------------------------------
     def decompress(self, latent_scales, latent_means,
                    decode_slice: Callable[[int, torch.Tensor], torch.Tensor]):

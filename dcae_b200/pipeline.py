@@ -15,7 +15,17 @@ OUT_KEYS = ("y_hat", "means", "scales", "likelihoods")
 
 
 class HostPipeline:
-    def __init__(self, engine: EntropySliceLoop, B: int, h: int, w: int, depth: int = 2, want_symbols: bool = False):
+    """mode "forward": the four fp32 tensors of DCAE.forward (+ int32 symbols / indexes with want_symbols) come back.
+    mode "compress": what DCAE.compress hands to the range coder comes back -- int16 symbols, uint8 indexes in coder
+    order (dcae.py:742-743; `dcae_pack_symbols`), the overflow count and the bpp numerator; y_hat stays on the device
+    for g_s (`dev_out[k]["y_hat"]`): 3 bytes per element over PCIe instead of 16."""
+
+    def __init__(self, engine: EntropySliceLoop, B: int, h: int, w: int, depth: int = 2, want_symbols: bool = False,
+                 mode: str = "forward"):
+        if mode not in ("forward", "compress"):
+            raise ValueError(mode)
+        self.mode = mode
+        want_symbols = want_symbols or mode == "compress"
         self.eng, self.depth, self.want_symbols = engine, depth, want_symbols
         dev = engine.device
         self.s_h2d, self.s_cmp, self.s_d2h = (torch.cuda.Stream(dev) for _ in range(3))
@@ -24,9 +34,16 @@ class HostPipeline:
         self.dev_out: List[Dict[str, torch.Tensor]] = []
         self.host_out: List[Dict[str, torch.Tensor]] = []
         keys = OUT_KEYS + (("symbols", "indexes") if want_symbols else ())
+        if mode == "compress":
+            keys = ("symbols16", "indexes8", "overflow", "log2_lik_sum")
         with torch.cuda.stream(self.s_cmp):
             for k in range(depth):      # one warm call per slot creates the output buffers (and the plan)
                 o = engine.forward(*self.dev_in[k], want_symbols=want_symbols)
+                if mode == "compress":
+                    n = o["symbols"].numel()
+                    o["symbols16"] = torch.empty(n, dtype=torch.int16, device=dev)
+                    o["indexes8"] = torch.empty(n, dtype=torch.uint8, device=dev)
+                    o["overflow"] = torch.zeros(1, dtype=torch.int64, device=dev)
                 self.dev_out.append(o)
                 self.host_out.append({key: torch.empty(o[key].shape, dtype=o[key].dtype).pin_memory() for key in keys})
         self.s_cmp.synchronize()
@@ -54,7 +71,13 @@ class HostPipeline:
             with torch.cuda.stream(self.s_cmp):
                 self.s_cmp.wait_event(self.ev_in[k])
                 self.s_cmp.wait_event(self.ev_out[k])   # the previous outputs of this slot have left the device
-                self.eng.forward(*self.dev_in[k], want_symbols=self.want_symbols, out=self.dev_out[k])
+                o = self.eng.forward(*self.dev_in[k], want_symbols=self.want_symbols, out=self.dev_out[k])
+                if self.mode == "compress":
+                    from . import _lib
+                    with torch.cuda.device(self.eng.device):
+                        _lib.check(self.eng.lib.dcae_pack_symbols(o["symbols"].data_ptr(), o["indexes"].data_ptr(), o["symbols"].numel(),
+                                                                  o["symbols16"].data_ptr(), o["indexes8"].data_ptr(), o["overflow"].data_ptr(),
+                                                                  self.s_cmp.cuda_stream), "dcae_pack_symbols")
                 self.ev_cmp[k].record(self.s_cmp)
             with torch.cuda.stream(self.s_d2h):
                 self.s_d2h.wait_event(self.ev_cmp[k])

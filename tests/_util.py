@@ -5,7 +5,7 @@ import numpy as np
 import torch
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-GOLDEN_CASES = ["slice_loop_b2_7x9", "slice_loop_b1_8x12"]
+GOLDEN_CASES = ["slice_loop_b2_7x9", "slice_loop_b1_8x12", "slice_loop_b1_16x16"]
 
 
 def load_golden(name):

@@ -4,7 +4,7 @@
 
 What runs: `/root/reference/models/dcae.py` `DCAE.forward` (:623-677), `DCAE.compress` (:698-761)
 and `DCAE.decompress` (:859-910), loaded by file path with import stubs
-(`tests/_reference_loader.py`).  Everything outside the hot path is replaced by injectors so the
+(`oracle/reference_loader.py`).  Everything outside the hot path is replaced by injectors so the
 loops see chosen `(y, latent_scales, latent_means)`:
   g_a -> returns y;  h_a -> zeros;  entropy_bottleneck -> stub;  h_z_s1/h_z_s2 -> return the latents;
   g_s -> identity (so "x_hat" is y_hat);  rANS encoder/decoder -> recorders of (symbols, indexes).
@@ -33,6 +33,9 @@ CASES = {
     # name: (seed_params, seed_inputs, B, h, w)
     "slice_loop_b2_7x9": (7, 11, 2, 7, 9),
     "slice_loop_b1_8x12": (7, 12, 1, 8, 12),
+    # one image of 256x256 (BASELINE config #1): B = 1 and h, w multiples of 4, so the reference's decompress() runs
+    # (dcae.py:866, :894) and its golden output spans two 128-token tiles
+    "slice_loop_b1_16x16": (7, 13, 1, 16, 16),
 }
 
 

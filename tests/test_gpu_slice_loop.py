@@ -17,7 +17,9 @@ pytestmark = pytest.mark.gpu
 
 FP32_TOL = 1e-5
 # (per-slice teacher-forced rel tol, max teacher-forced sym/idx mismatch rate, max free-running mismatch rate)
-MODES = {"fp32": (FP32_TOL, 1e-3, 2e-3), "tf32x3": (FP32_TOL, 1e-3, 5e-2), "f16x3": (FP32_TOL, 1e-3, 5e-2), "tf32": (1e-2, 5e-2, 0.3)}
+# the rates are <= 5 x the worst value observed on B200 over the three golden cases (printed by the tests;
+# profiles/r02/parity_rates.txt): a regression 10 x worse than today fails
+MODES = {"fp32": (FP32_TOL, 2e-4, 2e-4), "tf32x3": (FP32_TOL, 5e-4, 7.5e-4), "f16x3": (FP32_TOL, 5e-4, 5e-4), "tf32": (1e-2, 5e-2, 0.3)}
 
 _engines = {}
 
@@ -137,11 +139,12 @@ def test_stagewise_taps_vs_oracle(math, lively_params):
     assert rel_err(got, dict_info.permute(0, 2, 3, 1).reshape(-1, 320)) < FP32_TOL
 
 
+@pytest.mark.parametrize("case", ["slice_loop_b1_8x12", "slice_loop_b1_16x16"])
 @pytest.mark.parametrize("math", ["fp32", "tf32x3", "f16x3"])
-def test_decompress_reproduces_compress_bit_exactly(math, lively_params):
+def test_decompress_reproduces_compress_bit_exactly(math, case, lively_params):
     """The codec property the reference fights for: the decoder regenerates the SAME indexes
     from its own scales and the same y_hat, bit for bit, on this device."""
-    g = load_golden("slice_loop_b1_8x12")
+    g = load_golden(case)
     eng = engine(lively_params, math)
     y, ls, lm = (g[k].cuda() for k in ("y", "latent_scales", "latent_means"))
     enc = eng.compress(y, ls, lm)
@@ -149,8 +152,12 @@ def test_decompress_reproduces_compress_bit_exactly(math, lively_params):
     assert torch.equal(dec["indexes"], enc["indexes"])
     assert torch.equal(dec["y_hat"], enc["y_hat"])
     # and against the reference's own decompress() output (x_hat = clamp(y_hat, 0, 1) in the golden run)
-    if math == "fp32":
-        assert mismatch_rate(dec["indexes"].cpu(), g["dec_indexes"]) <= 2e-3
+    assert mismatch_rate(dec["indexes"].cpu(), g["dec_indexes"]) <= MODES[math][2]
+    # teacher-forced decode of the REFERENCE's symbols: y_hat of the reference's decompress() (x_hat = clamp(y_hat, 0, 1))
+    ref_sym = g["symbols"].cuda()
+    forced = eng.decompress(ls, lm, lambda i, idx: ref_sym[i])
+    err = float((forced["y_hat"].clamp(0, 1).cpu() - g["dec_y_hat"]).abs().max())
+    assert err < FP32_TOL * float(g["y_hat"].abs().max())          # same absolute bar as the unclamped y_hat comparison
 
 
 def test_batch_invariance_and_determinism(lively_params):
@@ -344,3 +351,70 @@ def test_cuda_graph_replay_equals_stream_launches(lively_params):
     torch.cuda.synchronize()
     again = eng.forward(y, ls, lm, want_symbols=True)
     assert torch.equal(out["symbols"], again["symbols"]) and torch.equal(out["y_hat"], again["y_hat"])
+
+
+@pytest.mark.parametrize("name,B,h,w", [("config2_kodak_768x512", 2, 32, 48), ("config3_clic_2048x1408", 1, 88, 128),
+                                        ("config5_4k_3840x2176", 1, 136, 240)])
+@pytest.mark.parametrize("math", ["f16x3"])
+def test_full_depth_parity_at_baseline_sizes(name, B, h, w, math, lively_params):
+    """All FIVE slices at the BASELINE.json latent sizes against the CPU oracle, teacher-forced: slice i is computed
+    from the oracle's own symbols of slices < i (replayed through the decode path, what DCAE.decompress does), so
+    mu / scale of every slice -- the long-K cc1 of slices 1-4, the LRP chain, the y_hat planes feeding later slices,
+    multi-wave persistent schedules -- are compared element for element at <= 1e-5, and symbols / indexes by rate."""
+    from dcae_b200 import _lib
+    eng = engine(lively_params, math)
+    gen = torch.Generator().manual_seed(4321)
+    y = 4 * torch.randn(B, 320, h, w, generator=gen)
+    ls, lm = torch.randn(B, 320, h, w, generator=gen), torch.randn(B, 320, h, w, generator=gen)
+    o_sym, o_idx, o_yhat, o_mu, o_sc = SliceLoopOracle(lively_params).compress(y, ls, lm)
+    yc, lsc, lmc = y.cuda(), ls.cuda(), lm.cuda()
+    lib, plan, s = eng.lib, eng._plan(B, h, w), _lib.current_stream(eng.device)
+    _lib.check(lib.dcae_slice_loop_load(plan.handle, yc.data_ptr(), lsc.data_ptr(), lmc.data_ptr(), s))
+    idx = torch.empty(B, 64, h, w, dtype=torch.int32, device="cuda")
+    tok2img = lambda t: t.reshape(B, h, w, -1).permute(0, 3, 1, 2)
+    worst = {"mu": 0.0, "scale": 0.0, "idx": 0.0, "sym": 0.0}
+    for i in range(5):
+        sl = slice(64 * i, 64 * i + 64)
+        _lib.check(lib.dcae_slice_loop_params(plan.handle, i, s))
+        _lib.check(lib.dcae_slice_loop_indexes(plan.handle, i, idx.data_ptr(), s))
+        mu = tok2img(eng.tap("means", B, h, w)[:, sl]).cpu()
+        sc = tok2img(eng.tap("scales", B, h, w)[:, sl]).cpu()
+        e_mu, e_sc = rel_err(mu, o_mu[:, sl]), rel_err(sc, o_sc[:, sl])
+        assert e_mu < FP32_TOL and e_sc < FP32_TOL, (i, e_mu, e_sc)
+        worst["mu"], worst["scale"] = max(worst["mu"], e_mu), max(worst["scale"], e_sc)
+        worst["idx"] = max(worst["idx"], mismatch_rate(idx.cpu(), o_idx[i]))
+        worst["sym"] = max(worst["sym"], mismatch_rate(ogc.quantize(y[:, sl], "symbols", mu), o_sym[i]))
+        assert torch.equal(idx.cpu(), ogc.build_indexes(sc, ogc.get_scale_table()))      # kernel 3 on the device's own scale
+        sym = o_sym[i].cuda().contiguous()
+        _lib.check(lib.dcae_slice_loop_decode(plan.handle, i, sym.data_ptr(), s))
+    y_hat = torch.empty_like(yc)
+    _lib.check(lib.dcae_slice_loop_store(plan.handle, y_hat.data_ptr(), None, None, None, None, None, None, s))
+    torch.cuda.synchronize()
+    worst["y_hat"] = rel_err(y_hat.cpu(), o_yhat)
+    print(f"\n[{name} {math}] T={B * h * w} teacher-forced, all 5 slices: " + ", ".join(f"{k} {v:.2e}" for k, v in worst.items()))
+    assert worst["y_hat"] < FP32_TOL
+    assert worst["idx"] <= MODES[math][1] and worst["sym"] <= MODES[math][1]
+
+
+def test_range_coder_round_trip_through_the_slice_loop(lively_params):
+    """SURVEY 8f N1 + N2: compress_to_string -> decompress_from_string on the device reproduces y_hat bit for bit, the
+    stream decodes (pure-Python restatement of the coder) to exactly the symbols the loop emitted, and its length is the
+    likelihoods' bit count to a fraction of a percent (the tables quantise the same Gaussians)."""
+    from dcae_b200.gaussian_conditional import GaussianConditional
+    from oracle import rans as orans
+    g = load_golden("slice_loop_b2_7x9")
+    eng = engine(lively_params, "f16x3")
+    gcm = GaussianConditional(None).cuda()
+    gcm.update_scale_table(ogc.get_scale_table())
+    y, ls, lm = (g[k].cuda() for k in ("y", "latent_scales", "latent_means"))
+    enc = eng.compress(y, ls, lm, with_likelihoods=True)
+    out = eng.compress_to_string(y, ls, lm, gcm)
+    assert isinstance(out["y_string"], bytes) and out["overflow"] == 0
+    dec = eng.decompress_from_string(out["y_string"], ls, lm, gcm)
+    assert torch.equal(dec["y_hat"], enc["y_hat"]) and torch.equal(dec["indexes"], enc["indexes"])
+    q, ln, off = gcm.quantized_cdf.cpu().tolist(), gcm.cdf_length.cpu().tolist(), gcm.offset.cpu().tolist()
+    sym = orans.Decoder(out["y_string"]).decode(enc["indexes"].flatten().cpu().tolist(), q, ln, off)
+    assert sym == enc["symbols"].flatten().cpu().tolist()
+    bits = float(-torch.log2(enc["likelihoods"].double()).sum())
+    print(f"\nstream {len(out['y_string']) * 8} bits, -sum log2 lik {bits:.0f} bits")
+    assert abs(len(out["y_string"]) * 8 - bits) / bits < 0.08      # scales are coded at the next table entry up: a few % over
