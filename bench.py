@@ -416,7 +416,10 @@ def main():
     # kernel 3 alone at an HBM-sized footprint (per-slice launches are L2-resident at B=16)
     roofline_gc = None
     if rank == 0:
-        roofline_gc = gc_microbench(dev, lib, args.gc_micro_mb, peaks)
+        roofline_gc = gc_microbench(dev, lib, args.gc_micro_mb, peaks, variant="compress" if compress else "forward")
+        other = gc_microbench(dev, lib, args.gc_micro_mb, peaks, variant="forward" if compress else "compress")
+        ref_math = gc_microbench(dev, lib, args.gc_micro_mb, peaks, variant="compress", lik_math="reference")
+        roofline_gc["other_variants"] = [{k: r[k] for k in ("variant", "lik_math", "achieved", "frac", "ms")} for r in (other, ref_math)]
         roofline_gc["in_loop"] = {"ms_per_step": fam["gc"]["ms_per_step"], "launches_per_step": fam["gc"]["launches_per_step"],
                                   "GB/s": fam["gc"]["work_per_step"] / max(fam["gc"]["ms_per_step"], 1e-9) / 1e6,
                                   "traffic": ncu_traffic("prof_gc_final_summary.csv"),
@@ -481,10 +484,12 @@ def main():
         dist.destroy_process_group()
 
 
-def gc_microbench(dev, lib, mb, peaks):
-    """Kernel 3 timed alone on inputs far larger than L2: algorithmic 28 B/element."""
+def gc_microbench(dev, lib, mb, peaks, variant="compress", lik_math="fast"):
+    """Kernel 3 timed alone on inputs far larger than L2.  variant "compress": y, mu, scale in; lik, y_hat, sym, idx out
+    = 28 B/element; "forward": no int32 stores = 20 B/element."""
     from dcae_b200 import _lib
-    n = mb * (1 << 20) // GC_BYTES_PER_ELEM // 64 * 64
+    bpe = GC_BYTES_PER_ELEM if variant == "compress" else 20
+    n = mb * (1 << 20) // bpe // 64 * 64
     rows = n // 64
     g = torch.Generator(device=dev).manual_seed(1)
     y = 4 * torch.randn(rows, 64, device=dev, generator=g)
@@ -492,14 +497,16 @@ def gc_microbench(dev, lib, mb, peaks):
     sc = torch.exp(torch.empty(rows, 64, device=dev).uniform_(-3.0, 5.7, generator=g))
     from dcae_b200.entropy_model import get_scale_table
     table = get_scale_table().to(dev)
-    outs = [torch.empty(rows, 64, device=dev), torch.empty(rows, 64, device=dev),
-            torch.empty(rows, 64, device=dev, dtype=torch.int32), torch.empty(rows, 64, device=dev, dtype=torch.int32)]
+    outs = [torch.empty(rows, 64, device=dev), torch.empty(rows, 64, device=dev)]
     a = _lib.GcArgs()
     a.y, a.y_ld, a.mu, a.mu_ld, a.scale, a.scale_ld = y.data_ptr(), 64, mu.data_ptr(), 64, sc.data_ptr(), 64
     a.scale_table, a.n_table, a.scale_bound, a.lik_bound, a.mode = table.data_ptr(), 64, 0.11, 1e-9, 0
     a.rows, a.inner = rows, 64
+    a.lik_math = _lib.GC_LIK[lik_math]
     a.y_hat, a.y_hat_ld, a.lik, a.lik_ld = outs[0].data_ptr(), 64, outs[1].data_ptr(), 64
-    a.sym, a.sym_ld, a.idx, a.idx_ld = outs[2].data_ptr(), 64, outs[3].data_ptr(), 64
+    if variant == "compress":
+        outs += [torch.empty(rows, 64, device=dev, dtype=torch.int32), torch.empty(rows, 64, device=dev, dtype=torch.int32)]
+        a.sym, a.sym_ld, a.idx, a.idx_ld = outs[2].data_ptr(), 64, outs[3].data_ptr(), 64
     s = _lib.current_stream(dev)
     for _ in range(3):
         _lib.check(lib.dcae_gc_fused(a, s))
@@ -512,10 +519,10 @@ def gc_microbench(dev, lib, mb, peaks):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
-    gbs = n * GC_BYTES_PER_ELEM / (ms * 1e-3) / 1e9
+    gbs = n * bpe / (ms * 1e-3) / 1e9
     return {"kernel": "gc_fused_kernel", "bound": "hbm", "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s",
-            "frac": gbs / peaks["hbm"], "traffic": None, "elements": n, "ms": ms,
-            "note": f"kernel 3 alone, {n * GC_BYTES_PER_ELEM / 2**20:.0f} MiB algorithmic footprint (28 B/element), peak = {peaks['src']} copy bandwidth"}
+            "frac": gbs / peaks["hbm"], "traffic": None, "elements": n, "ms": ms, "variant": variant, "lik_math": lik_math,
+            "note": f"kernel 3 alone, {n * bpe / 2**20:.0f} MiB algorithmic footprint ({bpe} B/element, {variant} variant, likelihood math {lik_math!r}), peak = {peaks['src']} copy bandwidth"}
 
 
 if __name__ == "__main__":

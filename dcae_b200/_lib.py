@@ -11,6 +11,8 @@ LIB_PATH = os.path.join(_HERE, "libdcae_b200.so")
 OK = 0
 MATH = {"fp32": 0, "tf32x3": 1, "tf32": 2, "f16x3": 3}
 GC_EVAL, GC_NOISE, GC_DECODE = 0, 1, 2
+GC_LIK = {"fast": 0, "reference": 1}
+OPT_LIK_MATH, OPT_WANT_SYMBOLS = 0, 1
 ACT_NONE, ACT_GELU, ACT_HALF_TANH = 0, 1, 2
 
 c_f32p = C.c_void_p   # device pointers travel as integers
@@ -38,6 +40,7 @@ class GcArgs(C.Structure):
         ("sym", c_i32p), ("sym_ld", C.c_int64),
         ("idx", c_i32p), ("idx_ld", C.c_int64),
         ("log2_partials", c_f32p),
+        ("lik_math", C.c_int32),
     ]
 
 
@@ -129,6 +132,7 @@ SIGNATURES = {
     "dcae_slice_loop_check_f16_range": (C.c_int, [_P, _I32, C.POINTER(C.c_ulonglong)]),
     "dcae_count_f16_clamped": (C.c_int, [C.POINTER(Planes), _I64, _I32, _P, _P]),
     "dcae_slice_loop_destroy": (None, [_P]),
+    "dcae_slice_loop_set_option": (C.c_int, [_P, _I32, _I32]),
     "dcae_slice_loop_load": (C.c_int, [_P, _P, _P, _P, _P]),
     "dcae_slice_loop_params": (C.c_int, [_P, _I32, _P]),
     "dcae_slice_loop_encode": (C.c_int, [_P, _I32, _I32, _P, _P]),

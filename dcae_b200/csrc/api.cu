@@ -211,6 +211,8 @@ struct dcae_slice_loop {
   cudaStream_t side;
   cudaEvent_t ev_fork, ev_join;
   int n_table;                       // entries of scale_table (2..256)
+  int lik_math;                      // DCAE_GC_LIK_FAST (default) / DCAE_GC_LIK_REFERENCE
+  bool want_sym;                     // encode also emits int32 symbols / indexes (DCAE_OPT_WANT_SYMBOLS; forward sets it per call)
   bool check_range;                  // DCAE_MATH_F16X3: count operand-plane elements that hit the fp16 clamp (see dcae_slice_loop_check_f16_range)
   unsigned long long* sat_count;     // device counter, part of the workspace
 };
@@ -300,6 +302,7 @@ extern "C" int dcae_slice_loop_create(dcae_slice_loop** out, int32_t B, int32_t 
   memcpy(p->wt, weights, sizeof(dcae_slice_weights) * NS);
   p->scale_table = scale_table;
   p->n_table = scale_table ? n_table : 0;
+  p->want_sym = true;
   p->n_part = dcae_gc_num_partials(p->T, SL);
   if (p->pm) {
     // padded K windows over-read a few never-written plane columns (their weight planes are zero): make them finite
@@ -321,6 +324,21 @@ extern "C" int dcae_slice_loop_create(dcae_slice_loop** out, int32_t B, int32_t 
 }
 
 extern "C" void dcae_slice_loop_destroy(dcae_slice_loop* p) { free_slice_loop(p); }
+
+extern "C" int dcae_slice_loop_set_option(dcae_slice_loop* p, int32_t option, int32_t value) {
+  DCAE_REQUIRE(p, "dcae_slice_loop_set_option: null plan");
+  switch (option) {
+    case DCAE_OPT_WANT_SYMBOLS:
+      p->want_sym = value != 0;
+      return DCAE_OK;
+    case DCAE_OPT_LIK_MATH:
+      DCAE_REQUIRE(value == DCAE_GC_LIK_FAST || value == DCAE_GC_LIK_REFERENCE, "dcae_slice_loop_set_option: bad lik_math %d", value);
+      p->lik_math = value;
+      return DCAE_OK;
+  }
+  set_error("dcae_slice_loop_set_option: unknown option %d", option);
+  return DCAE_E_INVALID;
+}
 
 // ---- small builders --------------------------------------------------------------------------
 static dcae_planes pl(const PBuf& b, int col = 0) {
@@ -595,6 +613,7 @@ static dcae_gc_args gc_base(dcae_slice_loop* p, int i) {
   a.scale_table = p->scale_table; a.n_table = p->n_table;
   a.scale_bound = 0.11f; a.lik_bound = 1e-9f;
   a.rows = p->T; a.inner = SL;
+  a.lik_math = p->lik_math;
   return a;
 }
 
@@ -611,8 +630,10 @@ extern "C" int dcae_slice_loop_encode(dcae_slice_loop* p, int32_t i, int32_t gc_
   a.y_hat = p->sup.p + SUP_PRE; a.y_hat_ld = SUP_LD;
   if (p->pm) a.y_hat16 = pl(p->supp, SUP_PRE);
   a.lik = p->lik.p + SL * i; a.lik_ld = M;
-  a.sym = p->sym + SL * i; a.sym_ld = M;
-  if (p->scale_table) { a.idx = p->idx + SL * i; a.idx_ld = M; }
+  if (p->want_sym) {                 // forward without symbols: the 20 B/element variant (no int32 stores)
+    a.sym = p->sym + SL * i; a.sym_ld = M;
+    if (p->scale_table) { a.idx = p->idx + SL * i; a.idx_ld = M; }
+  }
   a.log2_partials = p->part.p + (int64_t)i * p->n_part;
   DCAE_TRY(dcae_gc_fused(&a, s));
   DCAE_TRY(chk(p, a.y_hat16, SL, s));
@@ -662,6 +683,7 @@ extern "C" int dcae_slice_loop_store(dcae_slice_loop* p, float* y_hat, float* me
   if (scales) DCAE_TRY(dcae_op_tokens_to_nchw(p->scales.p, M, p->B, M, p->HW, scales, s));
   if (lik) DCAE_TRY(dcae_op_tokens_to_nchw(p->lik.p, M, p->B, M, p->HW, lik, s));
   const int64_t per_slice = (int64_t)p->B * SL * p->HW;
+  DCAE_REQUIRE(!(symbols || indexes) || p->want_sym, "dcae_slice_loop_store: symbols / indexes requested but DCAE_OPT_WANT_SYMBOLS was off during encode");
   for (int i = 0; i < NS; ++i) {
     if (symbols) DCAE_TRY(dcae_op_tokens_to_nchw_i32(p->sym + SL * i, M, p->B, SL, p->HW, symbols + i * per_slice, s));
     if (indexes) {
@@ -677,6 +699,7 @@ extern "C" int dcae_slice_loop_forward(dcae_slice_loop* p, const float* y, const
                                        const float* latent_means, float* y_hat, float* means, float* scales, float* lik,
                                        int32_t* symbols, int32_t* indexes, float* log2_lik_sum, void* s) {
   DCAE_REQUIRE(p && y, "dcae_slice_loop_forward: null argument");
+  p->want_sym = symbols != nullptr || indexes != nullptr;
   DCAE_TRY(dcae_slice_loop_load(p, y, latent_scales, latent_means, s));
   for (int i = 0; i < NS; ++i) {
     DCAE_TRY(dcae_slice_loop_params(p, i, s));

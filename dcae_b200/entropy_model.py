@@ -40,6 +40,7 @@ class _Plan:
         _lib.check(lib.dcae_slice_loop_create(C.byref(self.handle), B, h, w, eng.weights.array, table, n_table, base,
                                               nbytes, _lib.MATH[eng.math]), "dcae_slice_loop_create")
         self.lib = lib
+        _lib.check(lib.dcae_slice_loop_set_option(self.handle, _lib.OPT_LIK_MATH, _lib.GC_LIK[eng.likelihood_math]), "set_option")
 
     def __del__(self):
         try:
@@ -52,6 +53,8 @@ class _Plan:
 class EntropySliceLoop:
     """params: reference state dict (hot-path keys).
     math: 'f16x3' (default: fp16 hi/lo planes, fp32-level accuracy) | 'tf32x3' | 'fp32' (FFMA) | 'tf32' (reduced).
+    likelihood_math: 'fast' (default: cancellation-free evaluation of kernel 3's likelihood, <= 1e-5 of the exact value) |
+    'reference' (the reference's op order with libdevice erfcf: bit-identical to torch-CUDA on dcae.py:839-857; test mode).
     lanes: images are independent, so `forward` splits the batch into this many sub-batches, each with its
     own plan on its own stream.  Every kernel of the loop is a persistent grid with a partly filled last wave (960
     tiles on 148 SMs; 192 for the small conv layers) and the loop is one dependent chain, so a lone lane leaves SMs
@@ -59,9 +62,12 @@ class EntropySliceLoop:
     depend on the split (tests: batch invariance)."""
 
     def __init__(self, params: Dict[str, torch.Tensor], device="cuda:0", math: str = "f16x3",
-                 scale_table: Optional[torch.Tensor] = None, lanes: int = 2):
+                 scale_table: Optional[torch.Tensor] = None, lanes: int = 2, likelihood_math: str = "fast"):
         if math not in _lib.MATH:
             raise ValueError(f"math must be one of {list(_lib.MATH)}")
+        if likelihood_math not in _lib.GC_LIK:
+            raise ValueError(f"likelihood_math must be one of {list(_lib.GC_LIK)}")
+        self.likelihood_math = likelihood_math
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise _lib.DcaeError("dcae_b200 runs on CUDA devices only (no CPU fallback)")
@@ -236,6 +242,7 @@ class EntropySliceLoop:
                                                    _lib.ptr(sym), _lib.ptr(idx), log2_sum.data_ptr(), s),
                        "dcae_slice_loop_forward")
         else:
+            _lib.check(lib.dcae_slice_loop_set_option(plan.handle, _lib.OPT_WANT_SYMBOLS, int(sym is not None)), "set_option")
             _lib.check(lib.dcae_slice_loop_load(plan.handle, y.data_ptr(), ls.data_ptr(), lm.data_ptr(), s), "load")
             for i, nz in enumerate(noise.chunk(NUM_SLICES, 1)):
                 nz = nz.contiguous()
@@ -360,6 +367,7 @@ class EntropySliceLoop:
         with torch.cuda.device(self.device):
             _lib.check(self.lib.dcae_slice_loop_module_dca(self._plan(B, h, w).handle, i, x.data_ptr(), out.data_ptr(),
                                                            self._stream()), "dcae_slice_loop_module_dca")
+        self.last_launches = int(self.lib.dcae_launch_count())
         return out
 
     def module_conv(self, i: int, which: int, x: torch.Tensor) -> torch.Tensor:
@@ -372,6 +380,7 @@ class EntropySliceLoop:
         with torch.cuda.device(self.device):
             _lib.check(self.lib.dcae_slice_loop_module_conv(self._plan(B, h, w).handle, i, which, x.data_ptr(), out.data_ptr(),
                                                             self._stream()), "dcae_slice_loop_module_conv")
+        self.last_launches = int(self.lib.dcae_launch_count())
         return out
 
     # ---- debugging / stage-wise parity (the reference's debug_save pattern, dcae_5_fixed.py:29-34) ---

@@ -29,8 +29,11 @@ class _Bound(nn.Module):
 
 class GaussianConditional(nn.Module):
     def __init__(self, scale_table=None, scale_bound: float = 0.11, tail_mass: float = 1e-9,
-                 likelihood_bound: float = 1e-9, entropy_coder_precision: int = 16):
+                 likelihood_bound: float = 1e-9, entropy_coder_precision: int = 16, likelihood_math: str = "fast"):
         super().__init__()
+        if likelihood_math not in _lib.GC_LIK:
+            raise ValueError(f"likelihood_math must be one of {list(_lib.GC_LIK)}")
+        self.likelihood_math = likelihood_math      # "reference": the reference's op order, bit-identical to torch-CUDA (test mode)
         self.tail_mass = float(tail_mass)
         self.entropy_coder_precision = int(entropy_coder_precision)
         # compressai's published module also owns `scale_bound`, `lower_bound_scale.bound` and
@@ -148,6 +151,7 @@ class GaussianConditional(nn.Module):
             a.scale_table, a.n_table = table.data_ptr(), table.numel()
         a.scale_bound, a.lik_bound, a.mode = self._bounds[0], self._bounds[1], mode
         a.rows, a.inner = n_rows, inner
+        a.lik_math = _lib.GC_LIK[self.likelihood_math]
         outs = {}
         for name, dt in (("y_hat", torch.float32), ("lik", torch.float32), ("sym", torch.int32), ("idx", torch.int32)):
             if name in want:

@@ -80,6 +80,13 @@ int dcae_device_check(void);
  * receives per-block sums of log2(lik) in a fixed order (bpp numerator, train.py:82-85).
  * ------------------------------------------------------------------------------------------*/
 enum { DCAE_GC_EVAL = 0, DCAE_GC_NOISE = 1, DCAE_GC_DECODE = 2 };
+/* How the likelihood is evaluated.  Symbols, indexes and y_hat do not depend on it.
+ * FAST (0, the default of a zero-initialised struct): erfc(x) = 2^P(x) with a divided-difference form of
+ *   erfc(a) - erfc(b), no cancellation: <= 1e-5 relative to the EXACT value of the reference's formula everywhere above
+ *   the 1e-9 floor (measured 6e-6; the reference's own fp32 evaluation is at 1.5e-4 at large scales).
+ * REFERENCE (1): the reference's op order with libdevice erfcf and IEEE divisions: bit-identical to torch evaluating
+ *   dcae.py:839-857 on the GPU; about twice the instructions (the test mode). */
+enum { DCAE_GC_LIK_FAST = 0, DCAE_GC_LIK_REFERENCE = 1 };
 
 typedef struct {
   const float* y;          int64_t y_ld;
@@ -98,6 +105,7 @@ typedef struct {
   int32_t* sym;   int64_t sym_ld;
   int32_t* idx;   int64_t idx_ld;
   float* log2_partials;
+  int32_t lik_math;                               /* DCAE_GC_LIK_FAST (default) or DCAE_GC_LIK_REFERENCE */
 } dcae_gc_args;
 
 int dcae_gc_fused(const dcae_gc_args* a, void* stream);
@@ -271,6 +279,12 @@ int dcae_slice_loop_create(dcae_slice_loop** out, int32_t B, int32_t h, int32_t 
                            const dcae_slice_weights* weights, const float* scale_table, int32_t n_table,
                            void* workspace, size_t workspace_bytes, int math);
 void dcae_slice_loop_destroy(dcae_slice_loop* p);
+/* Plan options.  DCAE_OPT_LIK_MATH: DCAE_GC_LIK_FAST (default) or DCAE_GC_LIK_REFERENCE for kernel 3's likelihood.
+ * DCAE_OPT_WANT_SYMBOLS (default 1): dcae_slice_loop_encode also writes the int32 symbols / indexes (28 B/element);
+ * 0 = DCAE.forward only needs y_hat and likelihoods (20 B/element).  dcae_slice_loop_forward sets it per call from its
+ * symbols / indexes arguments. */
+enum { DCAE_OPT_LIK_MATH = 0, DCAE_OPT_WANT_SYMBOLS = 1 };
+int dcae_slice_loop_set_option(dcae_slice_loop* p, int32_t option, int32_t value);
 
 /* NCHW fp32 [B,320,h,w] -> token-major workspace.  y may be NULL (decompress). */
 int dcae_slice_loop_load(dcae_slice_loop* p, const float* y, const float* latent_scales,

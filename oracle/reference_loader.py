@@ -98,12 +98,13 @@ def _install_stubs():
         def __init__(self, channels, *a, **k):
             super().__init__()
             self.channels = channels
+            self.register_buffer("_where", torch.zeros(1), persistent=False)      # follows .to(device)
 
         def forward(self, z):
             return z, torch.ones_like(z)
 
         def _get_medians(self):
-            return torch.zeros(1, self.channels, 1, 1)
+            return torch.zeros(1, self.channels, 1, 1, device=self._where.device)
 
         def compress(self, z):
             self._z = torch.round(z)

@@ -18,11 +18,24 @@ LIK_RTOL = 1e-5     # north-star tolerance for likelihoods
 LIK_ATOL = 4 * 5.96e-8
 
 
-def _gc():
+def _gc(likelihood_math="reference"):
+    """reference = the reference's op order, bit-identical to torch-CUDA (what most tests below pin);
+    fast = the production default, checked against the exact value in test_fast_likelihood_*."""
     from dcae_b200.gaussian_conditional import GaussianConditional
-    g = GaussianConditional(None).cuda()
+    g = GaussianConditional(None, likelihood_math=likelihood_math).cuda()
     g.update_scale_table(orc.get_scale_table())
     return g
+
+
+def _exact_likelihood(out, mu, scale, bound=0.11):
+    """The reference's formula (dcae.py:839-857) in fp64 on the fp32 inputs the kernel sees: v = |fl32(out - mu)|."""
+    v = (out - mu).abs().double()
+    s = torch.clamp(scale, min=bound).double()
+    k = 1.0 / (s * (2.0 ** 0.5))
+    a, b = (v - 0.5) * k, (v + 0.5) * k
+    # erfc(a) - erfc(b) without cancellation in fp64: via erf for small arguments
+    small = b < 3.0
+    return torch.where(small, 0.5 * (torch.erf(b) - torch.erf(a)), 0.5 * (torch.erfc(a) - torch.erfc(b)))
 
 
 def _direct_inputs(shape, seed=4321):
@@ -197,3 +210,72 @@ def test_kernel3_against_the_plain_c_oracle():
     want_hat, want_lik = gc_c.forward_eval(y, scale, mu)
     assert torch.equal(y_hat.cpu(), want_hat)
     _assert_lik_close(lik.cpu(), want_lik)
+
+
+# ---- the production likelihood (DCAE_GC_LIK_FAST) -------------------------------------------------------------------
+def test_fast_likelihood_against_the_exact_value_1e7_samples():
+    """10^7 samples, scales log-uniform over [0.05, 300] (all 64 bins and the clamp), |y - mu| out to the floor:
+    PURE relative error <= 1e-5 against the fp64 value of the reference's formula for every element above the 1e-9
+    floor -- no absolute slack.  (The reference's own fp32 evaluation is only within ~1.5e-4 of that value at large
+    scales, where its two erfc terms cancel; tools/fit_erfc.py.)  Symbols / indexes / y_hat are the same bits in both
+    modes."""
+    fast, ref = _gc("fast"), _gc("reference")
+    g = torch.Generator().manual_seed(99)
+    n = 10_000_000
+    scale = torch.exp(torch.empty(n // 64, 64).uniform_(-3.0, 5.7, generator=g))
+    mu = 2 * torch.randn(n // 64, 64, generator=g)
+    # a third typical (sigma-sized residuals), a third far tails, a third tiny residuals
+    kind = torch.randint(0, 3, (n // 64, 64), generator=g)
+    resid = torch.randn(n // 64, 64, generator=g) * scale.clamp(min=0.11) * torch.tensor([1.0, 5.0, 0.2])[kind]
+    y = mu + resid
+    yc, mc, sc = y.cuda(), mu.cuda(), scale.cuda()
+    sym_f, idx_f, yh_f, lik_f = fast.fused(yc, sc, mc)
+    sym_r, idx_r, yh_r, lik_r = ref.fused(yc, sc, mc)
+    assert torch.equal(sym_f, sym_r) and torch.equal(idx_f, idx_r) and torch.equal(yh_f, yh_r)
+    exact = _exact_likelihood(yh_f, mc, sc)
+    above = exact >= 1e-9 * (1 + 1e-4)
+    rel_f = ((lik_f.double() - exact).abs() / exact)[above]
+    rel_r = ((lik_r.double() - exact).abs() / exact)[above]
+    print(f"\nfast likelihood vs exact over {int(above.sum())} elements above the floor: max rel {float(rel_f.max()):.2e} "
+          f"(p99.99 {float(rel_f.quantile(0.9999)):.2e}); "
+          f"reference-order fp32 formula: max rel {float(rel_r.max()):.2e}")
+    assert float(rel_f.max()) <= LIK_RTOL
+    below = exact < 1e-9 * (1 - 1e-4)
+    assert bool((lik_f[below] == 1e-9).all())                        # floored exactly like the reference
+    # and against the reference-order evaluation: 1e-5 relative + the reference's own rounding noise (2 erfc terms near 1)
+    _assert_lik_close(lik_f.cpu(), lik_r.cpu())
+
+
+def test_fast_likelihood_edges_noise_mode_and_nan():
+    fast = _gc("fast")
+    table = orc.get_scale_table()
+    # SURVEY 8c edge vectors: |v| = 0, 0.5, integers, 40 sigma; scales at / around the bound and every table entry
+    scales = torch.cat([torch.tensor([-1.0, 0.0, 0.11, 0.1099999, 0.1100001, 1e4, 3e38, float("inf")]), table,
+                        torch.nextafter(table, torch.tensor(0.0)), torch.nextafter(table, torch.tensor(1e9))])
+    resid = torch.tensor([0.0, 0.5, -0.5, 1.0, 2.0, 3.5, 7.0, 40.0])
+    S, R = torch.meshgrid(scales, resid, indexing="ij")
+    mu = torch.full_like(S, 0.25)
+    y = mu + R * torch.clamp(S, min=0.11).clamp(max=1e4)
+    sym, idx, y_hat, lik = fast.fused(y.cuda(), S.contiguous().cuda(), mu.cuda())
+    assert torch.equal(sym.cpu(), orc.quantize(y, "symbols", mu)) and torch.equal(idx.cpu(), orc.build_indexes(S.contiguous(), table))
+    exact = _exact_likelihood(y_hat.cpu(), mu, S).clamp(min=1e-9)
+    rel = (lik.cpu().double() - exact).abs() / exact
+    assert float(rel.max()) <= LIK_RTOL, float(rel.max())
+    # training mode (dcae.py:657 with self.training): continuous v = |y + noise - mu|
+    g = torch.Generator().manual_seed(5)
+    y, mu, scale = _direct_inputs((4, 64, 16, 16), seed=77)
+    noise = torch.empty_like(y).uniform_(-0.5, 0.5, generator=g)
+    out, lik = fast(y.cuda(), scale.cuda(), mu.cuda(), training=True, noise=noise.cuda())
+    exact = _exact_likelihood((y + noise), mu, scale).clamp(min=1e-9)
+    rel = (lik.cpu().double() - exact).abs() / exact
+    assert float(rel.max()) <= LIK_RTOL, float(rel.max())
+    # NaN in -> NaN out, floor applied like torch.max
+    y = torch.tensor([[1.0, float("nan"), 2.0, 3.0]])
+    mu = torch.tensor([[0.0, 0.0, float("nan"), 0.0]])
+    sc = torch.tensor([[1.0, 1.0, 1.0, float("nan")]])
+    _, _, _, lik = fast.fused(y.cuda(), sc.cuda(), mu.cuda())
+    assert torch.isnan(lik.cpu()).tolist() == [[False, True, True, True]]
+    y = torch.tensor([[0.0, 40.0, 400.0, -1e6, float("inf"), 3.0, 0.0, 0.0]])
+    sc = torch.tensor([[0.11, 1.0, 1.0, 0.5, 1.0, float("inf"), 0.0, 0.0]])
+    _, _, _, lik = fast.fused(y.cuda(), sc.cuda(), torch.zeros(1, 8).cuda())
+    assert lik.cpu().tolist()[0][1:6] == [pytest.approx(1e-9)] * 5 and float(lik[0, 0]) > 0.99999

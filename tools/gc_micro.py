@@ -8,6 +8,7 @@ from dcae_b200 import _lib
 lib = _lib.load()
 dev = torch.device("cuda:0")
 peaks = bench.load_peaks()
-for _ in range(3):
-    r = bench.gc_microbench(dev, lib, 1024, peaks)
-    print(f"gc micro: {r['ms']:.4f} ms  {r['achieved']:.0f} GB/s  frac {r['frac']:.3f}")
+for variant, lik in (("compress", "fast"), ("forward", "fast"), ("compress", "reference"), ("forward", "reference")):
+    for _ in range(2):
+        r = bench.gc_microbench(dev, lib, 1024, peaks, variant=variant, lik_math=lik)
+    print(f"gc micro [{variant:8s} {lik:9s}]: {r['ms']:.4f} ms  {r['achieved']:.0f} GB/s  frac {r['frac']:.3f}")
