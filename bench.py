@@ -262,7 +262,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--math", default="f16x3", choices=["f16x3", "tf32x3", "tf32", "fp32"])
+    ap.add_argument("--math", default="f16x3", choices=["f16x3", "f16", "tf32x3", "tf32", "fp32"])
     ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS), help="BASELINE.json config number (2 = the headline)")
     ap.add_argument("--mode", default=None, choices=["forward", "compress"], help="override the config's mode")
     ap.add_argument("--batch", type=int, default=0, help="images per GPU per step (default: the config's)")
@@ -399,14 +399,15 @@ def main():
     gemm_tflops = fam["gemm"]["work_per_step"] / (fam["gemm"]["ms_per_step"] * 1e-3) / 1e12 if fam["gemm"]["ms_per_step"] else 0.0
     tc_peak = peaks["tc_sustained"]
     roofline = {
-        "kernel": {"f16x3": "gemm_f16x3_kernel (+ split_f16_planes_kernel)", "tf32x3": "gemm_tcgen05_kernel / gemm_tcgen05_2cta_kernel",
+        "kernel": {"f16x3": "gemm_f16x3_kernel (+ split_f16_planes_kernel)", "f16": "gemm_f16x3_kernel, single pass (hi planes only)", "tf32x3": "gemm_tcgen05_kernel / gemm_tcgen05_2cta_kernel",
                    "tf32": "gemm_tcgen05_kernel", "fp32": "gemm_simt_kernel"}[args.math],
         "bound": "tensor", "achieved": gemm_tflops, "peak": tc_peak, "unit": "TFLOP/s", "frac": gemm_tflops / tc_peak,
         "traffic": ncu_traffic("prof_gemm_final_summary.csv") if args.math == "f16x3" else None,
         "traffic_note": "mean dram__bytes_read + write per launch over the launches of profiles/r01/prof_gemm_final_summary.csv (ncu --set full, same command); operands are L2-resident between layers, so DRAM traffic is below the algorithmic operand bytes",
         "note": (f"achieved = algorithmic 2*T*N*K flop of all {fam['gemm']['launches_per_step']} dense-layer launches of a step / "
                  f"their summed CUDA-event time; peak = {peaks['src']} sustained dense bf16 (kernel timed inside a long step). "
-                 + {"f16x3": "Arithmetic is 3 fp16 MMAs (hi/lo operand planes, fp32 accumulate) per algorithmic MAC: ceiling = 1/3 of this peak; the fp16 plane split of each operand is included in the timed launches.",
+                 + {"f16": "Reduced-precision fast mode: one fp16 MMA per algorithmic MAC (hi planes only).",
+                    "f16x3": "Arithmetic is 3 fp16 MMAs (hi/lo operand planes, fp32 accumulate) per algorithmic MAC: ceiling = 1/3 of this peak; the fp16 plane split of each operand is included in the timed launches.",
                     "tf32x3": "Arithmetic is 3 TF32 MMAs per algorithmic MAC at half the bf16 rate: ceiling = 1/6 of this peak.",
                     "tf32": "Arithmetic is TF32 (half the bf16 rate): ceiling = 1/2 of this peak.",
                     "fp32": "FFMA reference mode: tensor cores unused."}[args.math]),
@@ -457,7 +458,8 @@ def main():
             "metric": f"entropy-model images/sec @{cfg['tag']}", "value": imgs / (ms_step * 1e-3), "unit": "images/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": {"f16x3": "f32 (fp16 hi+lo planes = 22-bit operands, 3-pass tcgen05, fp32 accumulate)",
+            "dtype": {"f16": "f16 operands (hi planes only), fp32 accumulate: reduced-precision fast mode, NOT the parity mode",
+                      "f16x3": "f32 (fp16 hi+lo planes = 22-bit operands, 3-pass tcgen05, fp32 accumulate)",
                       "tf32x3": "f32 (3xTF32 error-compensated tcgen05, fp32 accumulate)", "tf32": "tf32", "fp32": "f32"}[args.math],
             "data": "synthetic",
             "config": {"workload": cfg["workload"], "config": args.config, "mode": cfg["mode"],

@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdcae_b200.so")
 
 OK = 0
-MATH = {"fp32": 0, "tf32x3": 1, "tf32": 2, "f16x3": 3}
+MATH = {"fp32": 0, "tf32x3": 1, "tf32": 2, "f16x3": 3, "f16": 4}
 GC_EVAL, GC_NOISE, GC_DECODE = 0, 1, 2
 GC_LIK = {"fast": 0, "reference": 1}
 OPT_LIK_MATH, OPT_WANT_SYMBOLS = 0, 1

@@ -126,7 +126,7 @@ static int check_gemm_args(const dcae_operand* a, const dcae_weight* w, const dc
 
 extern "C" int dcae_op_gemm(const dcae_operand* a, const dcae_weight* w, const dcae_epilogue* e, int math, void* stream) {
   DCAE_TRY(check_gemm_args(a, w, e));
-  DCAE_REQUIRE(math == DCAE_MATH_F16X3 || !e->out16_act.hi, "dcae_op_gemm: out16_act is a DCAE_MATH_F16X3 feature");
+  DCAE_REQUIRE(math == DCAE_MATH_F16X3 || math == DCAE_MATH_F16 || !e->out16_act.hi, "dcae_op_gemm: out16_act is a DCAE_MATH_F16X3 / F16 feature");
   ProfileScope prof(DCAE_PROF_GEMM, 2.0 * a->B * a->h * a->w * (double)w->N * (double)w->K, stream);
   switch (math) {
     case DCAE_MATH_FP32_SIMT:
@@ -138,7 +138,8 @@ extern "C" int dcae_op_gemm(const dcae_operand* a, const dcae_weight* w, const d
     case DCAE_MATH_TF32:
       DCAE_REQUIRE(a->base, "dcae_op_gemm(tf32): needs the fp32 operand");
       return gemm_tcgen05(a, w, e, 1, (cudaStream_t)stream);
-    case DCAE_MATH_F16X3: return gemm_tcgen05_f16x3(a, w, e, (cudaStream_t)stream);
+    case DCAE_MATH_F16X3: return gemm_tcgen05_f16x3(a, w, e, 3, (cudaStream_t)stream);
+    case DCAE_MATH_F16: return gemm_tcgen05_f16x3(a, w, e, 1, (cudaStream_t)stream);
   }
   set_error("dcae_op_gemm: unknown math mode %d", math);
   return DCAE_E_INVALID;
@@ -147,7 +148,7 @@ extern "C" int dcae_op_gemm(const dcae_operand* a, const dcae_weight* w, const d
 extern "C" int dcae_op_dict_attention(const float* q, int64_t q_ld, const dcae_planes* q16, const dcae_dict_kv* kv, int64_t T,
                                       float* out, int64_t out_ld, const dcae_planes* out16, int math, void* stream) {
   const dcae_planes o16 = planes_or_null(out16);
-  const bool f16 = math == DCAE_MATH_F16X3;
+  const bool f16 = math == DCAE_MATH_F16X3 || math == DCAE_MATH_F16;
   DCAE_REQUIRE((f16 || q) && kv && kv->Kh && kv->Vh && kv->head_scale && (out || o16.hi) && planes_ok(out16) && planes_ok(q16),
                "dcae_op_dict_attention: null pointer / bad planes");
   DCAE_REQUIRE(math != DCAE_MATH_FP32_SIMT || (out && !o16.hi), "dcae_op_dict_attention(fp32): fp16 planes are a tcgen05-path feature");
@@ -159,7 +160,9 @@ extern "C" int dcae_op_dict_attention(const float* q, int64_t q_ld, const dcae_p
   switch (math) {
     case DCAE_MATH_FP32_SIMT:
       return dict_attention_simt(q, q_ld, kv->Kh, kv->Vh, kv->head_scale, T, out, out_ld, (cudaStream_t)stream);
-    case DCAE_MATH_F16X3: return dict_attention_tcgen05_f16(q16, kv, T, out, out_ld, o16, (cudaStream_t)stream);
+    case DCAE_MATH_F16X3:
+    case DCAE_MATH_F16:   // the attention core stays 3-pass in the fast mode too (3 % of the step)
+      return dict_attention_tcgen05_f16(q16, kv, T, out, out_ld, o16, (cudaStream_t)stream);
     case DCAE_MATH_TF32X3: return dict_attention_tcgen05(q, q_ld, kv, T, out, out_ld, o16, 3, (cudaStream_t)stream);
     case DCAE_MATH_TF32: return dict_attention_tcgen05(q, q_ld, kv, T, out, out_ld, o16, 1, (cudaStream_t)stream);
   }
@@ -281,7 +284,7 @@ extern "C" int dcae_slice_loop_create(dcae_slice_loop** out, int32_t B, int32_t 
                                       size_t workspace_bytes, int math) {
   DCAE_REQUIRE(out && weights && workspace, "dcae_slice_loop_create: null argument");
   DCAE_REQUIRE(B > 0 && h > 0 && w > 0 && (int64_t)B * h * w < (1ll << 31) / 4, "dcae_slice_loop_create: bad shape B=%d h=%d w=%d", B, h, w);
-  DCAE_REQUIRE(math >= DCAE_MATH_FP32_SIMT && math <= DCAE_MATH_F16X3, "dcae_slice_loop_create: bad math mode %d", math);
+  DCAE_REQUIRE(math >= DCAE_MATH_FP32_SIMT && math <= DCAE_MATH_F16, "dcae_slice_loop_create: bad math mode %d", math);
   DCAE_REQUIRE(scale_table == nullptr || (n_table >= 2 && n_table <= 256), "dcae_slice_loop_create: scale table of %d entries (2..256 supported: indexes travel as uint8)", n_table);
   DCAE_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, "dcae_slice_loop_create: workspace must be 256-byte aligned");
   DCAE_TRY(dcae_device_check());
@@ -289,7 +292,7 @@ extern "C" int dcae_slice_loop_create(dcae_slice_loop** out, int32_t B, int32_t 
   DCAE_REQUIRE(p != nullptr, "dcae_slice_loop_create: out of host memory");
   memset(static_cast<void*>(p), 0, sizeof(*p));
   p->B = B; p->h = h; p->w = w; p->math = math;
-  p->pm = math == DCAE_MATH_F16X3;
+  p->pm = math == DCAE_MATH_F16X3 || math == DCAE_MATH_F16;
   p->HW = (int64_t)h * w;
   p->T = (int64_t)B * h * w;
   const size_t need = carve(p, nullptr);

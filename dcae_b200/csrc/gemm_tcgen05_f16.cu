@@ -53,6 +53,7 @@ struct F16Params {
   int has_o32, has_o16, has_o16a;
   int pdl;                   // launched with programmatic stream serialization: see griddepcontrol below
   int fuse_b;                // single CTA, BN <= 128: one N = 2 BN MMA covers a_hi x [b_hi; b_lo], see the MMA issuer
+  int passes;                // 3 = hi/lo error-compensated (fp32-level accuracy); 1 = DCAE_MATH_F16: a_hi x b_hi only, lo planes never loaded
   uint32_t stage_bytes, b_bytes;
   unsigned long long* dbg;   // DCAE_F16_DBG=1: per-CTA role counters (16 u64 each), see dump in the host wrapper
 };
@@ -321,8 +322,8 @@ __device__ __forceinline__ void gemm_f16x3_body(const CUtensorMap& map_ah, const
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   }
 
-  // per-stage smem: [A_hi | A_lo | B_hi | B_lo]; the two epilogue staging buffers follow the stages
-  const uint32_t off_al = A16_BYTES, off_bh = 2 * A16_BYTES, off_bl = off_bh + p.b_bytes;
+  // per-stage smem: [A_hi | A_lo | B_hi | B_lo] (single pass: [A_hi | B_hi]); the two epilogue staging buffers follow the stages
+  const uint32_t off_al = A16_BYTES, off_bh = (p.passes == 3 ? 2 : 1) * A16_BYTES, off_bl = off_bh + p.b_bytes;
   const uint32_t stg_base = smem0 + (uint32_t)p.stages * p.stage_bytes;
   const int n_chunks = (p.KB + p.chunk_kb - 1) / p.chunk_kb;
 
@@ -356,18 +357,20 @@ __device__ __forceinline__ void gemm_f16x3_body(const CUtensorMap& map_ah, const
           if (p.taps == 9) { dy = tap / 3 - 1; dx = tap % 3 - 1; }
           const int nrow = n0 + (int)rank * (p.BN >> 1);
           if (elect_one()) {
+            const bool lo_too = p.passes == 3;
+            const uint32_t bytes = (lo_too ? 2u : 1u) * (A16_BYTES + p.b_bytes);
             if (PAIR) {
-              if (leader) mbar_expect_tx(fb, 2 * (2 * A16_BYTES + 2 * p.b_bytes));      // bytes landing in BOTH CTAs
+              if (leader) mbar_expect_tx(fb, 2 * bytes);      // bytes landing in BOTH CTAs
               tma_load_4d_2sm(sbase, &map_ah, fb, c, x0 + dx, y0 + dy, b);
-              tma_load_4d_2sm(sbase + off_al, &map_al, fb, c, x0 + dx, y0 + dy, b);
+              if (lo_too) tma_load_4d_2sm(sbase + off_al, &map_al, fb, c, x0 + dx, y0 + dy, b);
               tma_load_2d_2sm(sbase + off_bh, &map_bh, fb, kb * BK16, nrow);
-              tma_load_2d_2sm(sbase + off_bl, &map_bl, fb, kb * BK16, nrow);
+              if (lo_too) tma_load_2d_2sm(sbase + off_bl, &map_bl, fb, kb * BK16, nrow);
             } else {
-              mbar_expect_tx(fb, 2 * A16_BYTES + 2 * p.b_bytes);
+              mbar_expect_tx(fb, bytes);
               tma_load_4d(sbase, &map_ah, fb, c, x0 + dx, y0 + dy, b);
-              tma_load_4d(sbase + off_al, &map_al, fb, c, x0 + dx, y0 + dy, b);
+              if (lo_too) tma_load_4d(sbase + off_al, &map_al, fb, c, x0 + dx, y0 + dy, b);
               tma_load_2d(sbase + off_bh, &map_bh, fb, kb * BK16, n0);
-              tma_load_2d(sbase + off_bl, &map_bl, fb, kb * BK16, n0);
+              if (lo_too) tma_load_2d(sbase + off_bl, &map_bl, fb, kb * BK16, n0);
             }
           }
           __syncwarp();
@@ -408,7 +411,10 @@ __device__ __forceinline__ void gemm_f16x3_body(const CUtensorMap& map_ah, const
                 const uint32_t koff = k * UMMA_K16 * 2;
                 const uint64_t a_hi = make_smem_desc(sbase + koff), a_lo = make_smem_desc(sbase + off_al + koff);
                 const uint64_t b_hi = make_smem_desc(sbase + off_bh + koff), b_lo = make_smem_desc(sbase + off_bl + koff);
-                if (PAIR) {
+                if (p.passes == 1) {
+                  if (PAIR) mma_f16_2sm(tmem_acc, a_hi, b_hi, idesc, first | (uint32_t)(k != 0));
+                  else mma_f16(tmem_acc, a_hi, b_hi, idesc, first | (uint32_t)(k != 0));
+                } else if (PAIR) {
                   mma_f16_2sm(tmem_acc, a_lo, b_hi, idesc, first | (uint32_t)(k != 0));
                   mma_f16_2sm(tmem_acc, a_hi, b_lo, idesc, 1);
                   mma_f16_2sm(tmem_acc, a_hi, b_hi, idesc, 1);
@@ -614,7 +620,7 @@ inline int pad64(int v) { return (v + 63) / 64 * 64; }
 
 }  // namespace
 
-int gemm_tcgen05_f16x3(const dcae_operand* a, const dcae_weight* w, const dcae_epilogue* e, cudaStream_t s) {
+int gemm_tcgen05_f16x3(const dcae_operand* a, const dcae_weight* w, const dcae_epilogue* e, int passes, cudaStream_t s) {
   const int kc = a->k0 + a->k1, Kp = pad64(kc);
   const int64_t T = (int64_t)a->B * a->h * a->w;
   DCAE_REQUIRE(w->w16_hi && w->w16_lo && w->K16 == a->taps * Kp && w->descale > 0.f,
@@ -658,7 +664,10 @@ int gemm_tcgen05_f16x3(const dcae_operand* a, const dcae_weight* w, const dcae_e
   // A/B sweeps (profiles/r01/gemm_f16_pair_ab.jsonl, layer_times_bn_pair_sweep3.log): pairs win where the mainloop is
   // long or wide (cc1, proj, fc1, the K = 2 016 conv layers); everything else runs single-CTA with BN <= 128 so that
   // the fused [b_hi; b_lo] MMA applies (N = 320 -> 128 + 128 + 64 ragged beats 2 x 160 by 20 %, N = 224 likewise).
-  const bool pair_heur = (int64_t)a->taps * Kp >= 2048 || w->N >= 2048;
+  // single pass: the mainloop moves a third of the flops per operand byte less... per k-block a 128 x 128 tile is 256 tensor
+  // cycles against 32 KB of operands (128 B/clk, twice what the L2 -> SM path feeds), so every layer that can takes
+  // M = 256 pairs with the widest N tile (each CTA loads half of the weight rows: 62 B/clk at BN = 256)
+  const bool pair_heur = passes == 1 ? w->N >= 128 : ((int64_t)a->taps * Kp >= 2048 || w->N >= 2048);
   // The arithmetic (fused or three-MMA accumulation order) follows want_pair, a function of the layer shape only, so
   // that a result never depends on the batch size (a 1-tile problem cannot pair but keeps the pair path's order).
   const bool want_pair = pair_mode == 1 || (pair_mode == -1 && pair_heur);
@@ -667,6 +676,14 @@ int gemm_tcgen05_f16x3(const dcae_operand* a, const dcae_weight* w, const dcae_e
   if (const char* env = getenv("DCAE_TC_BN")) {        // tuning override; BN need not divide N (ragged last tile)
     const int bn = atoi(env);
     if (bn >= 32 && bn <= 256 && bn % 32 == 0) p.BN = bn;
+  }
+  p.passes = passes;
+  if (p.BN == 0 && passes == 1 && want_pair) {     // least padded work, then the widest tile (N = 640 -> 4 x 160, 672 -> 3 x 224)
+    int best = 1 << 30;
+    for (int bn = 256; bn >= 128; bn -= 32) {
+      const int padded = (w->N + bn - 1) / bn * bn;
+      if (padded < best) { best = padded; p.BN = bn; }
+    }
   }
   if (p.BN == 0 && !want_pair && fuse_mode != 0) p.BN = w->N >= 128 ? 128 : w->N;
   if (p.BN == 0) {
@@ -678,18 +695,18 @@ int gemm_tcgen05_f16x3(const dcae_operand* a, const dcae_weight* w, const dcae_e
   }
   DCAE_REQUIRE(p.BN > 0 && p.BN % 32 == 0, "gemm(f16x3): N=%d must be a multiple of 32", w->N);
   p.n_tiles_n = (w->N + p.BN - 1) / p.BN;      // a ragged last tile reads zero-filled weight rows and stores clipped
-  p.fuse_b = (fuse_mode != 0 && !want_pair && p.BN <= 128) ? 1 : 0;
+  p.fuse_b = (fuse_mode != 0 && !want_pair && p.BN <= 128 && passes == 3) ? 1 : 0;
   const int acc_cols = 2 * (p.fuse_b ? 2 * p.BN : p.BN);          // two chunk buffers
   p.tmem_cols = acc_cols <= 64 ? 64 : acc_cols <= 128 ? 128 : acc_cols <= 256 ? 256 : 512;
   p.total_tiles = p.n_tiles_n * (pair ? (m_tiles + 1) / 2 : m_tiles);
-  p.chunk_kb = CHUNK_MMAS / (p.fuse_b ? 8 : 12);      // accumulation chain per column: 2 (fused) or 3 MMAs per K = 16 step, 4 steps per k-block
+  p.chunk_kb = CHUNK_MMAS / (passes == 1 ? 4 : p.fuse_b ? 8 : 12);      // accumulation chain per column: 1, 2 (fused) or 3 MMAs per K = 16 step, 4 steps per k-block
   if (const char* env = getenv("DCAE_TC_CHUNK")) { const int v = atoi(env); if (v >= 1) p.chunk_kb = v; }
   p.descale = w->descale;
   p.dbg_nostore = getenv("DCAE_TC_NOSTORE") != nullptr;
   static const bool dbg_on = getenv("DCAE_F16_DBG") != nullptr;
   p.dbg = nullptr;
   p.b_bytes = (uint32_t)(pair ? p.BN / 2 : p.BN) * BK16 * 2;     // a pair's CTA holds half of the weight rows
-  p.stage_bytes = 2 * A16_BYTES + 2 * p.b_bytes;
+  p.stage_bytes = (passes == 3 ? 2 : 1) * (A16_BYTES + p.b_bytes);
   p.stages = (int)((SMEM_LIMIT - 2048 - 2 * STG_BYTES) / p.stage_bytes);
   if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
   if (const char* env = getenv("DCAE_TC_STAGES")) { const int v = atoi(env); if (v >= 1 && v < p.stages) p.stages = v; }

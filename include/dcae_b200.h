@@ -45,8 +45,11 @@ enum {
   DCAE_MATH_FP32_SIMT = 0, /* FFMA reference path: fp32 in, fp32 accumulate */
   DCAE_MATH_TF32X3 = 1,    /* tcgen05 kind::tf32, error-compensated 3-pass split: fp32-level accuracy */
   DCAE_MATH_TF32 = 2,      /* tcgen05 kind::tf32 single pass (like torch allow_tf32=True) */
-  DCAE_MATH_F16X3 = 3      /* tcgen05 kind::f16 on fp16 hi/lo operand planes, 3-pass: fp32-level accuracy (22-bit
+  DCAE_MATH_F16X3 = 3,     /* tcgen05 kind::f16 on fp16 hi/lo operand planes, 3-pass: fp32-level accuracy (22-bit
                               operands) at twice the TF32 MMA rate and half the operand bytes per flop */
+  DCAE_MATH_F16 = 4        /* the reduced-precision fast mode: same planes data flow, the dense layers multiply the hi
+                              planes only (11-bit operands, fp32 accumulate), a third of the tensor work.  NOT a parity
+                              mode: tolerance and symbol / index mismatch rates are measured and stated */
 };
 
 /* fp16 hi/lo planes of a token-major matrix: value = float(hi[t, c]) + float(lo[t, c]) (22 significant bits).
