@@ -5,6 +5,8 @@ Public surface (mirrors the reference's operator interface for this path only):
   HostPipeline          -- pinned-host-in / pinned-host-out streaming front end (overlapped copies)
   GaussianConditional   -- compressai-compatible quantise / likelihood / build_indexes (kernel 3)
   accelerate, DictCrossAttention, ConvStack -- module-level drop-ins for a reference DCAE instance (dcae_b200/modules.py)
+  EntropyModel, SliceLoopFunction -- the training form (autograd: kernels forward, torch-graph recompute backward)
+  ans.BufferedRansEncoder / RansDecoder -- the native range coder with compressai.ans' interface
   init_entropy_params   -- deterministic random-init weights with the reference's state-dict keys
 """
 from .params import init_entropy_params, entropy_param_shapes  # noqa: F401
@@ -21,6 +23,9 @@ def __getattr__(name):
     if name in ("accelerate", "DictCrossAttention", "ConvStack"):
         from . import modules
         return getattr(modules, name)
+    if name in ("EntropyModel", "SliceLoopFunction", "GaussianLikelihoodFunction", "rate_distortion_loss"):
+        from . import training
+        return getattr(training, name)
     if name == "GaussianConditional":
         from .gaussian_conditional import GaussianConditional
         return GaussianConditional

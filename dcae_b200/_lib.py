@@ -44,6 +44,16 @@ class GcArgs(C.Structure):
     ]
 
 
+class GcBwdArgs(C.Structure):
+    _fields_ = [
+        ("y", c_f32p), ("y_ld", C.c_int64), ("mu", c_f32p), ("mu_ld", C.c_int64), ("scale", c_f32p), ("scale_ld", C.c_int64),
+        ("noise", c_f32p), ("noise_ld", C.c_int64), ("grad_lik", c_f32p), ("grad_lik_ld", C.c_int64),
+        ("scale_bound", C.c_float), ("lik_bound", C.c_float), ("mode", C.c_int32), ("rows", C.c_int64), ("inner", C.c_int64),
+        ("grad_y", c_f32p), ("grad_y_ld", C.c_int64), ("grad_mu", c_f32p), ("grad_mu_ld", C.c_int64),
+        ("grad_scale", c_f32p), ("grad_scale_ld", C.c_int64),
+    ]
+
+
 class Operand(C.Structure):
     _fields_ = [("base", c_f32p), ("ld", C.c_int64), ("col0", C.c_int32), ("k0", C.c_int32),
                 ("col1", C.c_int32), ("k1", C.c_int32), ("taps", C.c_int32),
@@ -112,6 +122,7 @@ SIGNATURES = {
     "dcae_profile_stop": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_I64)]),
     "dcae_profile_dump": (C.c_int, [C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_I64)]),
     "dcae_gc_fused": (C.c_int, [C.POINTER(GcArgs), _P]),
+    "dcae_gc_backward": (C.c_int, [C.POINTER(GcBwdArgs), _P]),
     "dcae_gc_num_partials": (_I64, [_I64, _I64]),
     "dcae_reduce_partials": (C.c_int, [_P, _I64, _P, _P]),
     "dcae_op_gemm": (C.c_int, [C.POINTER(Operand), C.POINTER(Weight), C.POINTER(Epilogue), C.c_int, _P]),

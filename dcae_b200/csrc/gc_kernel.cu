@@ -371,6 +371,48 @@ __global__ void __launch_bounds__(GC_THREADS) gc_eval_hot_kernel(const GcHotPara
   }
 }
 
+// ---- kernel 3 backward (training config #4; train.py:165-179 differentiates the rate term through this) ------------
+// lik = max(Phi(u) - Phi(l), lik_bound), u = (1/2 - v) / s, l = (-1/2 - v) / s, v = |out - mu|, s = max(scale, scale_bound)
+// (dcae.py:839-857).  With g = dL/dlik and phi the standard normal density:
+//   g' = g [lik_raw >= lik_bound or g < 0]                       (compressai LowerBound: gradient passes towards the bound)
+//   dL/dv = -g' (phi(u) - phi(l)) / s,   dL/ds = -g' (u phi(u) - l phi(l)) / s,   dL/dscale = dL/ds [scale >= scale_bound or dL/ds < 0]
+//   NOISE mode (out = y + noise):  dL/dy = dL/dv sign(out - mu),  dL/dmu = -dL/dy
+//   EVAL mode  (out = round(y - mu) + mu: no gradient through round, and d out / d mu = 1 cancels d|out - mu| / d mu): 0, 0
+__global__ void __launch_bounds__(GC_THREADS) gc_backward_kernel(const dcae_gc_bwd_args a, int64_t groups, uint32_t inner4) {
+  for (int64_t g = (int64_t)blockIdx.x * GC_THREADS + threadIdx.x; g < groups; g += (int64_t)gridDim.x * GC_THREADS) {
+    const int64_t row = g / inner4, col = (g - row * inner4) * 4;
+    const float4 y4 = __ldg(reinterpret_cast<const float4*>(a.y + row * a.y_ld + col));
+    const float4 m4 = __ldg(reinterpret_cast<const float4*>(a.mu + row * a.mu_ld + col));
+    const float4 s4 = __ldg(reinterpret_cast<const float4*>(a.scale + row * a.scale_ld + col));
+    const float4 g4 = __ldg(reinterpret_cast<const float4*>(a.grad_lik + row * a.grad_lik_ld + col));
+    float4 n4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (a.mode == DCAE_GC_NOISE) n4 = __ldg(reinterpret_cast<const float4*>(a.noise + row * a.noise_ld + col));
+    const float y[4] = {y4.x, y4.y, y4.z, y4.w}, mu[4] = {m4.x, m4.y, m4.z, m4.w}, sc[4] = {s4.x, s4.y, s4.z, s4.w};
+    const float gl[4] = {g4.x, g4.y, g4.z, g4.w}, nz[4] = {n4.x, n4.y, n4.z, n4.w};
+    float gy[4], gm[4], gs[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float out = a.mode == DCAE_GC_NOISE ? y[k] + nz[k] : rintf(y[k] - mu[k]) + mu[k];
+      const float d = out - mu[k];
+      const float v = fabsf(d);
+      const float s = nan_max(sc[k], a.scale_bound);
+      const float u = (0.5f - v) / s, l = (-0.5f - v) / s;
+      const float raw = 0.5f * erfcf(-0.70710678118654752440f * u) - 0.5f * erfcf(-0.70710678118654752440f * l);
+      const float gp = (raw >= a.lik_bound || gl[k] < 0.f) ? gl[k] : 0.f;
+      const float pu = 0.3989422804014327f * expf(-0.5f * u * u), pl = 0.3989422804014327f * expf(-0.5f * l * l);
+      const float dv = -gp * (pu - pl) / s;
+      const float ds = -gp * (u * pu - l * pl) / s;
+      gs[k] = (sc[k] >= a.scale_bound || ds < 0.f) ? ds : 0.f;
+      const float sgn = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
+      gy[k] = a.mode == DCAE_GC_NOISE ? dv * sgn : 0.f;
+      gm[k] = -gy[k];
+    }
+    if (a.grad_y) *reinterpret_cast<float4*>(a.grad_y + row * a.grad_y_ld + col) = make_float4(gy[0], gy[1], gy[2], gy[3]);
+    if (a.grad_mu) *reinterpret_cast<float4*>(a.grad_mu + row * a.grad_mu_ld + col) = make_float4(gm[0], gm[1], gm[2], gm[3]);
+    if (a.grad_scale) *reinterpret_cast<float4*>(a.grad_scale + row * a.grad_scale_ld + col) = make_float4(gs[0], gs[1], gs[2], gs[3]);
+  }
+}
+
 __global__ void reduce_partials_kernel(const float* __restrict__ p, int64_t n, float* __restrict__ out) {
   // one block, 256 threads; each thread sums a strided subsequence in index order, then a fixed tree
   __shared__ float sh[256];
@@ -526,6 +568,24 @@ extern "C" int dcae_reduce_partials(const float* partials, int64_t n, float* out
   using namespace dcae;
   DCAE_REQUIRE(partials != nullptr && out != nullptr && n >= 0, "dcae_reduce_partials: bad arguments");
   reduce_partials_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(partials, n, out);
+  DCAE_LAUNCH_CHECK();
+  return DCAE_OK;
+}
+
+extern "C" int dcae_gc_backward(const dcae_gc_bwd_args* a, void* stream) {
+  using namespace dcae;
+  DCAE_REQUIRE(a && a->y && a->mu && a->scale && a->grad_lik, "dcae_gc_backward: null input");
+  DCAE_REQUIRE(a->mode == DCAE_GC_EVAL || (a->mode == DCAE_GC_NOISE && a->noise), "dcae_gc_backward: mode must be EVAL or NOISE (with noise)");
+  DCAE_REQUIRE(a->rows >= 0 && a->inner >= 0 && a->inner % 4 == 0, "dcae_gc_backward: inner must be a multiple of 4");
+#define GCB_CHECK(ptr, ld) DCAE_REQUIRE((ptr) == nullptr || (aligned16(ptr) && (ld) % 4 == 0), "dcae_gc_backward: " #ptr " must be 16-byte aligned with ld %% 4 == 0")
+  GCB_CHECK(a->y, a->y_ld); GCB_CHECK(a->mu, a->mu_ld); GCB_CHECK(a->scale, a->scale_ld); GCB_CHECK(a->noise, a->noise_ld);
+  GCB_CHECK(a->grad_lik, a->grad_lik_ld); GCB_CHECK(a->grad_y, a->grad_y_ld); GCB_CHECK(a->grad_mu, a->grad_mu_ld); GCB_CHECK(a->grad_scale, a->grad_scale_ld);
+#undef GCB_CHECK
+  if (a->rows == 0 || a->inner == 0) return DCAE_OK;
+  const int64_t groups = a->rows * (a->inner / 4);
+  DCAE_REQUIRE(a->inner / 4 < (1ll << 32), "dcae_gc_backward: row too long");
+  ProfileScope prof(DCAE_PROF_GC, 28.0 * (double)a->rows * (double)a->inner, stream);
+  gc_backward_kernel<<<(unsigned)gc_blocks(a->rows, a->inner, 8), GC_THREADS, 0, (cudaStream_t)stream>>>(*a, groups, (uint32_t)(a->inner / 4));
   DCAE_LAUNCH_CHECK();
   return DCAE_OK;
 }

@@ -203,12 +203,19 @@ class GaussianConditional(nn.Module):
         return self._run(_lib.GC_EVAL, None, zeros, scales=scales, want=("idx",))["idx"]
 
     def forward(self, inputs, scales, means=None, training=None, noise: Optional[torch.Tensor] = None):
-        """-> (outputs, likelihood) like compressai (dcae.py:657); eval: outputs = round(x - mu) + mu."""
+        """-> (outputs, likelihood) like compressai (dcae.py:657); eval: outputs = round(x - mu) + mu.  Under autograd
+        the likelihood is a `training.GaussianLikelihoodFunction` node (kernel 3 forward, dcae_gc_backward backward)."""
         if training is None:
             training = self.training
+        if training and noise is None:
+            noise = torch.empty_like(inputs).uniform_(-0.5, 0.5)
+        if torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in (inputs, scales, means)):
+            from .training import gaussian_likelihood
+            mu = means if means is not None else torch.zeros_like(inputs)
+            lik = gaussian_likelihood(inputs, scales, mu, noise if training else None, self._bounds[0], self._bounds[1], self.likelihood_math)
+            outputs = inputs + noise if training else (torch.round(inputs - mu) + mu)      # torch ops: differentiable like compressai's
+            return outputs, lik
         if training:
-            if noise is None:
-                noise = torch.empty_like(inputs).uniform_(-0.5, 0.5)
             o = self._run(_lib.GC_NOISE, inputs, means, scales=scales, noise=noise, want=("lik",))
             return inputs + noise, o["lik"]
         o = self._run(_lib.GC_EVAL, inputs, means, scales=scales, want=("y_hat", "lik"))

@@ -28,11 +28,12 @@ HOT_PREFIXES = ("dt", "dt_cross_attention", "cc_mean_transforms", "cc_scale_tran
 
 
 def _no_grad_path(*tensors) -> None:
-    """The module-level drop-ins are inference kernels: refuse to run silently inside an autograd graph (the training
-    path is `dcae_b200.training.SliceLoopFunction`, which has a backward)."""
+    """The stand-alone module classes below are inference kernels: refuse to run silently inside an autograd graph
+    (`accelerate(net)` on a model with parameters differentiates through `dcae_b200.training.ModuleFunction`; the
+    whole-loop training path is `dcae_b200.training.SliceLoopFunction` / `EntropyModel`)."""
     if torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in tensors):
-        raise _lib.DcaeError("dcae_b200 module drop-ins are forward-only: an input requires grad.  Wrap the call in "
-                             "torch.no_grad() or use dcae_b200.training.SliceLoopFunction for the training step")
+        raise _lib.DcaeError("this dcae_b200 module is forward-only and an input requires grad: wrap the call in "
+                             "torch.no_grad(), or use accelerate(net) / dcae_b200.training for the training step")
 
 
 class _LoopModule(torch.nn.Module):
@@ -130,17 +131,42 @@ def accelerate(net: torch.nn.Module, device="cuda:0", math: str = "f16x3", state
         handle._orig_forward[mod] = True
         mod.forward = fn                      # instance attribute: nn.Module.__call__ picks it up before the class method
 
+    def needs_grad(prefix, *ins):
+        """Under autograd with something to differentiate: the call becomes a `training.ModuleFunction` node."""
+        if not torch.is_grad_enabled():
+            return None
+        sub = {k[len(prefix):]: v for k, v in tracked.items() if k.startswith(prefix)}
+        if any(isinstance(t, torch.Tensor) and t.requires_grad for t in ins) or any(v.requires_grad for v in sub.values()):
+            if not sub:
+                _no_grad_path(*ins)          # built from a detached state dict: nothing to differentiate into
+            return sub
+        return None
+
+    from . import torch_graph
+
     for i in range(NUM_SLICES):
         def dca(x, dt=None, i=i):
-            _no_grad_path(x, dt)
             handle.sync()
             _check_dt(loop, dt, strict_dt)
-            return loop.module_dca(i, x)
+            sub = needs_grad(f"dt_cross_attention.{i}.", x, dt)
+            if sub is None:
+                return loop.module_dca(i, x)
+            from .training import ModuleFunction
+            if dt is None:
+                dt = tracked["dt"].unsqueeze(0)
+            # dt arrives as self.dt.repeat([b, 1, 1]) (dcae.py:625): K / V are batch invariant, image 0's copy carries the gradient
+            graph = lambda ins, P: torch_graph.dictionary_cross_attention(ins[0], ins[1].reshape(-1, DICT_NUM, DICT_DIM)[0], P)   # noqa: E731
+            return ModuleFunction.apply(lambda xx, dd: loop.module_dca(i, xx), graph, list(sub), 2, x, dt, *sub.values())
 
         def conv(x, i=i, which=0):
-            _no_grad_path(x)
             handle.sync()
-            return loop.module_conv(i, which, x)
+            name = ("cc_mean_transforms", "cc_scale_transforms", "lrp_transforms")[which]
+            sub = needs_grad(f"{name}.{i}.", x)
+            if sub is None:
+                return loop.module_conv(i, which, x)
+            from .training import ModuleFunction
+            graph = lambda ins, P: torch_graph.conv_stack(ins[0], P)      # noqa: E731
+            return ModuleFunction.apply(lambda xx: loop.module_conv(i, which, xx), graph, list(sub), 1, x, *sub.values())
 
         patch(net.dt_cross_attention[i], dca)
         for which, name in enumerate(("cc_mean_transforms", "cc_scale_transforms", "lrp_transforms")):

@@ -112,6 +112,25 @@ typedef struct {
 } dcae_gc_args;
 
 int dcae_gc_fused(const dcae_gc_args* a, void* stream);
+/* Backward of the likelihood for the training step (train.py:165-179 differentiates the rate term of :82-85 through
+ * compressai's GaussianConditional.forward, called at dcae.py:657 with self.training).  Given dL/dlik it returns
+ * dL/dy, dL/dmu (NOISE mode; zero in EVAL mode, where round() blocks them) and dL/dscale, with the LowerBound rule of
+ * compressai for both bounds: the gradient passes where the input is above the bound or the gradient pushes it up.
+ * Same row-strided tensor convention as dcae_gc_fused; any output may be NULL. */
+typedef struct {
+  const float* y;        int64_t y_ld;
+  const float* mu;       int64_t mu_ld;
+  const float* scale;    int64_t scale_ld;
+  const float* noise;    int64_t noise_ld;       /* NOISE mode */
+  const float* grad_lik; int64_t grad_lik_ld;
+  float scale_bound; float lik_bound;
+  int32_t mode;                                  /* DCAE_GC_EVAL or DCAE_GC_NOISE */
+  int64_t rows; int64_t inner;
+  float* grad_y;     int64_t grad_y_ld;
+  float* grad_mu;    int64_t grad_mu_ld;
+  float* grad_scale; int64_t grad_scale_ld;
+} dcae_gc_bwd_args;
+int dcae_gc_backward(const dcae_gc_bwd_args* a, void* stream);
 /* number of per-block partial sums dcae_gc_fused writes for this problem size */
 int64_t dcae_gc_num_partials(int64_t rows, int64_t inner);
 /* out[0] = sum(partials[0..n)) in index order, one block (deterministic). */

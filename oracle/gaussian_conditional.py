@@ -36,9 +36,29 @@ def get_scale_table(min=SCALES_MIN, max=SCALES_MAX, levels=SCALES_LEVELS) -> tor
     return torch.exp(torch.linspace(math.log(min), math.log(max), levels))
 
 
+class LowerBoundFunction(torch.autograd.Function):
+    """compressai `ops.bound_ops.LowerBoundFunction` (published source; the package is absent here): forward
+    `torch.max(x, bound)`, backward passes the gradient where `x >= bound` OR the gradient pushes x up (`grad < 0`)."""
+
+    @staticmethod
+    def forward(ctx, x, bound):
+        ctx.save_for_backward(x, bound)
+        return torch.max(x, bound)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        x, bound = ctx.saved_tensors
+        pass_through_if = (x >= bound) | (grad_output < 0)
+        return pass_through_if * grad_output, None
+
+
 def lower_bound(x: torch.Tensor, bound: float) -> torch.Tensor:
-    """compressai LowerBound.forward: torch.max(x, bound) (dcae.py:846 restates it for scales)."""
-    return torch.max(x, torch.tensor(bound, dtype=x.dtype))
+    """compressai LowerBound.forward: torch.max(x, bound) (dcae.py:846 restates it for scales); under autograd with
+    LowerBound's own backward rule (the training step, train.py:165-179, differentiates through both bounds)."""
+    b = torch.tensor(bound, dtype=x.dtype, device=x.device)
+    if torch.is_grad_enabled() and x.requires_grad:
+        return LowerBoundFunction.apply(x, b)
+    return torch.max(x, b)
 
 
 def standardized_cumulative(inputs: torch.Tensor) -> torch.Tensor:

@@ -112,8 +112,8 @@ def test_a_different_dictionary_is_refused(nets):
         handle.loop._dt_checked = False
         with pytest.raises(ValueError):
             fast.dt_cross_attention[0](x, fast.dt.repeat([1, 1, 1]) + 1.0)
-    with pytest.raises(Exception):
-        fast.dt_cross_attention[0](x.requires_grad_(), None)         # forward-only: no silent zero gradients
+    out = fast.dt_cross_attention[0](x.requires_grad_(), None)       # under autograd: a recompute node, never silent zero gradients
+    assert out.grad_fn is not None
 
 
 def test_f16_range_check(nets, lively_params):
