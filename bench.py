@@ -41,6 +41,8 @@ CONFIGS = {
             workload="DCAE entropy-model forward (slice loop), batch 16 synthetic Kodak-shaped 768x512 images per GPU (BASELINE config #2)"),
     3: dict(H=1365, W=2048, batch=4, mode="compress", tag="2048x1365",
             workload="DCAE compress() slice loop (quantize + build_indexes + likelihoods), synthetic CLIC-shaped 2048x1365 images, 4 per GPU per step (BASELINE config #3)"),
+    4: dict(H=256, W=256, batch=8, mode="train", tag="256x256 crops (training)",
+            workload="DCAE entropy-model rate-distortion training step (MSE lambda = 0.013: forward, train.py:82-88 loss, backward, grad clip 1.0, Adam) on 8 x 256x256 crops per GPU, DDP gradient all-reduce over NCCL (BASELINE config #4)"),
     5: dict(H=2160, W=3840, batch=4, mode="forward", tag="3840x2160",
             workload="DCAE entropy-model forward (slice loop), synthetic 4K 3840x2160 images, 4 per GPU per step (BASELINE config #5)"),
 }
@@ -240,11 +242,19 @@ def run_reference(args):
     cfg = CONFIGS[args.config]
     n_img = args.batch or cfg["batch"]
     warm = max(args.warmup, 3) if args.config == 2 else min(args.warmup, 1)
-    rate, threads, dt, kind = cpu_reference_rate(cfg, n_img, args.steps, warm)
+    if args.config == 4:
+        torch.set_num_threads(os.cpu_count() or 1)
+        rate, dt, kind = reference_train_rate(cfg, "cpu", n_img, args.steps, warm)
+        threads = os.cpu_count() or 1
+        if rate is None:
+            print(json.dumps({"impl": "reference", "unavailable": "reference models/dcae.py not staged in oracle/_ref"}), flush=True)
+            return
+    else:
+        rate, threads, dt, kind = cpu_reference_rate(cfg, n_img, args.steps, warm)
     what = ("unmodified /root/reference/models/dcae.py classes (DCAE.%s slice loop on injected latents; GaussianConditional = oracle restatement, compressai absent)" % cfg["mode"]
             if kind == "reference" else "torch-CPU fp32 oracle port of dcae.py:638-670")
     line = {
-        "impl": "reference", "metric": f"entropy-model images/sec @{cfg['tag']}", "value": rate, "unit": "images/s",
+        "impl": "reference", "metric": "entropy-model training images/sec @256x256 crops" if args.config == 4 else f"entropy-model images/sec @{cfg['tag']}", "value": rate, "unit": "images/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": warm, "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": cfg["workload"], "batch_per_gpu": n_img, "mode": cfg["mode"], "where": "host CPU, torch fp32, all threads"},
@@ -254,6 +264,212 @@ def run_reference(args):
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+# ---- BASELINE config #4: the training step ---------------------------------------------------------------------------
+def _train_loss(lik, y_hat, target, pixels):
+    """train.py:82-88 (type mse, lambda 0.013) on the slice loop's outputs; the synthesis transform is outside the hot path,
+    so the distortion is measured on y_hat against y."""
+    import math
+    bpp = torch.log(lik).sum() / (-math.log(2) * pixels)
+    return 0.013 * 255 ** 2 * torch.mean((y_hat - target) ** 2) + bpp
+
+
+def reference_train_rate(cfg, device, n_images, steps, warmup, seed=0):
+    """The reference's own classes (oracle/_ref) doing the same step with torch autograd: DCAE.forward in train() mode on
+    injected latents, loss, backward, clip, Adam over the hot-path parameters.  -> (images/s, s/step, kind)."""
+    from dcae_b200.params import init_entropy_params
+    from oracle import reference_loader as rl
+    if not rl.reference_available():
+        return None, None, "unavailable"
+    h, w = latent_hw(cfg)
+    dev = torch.device(device)
+    net = rl.build_reference_net(init_entropy_params(seed, "lively")).to(dev).train()
+    hot = [p for k, p in net.named_parameters() if k.split(".")[0] in rl.HOT_PREFIXES]
+    opt = torch.optim.Adam(hot, lr=1e-4)
+    y, ls, lm = (t.to(dev) for t in synth_latents(n_images, h, w))
+    pixels = n_images * cfg["H"] * cfg["W"]
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        out = net(rl.inject_latents(net, y, ls, lm))
+        loss = _train_loss(out["likelihoods"]["y"], out["x_hat"], y, pixels)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(hot, 1.0)
+        opt.step()
+        return loss
+
+    for _ in range(warmup):
+        step()
+    if dev.type == "cuda":
+        torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        loss = step()
+    float(loss.detach())
+    if dev.type == "cuda":
+        torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return n_images / dt, dt, "reference"
+
+
+def run_training(args):
+    """config #4 on N GPUs: one process per GPU, `dcae_b200.EntropyModel` under DistributedDataParallel
+    (find_unused_parameters=True as train.py:424), every step = H2D of the batch, forward on the library's kernels,
+    loss, backward (torch-graph recompute + dcae_gc_backward), NCCL gradient all-reduce, clip, Adam, D2H of the loss."""
+    cfg = CONFIGS[4]
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.backends.cuda.matmul.allow_tf32 = False          # the backward recompute is the fp32 graph
+    torch.backends.cudnn.allow_tf32 = False
+    from dcae_b200.params import init_entropy_params
+    from dcae_b200.training import EntropyModel
+    B = args.batch or cfg["batch"]
+    h, w = latent_hw(cfg)
+    model = EntropyModel(init_entropy_params(0, "lively"), device=dev, math=args.math).train()
+    ddp = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=True) if world > 1 else model
+    params = list(model.parameters())
+    opt = torch.optim.Adam(params, lr=1e-4)
+    host_in = synth_latents(B, h, w, seed=1234 + rank, pin=True)
+    dev_in = [torch.empty_like(t, device=dev) for t in host_in]
+    pixels = B * cfg["H"] * cfg["W"]
+    host_loss = torch.empty(1).pin_memory()
+    n_params = sum(p.numel() for p in params)
+
+    def step(sync=True, copy=True):
+        if copy:
+            for d, s_ in zip(dev_in, host_in):
+                d.copy_(s_, non_blocking=True)
+        opt.zero_grad(set_to_none=True)
+        ctx = ddp.no_sync() if (world > 1 and not sync) else _null()
+        with ctx:
+            out = ddp(*dev_in)
+            loss = _train_loss(out["likelihoods"], out["y_hat"], dev_in[0], pixels)
+            loss.backward()
+        torch.nn.utils.clip_grad_norm_(params, 1.0)
+        opt.step()
+        if copy:
+            host_loss.copy_(loss.detach().reshape(1), non_blocking=True)
+        return loss
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        barrier()
+        return float(ms) / steps
+
+    sampler = ClockSampler(local) if rank == 0 and not args.no_clock_sampler else None
+    for _ in range(max(args.warmup, 3)):
+        step()
+    if sampler:
+        sampler.mark()
+    ms_step = timed(lambda: step(copy=False), args.steps)          # inputs resident
+    clocks = sampler.stop() if sampler else None
+    launches = model.engine[0].last_launches
+    t0 = time.perf_counter()
+    barrier()
+    ms_e2e = timed(step, args.steps)                               # H2D of the batch + D2H of the loss inside
+    loss_value = float(host_loss[0])
+    ms_nosync = timed(lambda: step(sync=False, copy=False), args.steps) if world > 1 else ms_step
+    # the gradient all-reduce alone: one flat fp32 buffer of all hot-path gradients
+    ar_ms = None
+    if world > 1:
+        flat = torch.zeros(n_params, device=dev)
+        for _ in range(3):
+            dist.all_reduce(flat)
+        ar_ms = timed(lambda: dist.all_reduce(flat), 10)
+        del flat
+    # where the step goes on one rank: forward (kernels), backward (recompute + autograd), optimizer + repack
+    def phase_times():
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+        for d, s_ in zip(dev_in, host_in):
+            d.copy_(s_)
+        opt.zero_grad(set_to_none=True)
+        torch.cuda.synchronize()
+        ev[0].record()
+        model.sync()
+        ev[1].record()
+        out = model(*dev_in)
+        loss = _train_loss(out["likelihoods"], out["y_hat"], dev_in[0], pixels)
+        ev[2].record()
+        loss.backward()
+        ev[3].record()
+        torch.nn.utils.clip_grad_norm_(params, 1.0)
+        opt.step()
+        ev[4].record()
+        torch.cuda.synchronize()
+        return {k: ev[i].elapsed_time(ev[i + 1]) for i, k in enumerate(("repack_weights", "forward_kernels", "backward_recompute", "clip_adam"))}
+    phases = phase_times() if rank == 0 else None
+
+    cpu_baseline = torch_gpu_baseline = None
+    if rank == 0 and not args.no_cpu_baseline:
+        rate, dt, kind = reference_train_rate(cfg, "cpu", B, 1, 1)
+        if rate:
+            cpu_baseline = {"value": rate, "unit": "images/s", "cores": os.cpu_count(), "kind": kind, "ms_per_step": dt * 1e3,
+                            "sample": f"1 step x {B} crops after 1 warm-up: the reference's own classes, torch autograd, fp32, all host threads"}
+    if rank == 0 and not args.no_gpu_baseline:
+        try:
+            rate, dt, kind = reference_train_rate(cfg, dev, B, args.gpu_baseline_steps, 2)
+            torch_gpu_baseline = {"value": rate, "unit": "images/s", "ms_per_step": dt * 1e3, "kind": kind,
+                                  "sample": f"{args.gpu_baseline_steps} steps x {B} crops: the reference's own classes trained by eager PyTorch on this GPU (fp32, TF32 off)"}
+        except Exception as e:                      # noqa: BLE001
+            torch_gpu_baseline = {"value": None, "error": repr(e)[:200]}
+    if rank == 0:
+        imgs = B * world
+        line = {
+            "metric": "entropy-model training images/sec @256x256 crops", "value": imgs / (ms_step * 1e-3), "unit": "images/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 (forward: fp16 hi+lo planes, 3-pass tcgen05; backward: fp32 torch ops)", "data": "synthetic",
+            "config": {"workload": cfg["workload"], "config": 4, "mode": "train", "batch_per_gpu": B, "tokens_per_gpu": B * h * w, "math": args.math,
+                       "parallelism": f"DDP x{world}, find_unused_parameters=True (train.py:424)", "hot_path_parameters": n_params,
+                       "l2": "working set (weights 333 MB fp32 + packed planes) >> 126 MB L2; no flush needed"},
+            "e2e": {"value": imgs / (ms_e2e * 1e-3), "unit": "images/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": sum(t.numel() * 4 for t in host_in), "d2h_bytes_per_step": 4,
+                    "how": "per step: pinned host batch -> device, forward, loss, backward, all-reduce, clip, Adam, loss -> host"},
+            "gpu_launches": launches * args.steps, "gpu_launches_per_step": launches,
+            "gpu_launches_note": "launches of this library's kernels in the forward pass of a step (the backward recompute runs torch kernels + dcae_gc_backward)",
+            "clocks": clocks,
+            "roofline": {"kernel": "forward slice loop (see config #2 for the per-kernel rooflines)", "bound": "tensor", "achieved": None, "peak": None, "unit": "TFLOP/s", "frac": None, "traffic": None,
+                         "note": "the training step is dominated by the torch-op backward (phases below); the library's kernels are the forward phase"},
+            "phases_ms": phases,
+            "allreduce": {"gradient_bytes": n_params * 4, "alone_ms": ar_ms, "exposed_ms": (ms_step - ms_nosync) if world > 1 else 0.0,
+                          "note": "alone = one flat fp32 all-reduce of all hot-path gradients; exposed = step time with DDP sync minus the same step under no_sync()"},
+            "loss": loss_value,
+            "cpu_baseline": cpu_baseline, "torch_gpu_baseline": torch_gpu_baseline,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+class _null:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
 
 
 def main():
@@ -279,6 +495,8 @@ def main():
         CONFIGS[args.config] = dict(CONFIGS[args.config], mode=args.mode)
     if args.impl == "reference":
         return run_reference(args)
+    if args.config == 4:
+        return run_training(args)
     cfg = CONFIGS[args.config]
     compress = cfg["mode"] == "compress"
 

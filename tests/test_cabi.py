@@ -31,6 +31,28 @@ def test_every_declared_symbol_is_exported_and_bound(lib):
     assert set(_lib.SIGNATURES) == set(names)
 
 
+def test_range_coder_library_exports_its_header():
+    """include/dcae_rans.h: every declared symbol is exported by libdcae_rans.so and bound in dcae_b200/ans.py."""
+    import __graft_entry__ as ge
+    ge.build()
+    from dcae_b200 import ans
+    src = open(os.path.join(ROOT, "include", "dcae_rans.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    names = sorted(set(re.findall(r"\b(dcae_[a-z0-9_]+)\s*\(", src)))
+    lib = ans.load()
+    assert len(names) >= 10 and set(names) == set(ans.SIGNATURES)
+    for n in names:
+        assert hasattr(lib, n), n
+    import ctypes as C
+    import subprocess
+    import tempfile
+    prog = '#include <stdio.h>\n#include "dcae_rans.h"\nint main(){printf("%zu\\n", sizeof(dcae_rans_tables));return 0;}\n'
+    with tempfile.TemporaryDirectory() as td:
+        open(os.path.join(td, "t.c"), "w").write(prog)
+        subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-o", os.path.join(td, "t"), os.path.join(td, "t.c")], check=True)
+        assert int(subprocess.run([os.path.join(td, "t")], capture_output=True, text=True, check=True).stdout) == C.sizeof(ans.RansTables)
+
+
 def test_version_and_error_channel(lib):
     assert lib.dcae_version() == 100
     assert lib.dcae_gc_num_partials(24576, 64) == 1184
@@ -50,12 +72,13 @@ def test_ctypes_struct_layout_matches_header(lib):
     import subprocess
     import tempfile
     from dcae_b200 import _lib
-    prog = '#include <stdio.h>\n#include "dcae_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu\\n", sizeof(dcae_gc_args), sizeof(dcae_operand), sizeof(dcae_epilogue), sizeof(dcae_weight), sizeof(dcae_slice_weights));return 0;}\n'
+    prog = '#include <stdio.h>\n#include "dcae_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(dcae_gc_args), sizeof(dcae_operand), sizeof(dcae_epilogue), sizeof(dcae_weight), sizeof(dcae_slice_weights), sizeof(dcae_gc_bwd_args));return 0;}\n'
     with tempfile.TemporaryDirectory() as td:
         open(os.path.join(td, "t.c"), "w").write(prog)
         subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-o", os.path.join(td, "t"), os.path.join(td, "t.c")], check=True)
         sizes = [int(v) for v in subprocess.run([os.path.join(td, "t")], capture_output=True, text=True, check=True).stdout.split()]
-    assert sizes == [C.sizeof(_lib.GcArgs), C.sizeof(_lib.Operand), C.sizeof(_lib.Epilogue), C.sizeof(_lib.Weight), C.sizeof(_lib.SliceWeights)]
+    assert sizes == [C.sizeof(_lib.GcArgs), C.sizeof(_lib.Operand), C.sizeof(_lib.Epilogue), C.sizeof(_lib.Weight), C.sizeof(_lib.SliceWeights),
+                     C.sizeof(_lib.GcBwdArgs)]
 
 
 def test_no_cpu_fallback():
