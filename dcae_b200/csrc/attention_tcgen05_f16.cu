@@ -14,11 +14,16 @@
 // behind PV(g) with no barrier in between (one issuing thread, in-order tensor pipe).
 //
 //   S[128 x 128] = Q_e K_e^T                      2 k-steps x 3 passes, TMEM buffer g & 1
-//   softmax       two threads per token row (64 columns each), log2-domain, ex2.approx; P' = 1024 * 2^(t - max) so
-//                 that p_lo stays a normal fp16; the factor cancels against the row sum
+//   softmax       TWO warp groups in ping-pong: group 0 owns the even head steps (S/P buffer 0, O buffer 0), group 1 the
+//                 odd ones, so the dependent chain of one head (TMEM load -> max -> exchange -> ex2 -> pack -> TMEM store)
+//                 overlaps the other head's instead of following it (the chain, not a pipe, set the 5.3 k-cycle head
+//                 step: 8 and 16 warps on ONE head measured the same).  Inside a group two threads per token row
+//                 (64 columns each), log2-domain, ex2.approx; P' = 1024 * 2^(t - max) so that p_lo stays a normal fp16;
+//                 the factor cancels against the row sum
 //   O[128 x 32]  = P V_e                           8 k-steps x 3 passes, A operand (P) straight from TMEM
 //   epilogue      each thread of the pair scales 16 of the 32 O columns by descale_v / sum and writes them
-// Warps: 0 = TMA, 1 = MMA issuer + TMEM owner, 2..9 = softmax.  All waits are bounded (trap, never hang).
+// Warps: 0 = TMA, 1 = MMA issuer + TMEM owner, 2..9 = softmax group 0, 10..17 = softmax group 1.  All waits are bounded
+// (trap, never hang).
 #include <cuda_fp16.h>
 
 #include "common.cuh"
@@ -33,8 +38,9 @@ namespace {
 
 constexpr int AF_M = 128;                         // tokens per tile
 constexpr int AF_HEADS = 20, AF_HD = 32, AF_ND = 128;
-constexpr int AF_SUB = 4;                         // softmax threads per token row (column quarters of 32)
-constexpr int AF_THREADS = 64 + AF_SUB * 128;     // warps 0 TMA, 1 MMA, then AF_SUB x 4 softmax warps
+constexpr int AF_SUB = 2;                         // softmax threads per token row inside a group (column halves of 64)
+constexpr int AF_GROUPS = 2;                      // ping-pong softmax groups: group = head step & 1
+constexpr int AF_THREADS = 64 + AF_GROUPS * AF_SUB * 128;     // warps 0 TMA, 1 MMA, then AF_GROUPS x AF_SUB x 4 softmax warps
 constexpr int AF_QK_BYTES = AF_M * 128;           // 16 KB: a [128 x 64 halfs] tile (Q or K of a head pair, one plane)
 constexpr int AF_V_BYTES = 64 * 128;              // 8 KB: V^T chunk [64 rows (2 heads x 32 dims) x 64 entries], one plane
 constexpr int AF_STAGE = 4 * AF_QK_BYTES + 4 * AF_V_BYTES;   // 96 KB per head PAIR
@@ -86,7 +92,9 @@ dict_attention_f16_kernel(const __grid_constant__ CUtensorMap map_qh, const __gr
   __shared__ __align__(8) uint64_t full_bar[AF_STAGES], empty_bar[AF_STAGES];
   __shared__ __align__(8) uint64_t s_full[2], p_ready[2], o_full[2], o_free[2];
   __shared__ uint32_t tmem_base_slot;
-  __shared__ float xm[2][AF_SUB][AF_M], xl[2][AF_SUB][AF_M];    // row max / row sum of each column range, double-buffered by head parity
+  // row max of each column range per group; row sums double-buffered by the group's own step parity (write_out of the
+  // previous head reads them while the current head's are written)
+  __shared__ float xm[AF_GROUPS][AF_SUB][AF_M], xl[AF_GROUPS][2][AF_SUB][AF_M];
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp: provably uniform
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -216,23 +224,24 @@ dict_attention_f16_kernel(const __grid_constant__ CUtensorMap map_qh, const __gr
     // Warps w, w + 4, w + 8, ... own the same 32 TMEM lanes (rows); each takes 128 / AF_SUB dictionary columns, so every
     // scheduler has AF_SUB softmax warps to alternate between.  Row max and row sum cross the group through shared
     // memory with one named barrier (AF_SUB x 32 threads) per head.
-    const int quarter = warp & 3, sub = (warp - 2) >> 2;
+    const int quarter = warp & 3, sub = ((warp - 2) >> 2) % AF_SUB, group = (warp - 2) / (4 * AF_SUB);
     const int r = quarter * 32 + lane;
     const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
     constexpr int HC = AF_ND / AF_SUB;     // columns per thread (32)
     constexpr int OC = AF_HD / AF_SUB;     // output columns per thread (8)
-    auto row_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(1 + quarter), "n"(AF_SUB * 32) : "memory"); };
+    auto row_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(1 + group * 4 + quarter), "n"(AF_SUB * 32) : "memory"); };
     auto write_out = [&](int g) {
       const int gp = (int)blockIdx.x + (g >> 1) * (int)gridDim.x;
       const int tile = gp / HP, head = (gp % HP) * 2 + (g & 1);
       float l = 0.f;
 #pragma unroll
-      for (int q = 0; q < AF_SUB; ++q) l += xl[g & 1][q][r];
+      for (int q = 0; q < AF_SUB; ++q) l += xl[g & 1][(g >> 1) & 1][q][r];
       const float inv = p.v_descale / l;
       mbar_wait(smem_u32(&o_full[g & 1]), (g >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       uint32_t o0[OC];
-      tmem_ld8_nowait(lane_addr + TF_O + (uint32_t)(g & 1) * 32 + sub * OC, o0);
+#pragma unroll
+      for (int c = 0; c < OC / 8; ++c) tmem_ld8_nowait(lane_addr + TF_O + (uint32_t)(g & 1) * 32 + sub * OC + c * 8, o0 + c * 8);
       tmem_ld_wait();
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive(smem_u32(&o_free[g & 1]));
@@ -251,8 +260,9 @@ dict_attention_f16_kernel(const __grid_constant__ CUtensorMap map_qh, const __gr
     };
     long long w_s = 0;
     const long long t_sm0 = clock64();
-    for (int g = 0; g < total; ++g) {
-      const int b = g & 1;
+    int last = -1;
+    for (int g = group; g < total; g += AF_GROUPS) {
+      const int b = g & 1;                                 // == group: each group keeps to its own S/P and O buffers
       const int head = (((int)blockIdx.x + (g >> 1) * (int)gridDim.x) % HP) * 2 + b;
       // softmax(sim * scale) = 2^(t - max t) / sum, t = acc * (k_descale * scale * log2 e)
       const float sc = __ldg(p.head_scale + head) * p.k_descale * 1.4426950408889634f;
@@ -286,23 +296,27 @@ dict_attention_f16_kernel(const __grid_constant__ CUtensorMap map_qh, const __gr
         s[j] = e;
         l8[j & 7] += e;
       }
-      if (g > 0) write_out(g - 1);
-      xl[b][sub][r] = ((l8[0] + l8[1]) + (l8[2] + l8[3])) + ((l8[4] + l8[5]) + (l8[6] + l8[7]));
+      if (last >= 0) write_out(last);                      // this group's previous head: its PV has had a whole head step
+      last = g;
+      xl[b][(g >> 1) & 1][sub][r] = ((l8[0] + l8[1]) + (l8[2] + l8[3])) + ((l8[4] + l8[5]) + (l8[6] + l8[7]));
       // packed fp16 pairs: word w = (P'[2w], P'[2w+1]); P_hi at columns [0, 64), P_lo at [64, 128) of the S/P buffer
       {
-        uint32_t hi[16], lo[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) f16_split2(s[2 * j], s[2 * j + 1], hi[j], lo[j]);
-        tmem_st16(lane_addr + TF_SP + (uint32_t)b * 128 + sub * 16, hi);
-        tmem_st16(lane_addr + TF_SP + (uint32_t)b * 128 + 64 + sub * 16, lo);
+        for (int c = 0; c < HC / 32; ++c) {
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f16_split2(s[32 * c + 2 * j], s[32 * c + 2 * j + 1], hi[j], lo[j]);
+          tmem_st16(lane_addr + TF_SP + (uint32_t)b * 128 + sub * (HC / 2) + c * 16, hi);
+          tmem_st16(lane_addr + TF_SP + (uint32_t)b * 128 + 64 + sub * (HC / 2) + c * 16, lo);
+        }
       }
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive(smem_u32(&p_ready[b]));
     }
-    if (total > 0) {
+    if (last >= 0) {
       row_sync();
-      write_out(total - 1);
+      write_out(last);
     }
     if (DBG && warp == 2 && lane == 0) {
       p.dbg[blockIdx.x * 8 + 6] = (unsigned long long)w_s;

@@ -75,7 +75,7 @@ class EntropySliceLoop:
         self.math = math
         with torch.cuda.device(self.device):
             _lib.check(self.lib.dcae_device_check(), "dcae_device_check")
-        self.weights = PackedWeights(params, self.device, split_tf32=True)
+        self.weights = PackedWeights(params, self.device, split_tf32=True, math=math)
         self.dictionary = params["dt"].detach().to(self.device, torch.float32).clone()     # what K / V were packed from
         if scale_table is None:
             scale_table = get_scale_table()
@@ -93,7 +93,7 @@ class EntropySliceLoop:
         rebuilt on the next call; the previous packed tensors are released once no launch uses them any more."""
         torch.cuda.synchronize(self.device)
         self._plans.clear()
-        self.weights = PackedWeights(params, self.device, split_tf32=True)
+        self.weights = PackedWeights(params, self.device, split_tf32=True, math=self.math)
         self.dictionary = params["dt"].detach().to(self.device, torch.float32).clone()
         self._dt_checked = False
 

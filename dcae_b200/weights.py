@@ -35,10 +35,14 @@ def f16_weight_planes(lib, w: torch.Tensor, taps: int, stream):
 class PackedWeights:
     """Owns every packed device tensor of the 5 slices and the ctypes array handed to the C ABI."""
 
-    def __init__(self, params: Dict[str, torch.Tensor], device: torch.device, split_tf32: bool = True):
+    def __init__(self, params: Dict[str, torch.Tensor], device: torch.device, split_tf32: bool = True, math: str = "all"):
+        """math: which operand formats to prepare -- "all", or the engine's math mode: the TF32 hi/lo split only for the
+        tf32 modes, the fp16 planes only for the f16 modes (a repack per optimizer step should not pay for both)."""
         self.device = device
         self._keep: List[torch.Tensor] = []
         self.split = split_tf32
+        self.want_tf32 = math in ("all", "tf32x3", "tf32")
+        self.want_f16 = math in ("all", "f16x3", "f16")
         self.lib = _lib.load()
         self.array = (_lib.SliceWeights * NUM_SLICES)()
         with torch.cuda.device(device):
@@ -64,13 +68,15 @@ class PackedWeights:
         out.w, out.N, out.K = w.data_ptr(), N, K
         if self.split:
             s = _lib.current_stream(self.device)
-            hi, lo = torch.empty_like(w), torch.empty_like(w)
-            self._keep += [hi, lo]
-            _lib.check(self.lib.dcae_split_tf32(w.data_ptr(), hi.data_ptr(), lo.data_ptr(), w.numel(), s), "dcae_split_tf32")
-            out.w_hi, out.w_lo = hi.data_ptr(), lo.data_ptr()
-            h16, l16, K16, descale = f16_weight_planes(self.lib, w, taps, s)
-            self._keep += [h16, l16]
-            out.w16_hi, out.w16_lo, out.K16, out.descale = h16.data_ptr(), l16.data_ptr(), K16, descale
+            if self.want_tf32:
+                hi, lo = torch.empty_like(w), torch.empty_like(w)
+                self._keep += [hi, lo]
+                _lib.check(self.lib.dcae_split_tf32(w.data_ptr(), hi.data_ptr(), lo.data_ptr(), w.numel(), s), "dcae_split_tf32")
+                out.w_hi, out.w_lo = hi.data_ptr(), lo.data_ptr()
+            if self.want_f16:
+                h16, l16, K16, descale = f16_weight_planes(self.lib, w, taps, s)
+                self._keep += [h16, l16]
+                out.w16_hi, out.w16_lo, out.K16, out.descale = h16.data_ptr(), l16.data_ptr(), K16, descale
         return out
 
     @staticmethod
