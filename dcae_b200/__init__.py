@@ -4,6 +4,7 @@ Public surface (mirrors the reference's operator interface for this path only):
   EntropySliceLoop      -- the channel-slice loop of DCAE.forward/compress/decompress
   HostPipeline          -- pinned-host-in / pinned-host-out streaming front end (overlapped copies)
   GaussianConditional   -- compressai-compatible quantise / likelihood / build_indexes (kernel 3)
+  EntropyBottleneck     -- compressai-compatible factorised prior for the hyper-latent z (one fused pass + the native coder)
   accelerate, DictCrossAttention, ConvStack -- module-level drop-ins for a reference DCAE instance (dcae_b200/modules.py)
   EntropyModel, SliceLoopFunction -- the training form (autograd: kernels forward, torch-graph recompute backward)
   ans.BufferedRansEncoder / RansDecoder -- the native range coder with compressai.ans' interface
@@ -26,6 +27,9 @@ def __getattr__(name):
     if name in ("EntropyModel", "SliceLoopFunction", "GaussianLikelihoodFunction", "rate_distortion_loss"):
         from . import training
         return getattr(training, name)
+    if name == "EntropyBottleneck":
+        from .entropy_bottleneck import EntropyBottleneck
+        return EntropyBottleneck
     if name == "GaussianConditional":
         from .gaussian_conditional import GaussianConditional
         return GaussianConditional

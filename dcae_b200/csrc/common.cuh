@@ -83,7 +83,10 @@ __device__ __forceinline__ float gelu_fast(float x) {
   r = fmaf(r, t, 0.14848162233829498f);
   r = fmaf(r, t, 0.9184163808822632f);
   r = fmaf(r, t, 1.6279085874557495f);
-  const float he = 0.5f * x * exp2f(-t * r);
+  // -t r >= -32: outside exp2f's denormal fix-up, so the bare MUFU.EX2 gives the same bits in 1 instruction instead of 4
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-t * r));
+  const float he = 0.5f * x * e;
   return x >= 0.f ? x - he : he;
 }
 

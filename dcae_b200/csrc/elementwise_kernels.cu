@@ -70,71 +70,91 @@ __global__ void __launch_bounds__(256) gelu_kernel(const float* __restrict__ x, 
 // groups so every load/store is a coalesced 16-byte access.  DX = 4 (72 registers) measured 8 % / 23 % faster than
 // DX = 8 (104 registers, 25 % occupancy) on the 640- / 1280-channel GLU launch, DX = 2 slower again (DCAE_DW_X).
 // ---------------------------------------------------------------------------------------------
-constexpr int DW_X = 8, DW_ROWS = 4;
+constexpr int DW_ROWS = 4;      // token rows per block; the tokens per thread (DX) are a template parameter: 4 by default, DCAE_DW_X = 2 / 8 for A/B
 
-// grid = (ceil(C4 / 32), ceil(h / DW_ROWS), B * ceil(w / DW_X)); block = 32 channel groups x DW_ROWS token rows, so the
+// grid = (ceil(C4 / 32), ceil(h / DW_ROWS), B * ceil(w / DX)); block = 32 channel groups x DW_ROWS token rows, so the
 // three input rows a thread needs are shared with its neighbours in the block through L1.
 // ACT: 0 none, 1 GELU (erff form, the fp32 path), 2 GELU through gelu_fast (planes-only output, i.e. the tensor-core
 // modes: measured issue-bound on erff, 67% issue utilisation at 25% occupancy, before the switch).
+// All element offsets are 32-bit (the host checks that every tensor spans < 2^32 elements): one IMAD per access and one
+// IMAD.WIDE onto the 64-bit base, instead of the 64-bit multiply chains that made integer work 45 % of the kernel
+// (round 1: 69 instructions per output element, 16 of them FFMA).
 template <int ACT, int DX>
-__global__ void __launch_bounds__(32 * DW_ROWS) dwconv3x3_kernel(const float* __restrict__ x, int64_t x_ld,
+__global__ void __launch_bounds__(32 * DW_ROWS) dwconv3x3_kernel(const float* __restrict__ x, uint32_t x_ld,
                                                         const float* __restrict__ wt, const float* __restrict__ bias,
                                                         int C4, int B, int h, int w,
-                                                        const float* __restrict__ gate, int64_t gate_ld,
-                                                        float* __restrict__ out, int64_t out_ld, const dcae_planes o16) {
+                                                        const float* __restrict__ gate, uint32_t gate_ld,
+                                                        float* __restrict__ out, uint32_t out_ld, const dcae_planes o16) {
   const int xg = (w + DX - 1) / DX;
-  const int C = C4 * 4;
+  const uint32_t C = (uint32_t)C4 * 4;
   const int c4 = blockIdx.x * 32 + (threadIdx.x & 31);
   const int yy = blockIdx.y * DW_ROWS + (threadIdx.x >> 5);
   const int b = blockIdx.z / xg;
   const int x0 = (blockIdx.z - b * xg) * DX;
   if (c4 >= C4 || yy >= h) return;
-  {
-    const int c = c4 * 4;
-    float4 k[9];
+  const uint32_t c = (uint32_t)c4 * 4;
+  const float* xb = x + c;
+  float4 k[9];
 #pragma unroll
-    for (int t = 0; t < 9; ++t) k[t] = __ldg(reinterpret_cast<const float4*>(wt + t * C + c));
-    const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + c));
-    float4 acc[DX];
+  for (int t = 0; t < 9; ++t) k[t] = __ldg(reinterpret_cast<const float4*>(wt + (uint32_t)t * C + c));
+  const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + c));
+  float4 acc[DX];
 #pragma unroll
-    for (int j = 0; j < DX; ++j) acc[j] = bv;
+  for (int j = 0; j < DX; ++j) acc[j] = bv;
+  const uint32_t img = (uint32_t)b * (uint32_t)h;
+  const bool interior = x0 >= 1 && x0 + DX + 1 <= w;
 #pragma unroll
-    for (int dy = -1; dy <= 1; ++dy) {
-      const int y2 = yy + dy;
-      if ((unsigned)y2 >= (unsigned)h) continue;
-      const float* row = x + ((int64_t)(b * h + y2) * w) * x_ld + c;
-      float4 p[DX + 2];
+  for (int dy = -1; dy <= 1; ++dy) {
+    const int y2 = yy + dy;
+    if ((unsigned)y2 >= (unsigned)h) continue;
+    const uint32_t row = (img + (uint32_t)y2) * (uint32_t)w;          // token index of (b, y2, 0)
+    float4 p[DX + 2];
+    if (interior) {        // block-uniform: the whole DX + 2 window lies inside the row (10 of 12 column groups at w = 48)
+      const float* pr = xb + (row + (uint32_t)(x0 - 1)) * x_ld;
+#pragma unroll
+      for (int j = 0; j < DX + 2; ++j) p[j] = __ldg(reinterpret_cast<const float4*>(pr + (uint32_t)j * x_ld));
+    } else {
 #pragma unroll
       for (int j = 0; j < DX + 2; ++j) {
         const int x2 = x0 - 1 + j;
-        p[j] = ((unsigned)x2 < (unsigned)w) ? __ldg(reinterpret_cast<const float4*>(row + (int64_t)x2 * x_ld))
-                                            : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-#pragma unroll
-      for (int j = 0; j < DX; ++j) {
-#pragma unroll
-        for (int dx = 0; dx < 3; ++dx) {
-          const float4 kk = k[(dy + 1) * 3 + dx];
-          const float4 v = p[j + dx];
-          acc[j].x = fmaf(v.x, kk.x, acc[j].x); acc[j].y = fmaf(v.y, kk.y, acc[j].y);
-          acc[j].z = fmaf(v.z, kk.z, acc[j].z); acc[j].w = fmaf(v.w, kk.w, acc[j].w);
-        }
+        p[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if ((unsigned)x2 < (unsigned)w) p[j] = __ldg(reinterpret_cast<const float4*>(xb + (row + (uint32_t)x2) * x_ld));
       }
     }
 #pragma unroll
     for (int j = 0; j < DX; ++j) {
-      const int x2 = x0 + j;
-      if (x2 >= w) break;
-      const int64_t t = (int64_t)(b * h + yy) * w + x2;
-      float4 a = acc[j];
-      if (ACT == 1) { a.x = gelu_erf(a.x); a.y = gelu_erf(a.y); a.z = gelu_erf(a.z); a.w = gelu_erf(a.w); }
-      if (ACT == 2) { a.x = gelu_fast(a.x); a.y = gelu_fast(a.y); a.z = gelu_fast(a.z); a.w = gelu_fast(a.w); }
-      if (gate != nullptr) {
-        const float4 g = __ldg(reinterpret_cast<const float4*>(gate + t * gate_ld + c));
-        a.x *= g.x; a.y *= g.y; a.z *= g.z; a.w *= g.w;
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const float4 kk = k[(dy + 1) * 3 + dx];
+        const float4 v = p[j + dx];
+        acc[j].x = fmaf(v.x, kk.x, acc[j].x); acc[j].y = fmaf(v.y, kk.y, acc[j].y);
+        acc[j].z = fmaf(v.z, kk.z, acc[j].z); acc[j].w = fmaf(v.w, kk.w, acc[j].w);
       }
-      if (out) *reinterpret_cast<float4*>(out + t * out_ld + c) = a;
-      if (o16.hi) store_planes4(o16, t, c, a);
+    }
+  }
+  const uint32_t t0 = (img + (uint32_t)yy) * (uint32_t)w + (uint32_t)x0;
+  const uint32_t p_ld = (uint32_t)o16.ld;
+  __half* const hi = static_cast<__half*>(o16.hi);
+  __half* const lo = static_cast<__half*>(o16.lo);
+#pragma unroll
+  for (int j = 0; j < DX; ++j) {
+    if (x0 + j >= w) break;
+    const uint32_t t = t0 + (uint32_t)j;
+    float4 a = acc[j];
+    if (ACT == 1) { a.x = gelu_erf(a.x); a.y = gelu_erf(a.y); a.z = gelu_erf(a.z); a.w = gelu_erf(a.w); }
+    if (ACT == 2) { a.x = gelu_fast(a.x); a.y = gelu_fast(a.y); a.z = gelu_fast(a.z); a.w = gelu_fast(a.w); }
+    if (gate != nullptr) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gate + (t * gate_ld + c)));
+      a.x *= g.x; a.y *= g.y; a.z *= g.z; a.w *= g.w;
+    }
+    if (out) *reinterpret_cast<float4*>(out + (t * out_ld + c)) = a;
+    if (hi) {
+      uint2 hv, lv;
+      f16_split2(a.x, a.y, hv.x, lv.x);
+      f16_split2(a.z, a.w, hv.y, lv.y);
+      const uint32_t o = t * p_ld + c;
+      *reinterpret_cast<uint2*>(hi + o) = hv;
+      *reinterpret_cast<uint2*>(lo + o) = lv;
     }
   }
 }
@@ -340,12 +360,17 @@ extern "C" int dcae_op_dwconv3x3(const float* x, int64_t x_ld, const float* wt, 
   DCAE_REQUIRE(aligned16(x) && aligned16(wt) && aligned16(bias) && aligned16(out) && aligned16(gate), "dcae_op_dwconv3x3: 16-byte alignment required");
   DCAE_REQUIRE(act == DCAE_ACT_NONE || act == DCAE_ACT_GELU, "dcae_op_dwconv3x3: act must be NONE or GELU");
   if ((int64_t)B * h * w == 0) return DCAE_OK;
+  {
+    const int64_t T = (int64_t)B * h * w, lim = 1ll << 32;
+    DCAE_REQUIRE(T * x_ld < lim && T * out_ld < lim && T * gate_ld < lim && T * o16.ld < lim && x_ld < lim && out_ld < lim && gate_ld < lim,
+                 "dcae_op_dwconv3x3: tensors of 2^32 elements or more are not supported (32-bit offsets)");
+  }
   static const int dw_x = [] { const char* v = getenv("DCAE_DW_X"); const int x = v ? atoi(v) : 4; return (x == 2 || x == 4 || x == 8) ? x : 4; }();
   const int xg = (w + dw_x - 1) / dw_x;
   DCAE_REQUIRE((int64_t)B * xg <= 65535 && (h + DW_ROWS - 1) / DW_ROWS <= 65535, "dcae_op_dwconv3x3: token grid too large");
   dim3 grid((unsigned)((C / 4 + 31) / 32), (unsigned)((h + DW_ROWS - 1) / DW_ROWS), (unsigned)(B * xg));
   const int variant = act == DCAE_ACT_NONE ? 0 : (out == nullptr ? 2 : 1);
-#define DW_LAUNCH(A, X) dwconv3x3_kernel<A, X><<<grid, 32 * DW_ROWS, 0, (cudaStream_t)stream>>>(x, x_ld, wt, bias, C / 4, B, h, w, gate, gate_ld, out, out_ld, o16)
+#define DW_LAUNCH(A, X) dwconv3x3_kernel<A, X><<<grid, 32 * DW_ROWS, 0, (cudaStream_t)stream>>>(x, (uint32_t)x_ld, wt, bias, C / 4, B, h, w, gate, (uint32_t)gate_ld, out, (uint32_t)out_ld, o16)
   if (dw_x == 4) { if (variant == 0) DW_LAUNCH(0, 4); else if (variant == 1) DW_LAUNCH(1, 4); else DW_LAUNCH(2, 4); }
   else if (dw_x == 2) { if (variant == 0) DW_LAUNCH(0, 2); else if (variant == 1) DW_LAUNCH(1, 2); else DW_LAUNCH(2, 2); }
   else { if (variant == 0) DW_LAUNCH(0, 8); else if (variant == 1) DW_LAUNCH(1, 8); else DW_LAUNCH(2, 8); }

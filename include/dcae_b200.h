@@ -137,6 +137,25 @@ int64_t dcae_gc_num_partials(int64_t rows, int64_t inner);
 int dcae_reduce_partials(const float* partials, int64_t n, float* out, void* stream);
 
 /* --------------------------------------------------------------------------------------------
+ * Hyper-latent entropy model (first part): compressai EntropyBottleneck.forward / quantize / dequantize as
+ * the reference calls them for z (dcae.py:629-633, :705-706, :861), one pass over NCHW z [B, C, h, w]:
+ *   out = round(z - median_c) + median_c (EVAL) | z + noise (NOISE) | float(sym_in) + median_c (DECODE)
+ *   lik = max(sigmoid(L_c(out + 1/2)) - sigmoid(L_c(out - 1/2)), lik_bound),  L_c = the channel's 1-3-3-3-3-1 network
+ *   sym = int32(round(z - median_c)),  z_hat = round(z - median_c) + median_c
+ * params: [C, 58] = per channel softplus(_matrix0..4) (3, 9, 9, 9, 3 row-major), _bias0..4 (3, 3, 3, 3, 1),
+ * tanh(_factor0..3) (3 each), packed by the host once per weight load.  Any output may be NULL.
+ * ------------------------------------------------------------------------------------------*/
+typedef struct {
+  const float* z; const float* noise; const int32_t* sym_in;
+  const float* params; const float* medians;
+  int32_t mode;            /* DCAE_GC_EVAL / DCAE_GC_NOISE / DCAE_GC_DECODE */
+  int32_t B, C; int64_t HW;
+  float lik_bound;
+  float* z_hat; float* lik; int32_t* sym;
+} dcae_eb_args;
+int dcae_eb_fused(const dcae_eb_args* a, void* stream);
+
+/* --------------------------------------------------------------------------------------------
  * Elementary token-major operators (each replaces one torch dispatch chain of dcae.py:300-509).
  * ------------------------------------------------------------------------------------------*/
 
