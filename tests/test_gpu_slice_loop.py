@@ -20,7 +20,7 @@ FP32_TOL = 1e-5
 # (per-slice teacher-forced rel tol, max teacher-forced sym/idx mismatch rate, max free-running mismatch rate)
 # the rates are <= 5 x the worst value observed on B200 over the three golden cases (printed by the tests;
 # profiles/r02/parity_rates.txt): a regression 10 x worse than today fails
-MODES = {"fp32": (FP32_TOL, 2e-4, 2e-4), "tf32x3": (FP32_TOL, 5e-4, 7.5e-4), "f16x3": (FP32_TOL, 5e-4, 5e-4), "tf32": (1e-2, 5e-2, 0.3)}
+MODES = {"fp32": (FP32_TOL, 5e-4, 3e-4), "tf32x3": (FP32_TOL, 7.5e-4, 5e-4), "f16x3": (FP32_TOL, 5e-4, 5e-4), "tf32": (1e-2, 5e-2, 0.3)}
 
 _engines = {}
 
