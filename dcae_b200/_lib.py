@@ -140,6 +140,7 @@ SIGNATURES = {
     "dcae_op_gelu": (C.c_int, [_P, _I64, _I32, _I64, _P, _I64, C.POINTER(Planes), _P]),
     "dcae_op_dwconv3x3": (C.c_int, [_P, _I64, _P, _P, _I32, _I32, _I32, _I32, _I32, _P, _I64, _P, _I64, C.POINTER(Planes), _P]),
     "dcae_op_spatial_gate": (C.c_int, [_P, _I64, _P, _I64, _P, _P, _I32, _I32, _I32, _I32, _P, _P, _I64, _P]),
+    "dcae_op_spatial_gate_ln": (C.c_int, [_P, _I64, _P, _I64, _P, _P, _I32, _I32, _I32, _I32, _P, _P, _I64, _P, _P, C.POINTER(Planes), _P]),
     "dcae_op_dict_attention": (C.c_int, [_P, _I64, C.POINTER(Planes), C.POINTER(DictKV), _I64, _P, _I64, C.POINTER(Planes), C.c_int, _P]),
     "dcae_op_nchw_to_tokens": (C.c_int, [_P, _I32, _I32, _I64, _P, _I64, C.POINTER(Planes), _P]),
     "dcae_op_tokens_to_nchw": (C.c_int, [_P, _I64, _I32, _I32, _I64, _P, _P]),

@@ -450,9 +450,15 @@ static int run_dca(dcae_slice_loop* p, int i, void* s, bool dict_f32 = false) { 
   }
   DCAE_TRY(gemm(p, opnd2(p, p->dc, 4 * D, p->dcp, 0, 4 * D, 1), W.dense_proj, epi(W.dense_proj_b, p->so.p, D), s));
   // x = s_out * spatial_atte(s_out) + res_scale_1(x)                         dcae.py:446, 484
-  DCAE_TRY(dcae_op_spatial_gate(p->so.p, D, p->x0.p, D, W.res_scale_1, W.spatial_w7, D, p->B, p->h, p->w, p->stats.p, p->x1.p, D, s));
-  // q = q_trans(lnx(x)); attention against the dictionary                    dcae.py:486-501
-  DCAE_TRY(dcae_op_layernorm(p->x1.p, D, W.lnx_g, W.lnx_b, D, T, ln32, D, &lnp, s));
+  // planes mode: the gate kernel also writes lnx(x) (the row is in its registers): one launch less per slice
+  if (pm) {
+    DCAE_TRY(dcae_op_spatial_gate_ln(p->so.p, D, p->x0.p, D, W.res_scale_1, W.spatial_w7, D, p->B, p->h, p->w, p->stats.p, p->x1.p, D,
+                                     W.lnx_g, W.lnx_b, &lnp, s));
+  } else {
+    DCAE_TRY(dcae_op_spatial_gate(p->so.p, D, p->x0.p, D, W.res_scale_1, W.spatial_w7, D, p->B, p->h, p->w, p->stats.p, p->x1.p, D, s));
+    // q = q_trans(lnx(x)); attention against the dictionary                    dcae.py:486-501
+    DCAE_TRY(dcae_op_layernorm(p->x1.p, D, W.lnx_g, W.lnx_b, D, T, ln32, D, &lnp, s));
+  }
   DCAE_TRY(chk(p, lnp, D, s));
   {
     dcae_epilogue e = epi(W.q_trans_b, p->q.p, D);

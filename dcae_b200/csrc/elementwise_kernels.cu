@@ -191,7 +191,9 @@ __global__ void __launch_bounds__(256) spatial_gate_kernel(const float* __restri
                                                            const float* __restrict__ res_scale,
                                                            const float* __restrict__ w7,
                                                            const float* __restrict__ stats, int B, int h, int w,
-                                                           float* __restrict__ out, int64_t out_ld) {
+                                                           float* __restrict__ out, int64_t out_ld,
+                                                           const float* __restrict__ ln_gamma, const float* __restrict__ ln_beta,
+                                                           const dcae_planes ln16) {
   const int lane = threadIdx.x & 31;
   const int64_t T = (int64_t)B * h * w;
   const int64_t t = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -211,6 +213,7 @@ __global__ void __launch_bounds__(256) spatial_gate_kernel(const float* __restri
   const float4* xr = reinterpret_cast<const float4*>(x0 + t * x0_ld);
   const float4* rs = reinterpret_cast<const float4*>(res_scale);
   float4* orow = reinterpret_cast<float4*>(out + t * out_ld);
+  float4 v[V];
 #pragma unroll
   for (int k = 0; k < V; ++k) {
     const float4 a = __ldg(sr + lane + 32 * k), b = __ldg(xr + lane + 32 * k), r = __ldg(rs + lane + 32 * k);
@@ -218,6 +221,34 @@ __global__ void __launch_bounds__(256) spatial_gate_kernel(const float* __restri
     o.x = a.x * gate + b.x * r.x; o.y = a.y * gate + b.y * r.y;
     o.z = a.z * gate + b.z * r.z; o.w = a.w * gate + b.w * r.w;
     orow[lane + 32 * k] = o;
+    v[k] = o;
+  }
+  if (ln16.hi == nullptr) return;
+  // fused LayerNorm of the row just produced (lnx of dcae.py:487): the warp holds all C values, so the separate
+  // layernorm launch and its re-read of the row go away.  Same two-pass arithmetic as layernorm_kernel: same bits.
+  constexpr int C = V * 128;
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < V; ++k) s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+  const float mean = warp_sum(s) * (1.0f / C);
+  float q = 0.f;
+#pragma unroll
+  for (int k = 0; k < V; ++k) {
+    float a = v[k].x - mean, b = v[k].y - mean, c = v[k].z - mean, d = v[k].w - mean;
+    q += (a * a + b * b) + (c * c + d * d);
+  }
+  const float rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / C) + 1e-5f);
+  const float4* g4 = reinterpret_cast<const float4*>(ln_gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(ln_beta);
+#pragma unroll
+  for (int k = 0; k < V; ++k) {
+    const float4 g = __ldg(g4 + lane + 32 * k), b = __ldg(b4 + lane + 32 * k);
+    float4 o;
+    o.x = (v[k].x - mean) * rstd * g.x + b.x;
+    o.y = (v[k].y - mean) * rstd * g.y + b.y;
+    o.z = (v[k].z - mean) * rstd * g.z + b.z;
+    o.w = (v[k].w - mean) * rstd * g.w + b.w;
+    store_planes4(ln16, t, (lane + 32 * k) * 4, o);
   }
 }
 
@@ -382,8 +413,17 @@ extern "C" int dcae_op_dwconv3x3(const float* x, int64_t x_ld, const float* wt, 
 extern "C" int dcae_op_spatial_gate(const float* s_out, int64_t s_ld, const float* x0, int64_t x0_ld,
                                     const float* res_scale, const float* w7, int32_t C, int32_t B, int32_t h, int32_t w,
                                     float* stats, float* out, int64_t out_ld, void* stream) {
+  return dcae_op_spatial_gate_ln(s_out, s_ld, x0, x0_ld, res_scale, w7, C, B, h, w, stats, out, out_ld, nullptr, nullptr, nullptr, stream);
+}
+
+extern "C" int dcae_op_spatial_gate_ln(const float* s_out, int64_t s_ld, const float* x0, int64_t x0_ld,
+                                       const float* res_scale, const float* w7, int32_t C, int32_t B, int32_t h, int32_t w,
+                                       float* stats, float* out, int64_t out_ld, const float* ln_gamma, const float* ln_beta,
+                                       const dcae_planes* ln_out16, void* stream) {
   ProfileScope prof(DCAE_PROF_OTHER, 0.0, stream);
+  const dcae_planes ln16 = planes_or_null(ln_out16);
   DCAE_REQUIRE(s_out && x0 && res_scale && w7 && stats && out, "dcae_op_spatial_gate: null pointer");
+  DCAE_REQUIRE(!ln16.hi || (ln_gamma && ln_beta && planes_ok(ln_out16) && aligned16(ln_gamma) && aligned16(ln_beta)), "dcae_op_spatial_gate_ln: LayerNorm output planes need gamma / beta (16-byte aligned)");
   DCAE_REQUIRE(C % 128 == 0 && C >= 128 && C <= 1024, "dcae_op_spatial_gate: C=%d must be a multiple of 128 in [128,1024]", C);
   DCAE_REQUIRE(aligned16(s_out) && aligned16(x0) && aligned16(res_scale) && aligned16(out) && s_ld % 4 == 0 && x0_ld % 4 == 0 && out_ld % 4 == 0,
                "dcae_op_spatial_gate: 16-byte alignment required");
@@ -396,7 +436,7 @@ extern "C" int dcae_op_spatial_gate(const float* s_out, int64_t s_ld, const floa
   case V:                                                                                                        \
     channel_stats_kernel<V><<<blocks, 256, 0, s>>>(s_out, s_ld, T, stats);                                       \
     count_launch();                                                                                              \
-    spatial_gate_kernel<V><<<blocks, 256, 0, s>>>(s_out, s_ld, x0, x0_ld, res_scale, w7, stats, B, h, w, out, out_ld); \
+    spatial_gate_kernel<V><<<blocks, 256, 0, s>>>(s_out, s_ld, x0, x0_ld, res_scale, w7, stats, B, h, w, out, out_ld, ln_gamma, ln_beta, ln16); \
     break;
     SG_CASE(1) SG_CASE(2) SG_CASE(3) SG_CASE(4) SG_CASE(5) SG_CASE(6) SG_CASE(7) SG_CASE(8)
 #undef SG_CASE

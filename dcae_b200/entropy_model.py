@@ -62,12 +62,17 @@ class EntropySliceLoop:
     depend on the split (tests: batch invariance)."""
 
     def __init__(self, params: Dict[str, torch.Tensor], device="cuda:0", math: str = "f16x3",
-                 scale_table: Optional[torch.Tensor] = None, lanes: int = 2, likelihood_math: str = "fast"):
+                 scale_table: Optional[torch.Tensor] = None, lanes: int = 2, likelihood_math: str = "fast",
+                 validate_f16_range: bool = True):
         if math not in _lib.MATH:
             raise ValueError(f"math must be one of {list(_lib.MATH)}")
         if likelihood_math not in _lib.GC_LIK:
             raise ValueError(f"likelihood_math must be one of {list(_lib.GC_LIK)}")
         self.likelihood_math = likelihood_math
+        # f16x3 / f16: the first forward() of an engine (and the first after refresh()) also runs the fp16 range check on
+        # its inputs (`check_f16_range`: one counting launch behind every producer, once), so a checkpoint whose
+        # activations leave the fp16 range raises instead of being clamped silently
+        self._range_checked = not (validate_f16_range and math in ("f16x3", "f16"))
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise _lib.DcaeError("dcae_b200 runs on CUDA devices only (no CPU fallback)")
@@ -161,6 +166,9 @@ class EntropySliceLoop:
             sym, idx = out["symbols"], out["indexes"]
         if B == 0 or h == 0 or w == 0:
             return out
+        if not self._range_checked and not torch.cuda.is_current_stream_capturing():
+            self._range_checked = True
+            self.check_f16_range(y, ls, lm)
         split = self._lane_split(B, h * w)
         self._last_call_lanes = len(split) > 1
         if len(split) == 1:
@@ -203,7 +211,7 @@ class EntropySliceLoop:
         the library's range check on (one small counting launch behind every producer of operand planes) and returns
         the number of clamped elements; 0 means the 22-bit operand claim held for these inputs.  Raises if not 0 and
         `math` is f16x3 -- use `math="tf32x3"` (fp32 operands in HBM, no range limit) for such a checkpoint."""
-        if self.math != "f16x3":
+        if self.math not in ("f16x3", "f16"):
             return 0
         y = self._check_in("y", y)
         B, _, h, w = y.shape
@@ -215,6 +223,7 @@ class EntropySliceLoop:
             self._run_forward(plan, self._stream(), y, self._check_in("latent_scales", latent_scales),
                               self._check_in("latent_means", latent_means), None, out, None, None, torch.empty(1, device=self.device))
             _lib.check(self.lib.dcae_slice_loop_check_f16_range(plan.handle, 0, C.byref(n)), "check_f16_range")
+        self._plans.pop((B, h, w, -2), None)           # its workspace is as large as a production plan's: do not keep it
         if n.value:
             raise _lib.DcaeError(f"f16x3: {n.value} activation elements exceed the fp16 range (|x| > 65504) and were clamped; "
                                  "run this checkpoint with math='tf32x3'")

@@ -233,6 +233,12 @@ int dcae_op_dwconv3x3(const float* x, int64_t x_ld, const float* wt, const float
 int dcae_op_spatial_gate(const float* s_out, int64_t s_ld, const float* x0, int64_t x0_ld,
                          const float* res_scale, const float* w7, int32_t C, int32_t B, int32_t h, int32_t w,
                          float* stats, float* out, int64_t out_ld, void* stream);
+/* The same with the LayerNorm that follows it in the module (lnx, dcae.py:487) fused in: the warp that produces a token's
+ * row also normalises it and writes LN(out) * gamma + beta as fp16 planes (ln_out16; NULL = no LayerNorm). */
+int dcae_op_spatial_gate_ln(const float* s_out, int64_t s_ld, const float* x0, int64_t x0_ld,
+                            const float* res_scale, const float* w7, int32_t C, int32_t B, int32_t h, int32_t w,
+                            float* stats, float* out, int64_t out_ld, const float* ln_gamma, const float* ln_beta,
+                            const dcae_planes* ln_out16, void* stream);
 /* Dictionary attention core (dcae.py:489-501): per head e (20 heads of 32):
  * out[t, e, :] = softmax_j( q[t, e, :] . K[e, j, :] * head_scale[e] ) V[e, j, :], j < 128.
  * The dictionary side is batch invariant (dcae.py:492-495) and prepared once per weight load:
