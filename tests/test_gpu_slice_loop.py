@@ -468,3 +468,29 @@ def test_fast_math_mode_f16_measured_tolerance(lively_params):
         enc = eng.compress(y, ls, lm)
         dec = eng.decompress(ls, lm, lambda i, idx: enc["symbols"][i])
         assert torch.equal(dec["indexes"], enc["indexes"]) and torch.equal(dec["y_hat"], enc["y_hat"])
+
+
+def test_f16x3_parity_holds_for_large_activations(lively_params):
+    """Advisor r1: the hi/lo fp16 planes were only exercised with O(1) activations.  Latents of magnitude ~50 and an
+    8 x wider x_trans push the pre-LayerNorm activations, the dense concat and the fc1 outputs into the hundreds to
+    thousands: slice 0 must still meet the fp32 bar against the CPU oracle, and the range check must report no clamp."""
+    from dcae_b200.entropy_model import EntropySliceLoop
+    p = {k: v.clone() for k, v in lively_params.items()}
+    p["dt_cross_attention.0.x_trans.weight"] *= 32.0
+    p["dt_cross_attention.0.mlp.fc1.weight"] *= 4.0
+    eng = EntropySliceLoop(p, device="cuda:0", math="f16x3")
+    gen = torch.Generator().manual_seed(314)
+    B, h, w = 1, 16, 24
+    y = 4 * torch.randn(B, 320, h, w, generator=gen)
+    ls, lm = 50 * torch.randn(B, 320, h, w, generator=gen), 50 * torch.randn(B, 320, h, w, generator=gen)
+    assert eng.check_f16_range(y.cuda(), ls.cuda(), lm.cuda()) == 0
+    enc = eng.compress(y.cuda(), ls.cuda(), lm.cuda())
+    _, mu0, sc0 = SliceLoopOracle(p).slice_params(0, ls, lm, [])
+    q0 = torch.cat([ls, lm], 1).permute(0, 2, 3, 1)            # slice 0's x_trans output, the widest pre-LayerNorm activation
+    big = float(torch.nn.functional.linear(q0, p["dt_cross_attention.0.x_trans.weight"], p["dt_cross_attention.0.x_trans.bias"]).abs().max())
+    e_mu, e_sc = rel_err(enc["means"][:, :64].cpu(), mu0), rel_err(enc["scales"][:, :64].cpu(), sc0)
+    print(f"\nlarge activations: max |x_trans output| {big:.0f}, slice-0 rel_err mu {e_mu:.2e} scale {e_sc:.2e}")
+    assert big > 300, big
+    assert e_mu < FP32_TOL and e_sc < FP32_TOL, (e_mu, e_sc)
+    with pytest.raises(Exception):          # and beyond the fp16 range the first call raises instead of clamping
+        EntropySliceLoop(p, device="cuda:0", math="f16x3").forward(y.cuda(), (ls * 1e5).cuda(), lm.cuda())
