@@ -30,7 +30,7 @@ class HostPipeline:
         dev = engine.device
         self.s_h2d, self.s_cmp, self.s_d2h = (torch.cuda.Stream(dev) for _ in range(3))
         shape = (B, 320, h, w)
-        self.dev_in = [[torch.empty(shape, device=dev) for _ in range(3)] for _ in range(depth)]
+        self.dev_in = [[torch.zeros(shape, device=dev) for _ in range(3)] for _ in range(depth)]     # zeros: the warm call below runs on them
         self.dev_out: List[Dict[str, torch.Tensor]] = []
         self.host_out: List[Dict[str, torch.Tensor]] = []
         keys = OUT_KEYS + (("symbols", "indexes") if want_symbols else ())
