@@ -13,7 +13,7 @@ MATH = {"fp32": 0, "tf32x3": 1, "tf32": 2, "f16x3": 3, "f16": 4}
 GC_EVAL, GC_NOISE, GC_DECODE = 0, 1, 2
 GC_LIK = {"fast": 0, "reference": 1}
 OPT_LIK_MATH, OPT_WANT_SYMBOLS = 0, 1
-ACT_NONE, ACT_GELU, ACT_HALF_TANH = 0, 1, 2
+ACT_NONE, ACT_GELU, ACT_HALF_TANH, ACT_RELU = 0, 1, 2, 3
 
 c_f32p = C.c_void_p   # device pointers travel as integers
 c_i32p = C.c_void_p
@@ -142,6 +142,9 @@ SIGNATURES = {
     "dcae_op_spatial_gate": (C.c_int, [_P, _I64, _P, _I64, _P, _P, _I32, _I32, _I32, _I32, _P, _P, _I64, _P]),
     "dcae_op_spatial_gate_ln": (C.c_int, [_P, _I64, _P, _I64, _P, _P, _I32, _I32, _I32, _I32, _P, _P, _I64, _P, _P, C.POINTER(Planes), _P]),
     "dcae_op_dict_attention": (C.c_int, [_P, _I64, C.POINTER(Planes), C.POINTER(DictKV), _I64, _P, _I64, C.POINTER(Planes), C.c_int, _P]),
+    "dcae_op_window_attention": (C.c_int, [_P, _I64, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P, _I32, _I32, _I32, _P, _I64, C.POINTER(Planes), _P]),
+    "dcae_op_space_to_depth": (C.c_int, [_P, _I64, _I32, _I32, _I32, _I32, _I32, _P, _I64, C.POINTER(Planes), _P]),
+    "dcae_op_depth_to_space": (C.c_int, [_P, _I64, _I32, _I32, _I32, _I32, _I32, _I32, _P, _I64, C.POINTER(Planes), _P]),
     "dcae_op_nchw_to_tokens": (C.c_int, [_P, _I32, _I32, _I64, _P, _I64, C.POINTER(Planes), _P]),
     "dcae_op_tokens_to_nchw": (C.c_int, [_P, _I64, _I32, _I32, _I64, _P, _P]),
     "dcae_op_tokens_to_nchw_i32": (C.c_int, [_P, _I64, _I32, _I32, _I64, _P, _P]),

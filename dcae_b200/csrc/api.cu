@@ -116,7 +116,7 @@ static int check_gemm_args(const dcae_operand* a, const dcae_weight* w, const dc
   DCAE_REQUIRE(a->B >= 0 && a->h >= 0 && a->w >= 0 && (int64_t)a->B * a->h * a->w < (1ll << 31), "dcae_op_gemm: bad token grid");
   DCAE_REQUIRE(a->ld % 4 == 0 && e->out_ld % 4 == 0 && aligned16(a->base) && aligned16(e->out), "dcae_op_gemm: operand/output must be 16-byte aligned, ld %% 4 == 0");
   DCAE_REQUIRE(a->col0 + a->k0 <= a->ld && (a->k1 == 0 || a->col1 + a->k1 <= a->ld), "dcae_op_gemm: operand columns exceed ld");
-  DCAE_REQUIRE(e->act >= DCAE_ACT_NONE && e->act <= DCAE_ACT_HALF_TANH, "dcae_op_gemm: bad activation %d", e->act);
+  DCAE_REQUIRE(e->act >= DCAE_ACT_NONE && e->act <= DCAE_ACT_RELU, "dcae_op_gemm: bad activation %d", e->act);
   DCAE_REQUIRE(e->act_cols % 4 == 0, "dcae_op_gemm: act_cols must be a multiple of 4");
   DCAE_REQUIRE((!e->addend || (aligned16(e->addend) && e->addend_ld % 4 == 0)) && (!e->residual || (aligned16(e->residual) && e->residual_ld % 4 == 0)) &&
                    aligned16(e->bias) && aligned16(e->res_scale),

@@ -150,6 +150,8 @@ int dict_attention_tcgen05(const float* q, int64_t q_ld, const dcae_dict_kv* kv,
                            dcae_planes out16, int passes, cudaStream_t s);
 int dict_attention_tcgen05_f16(const dcae_planes* q16, const dcae_dict_kv* kv, int64_t T, float* out, int64_t out_ld,
                                dcae_planes out16, cudaStream_t s);
+int layernorm_any(const float* x, int64_t x_ld, const float* gamma, const float* beta, int C, int64_t T, float* out, int64_t out_ld,
+                  dcae_planes o16, cudaStream_t s);
 int dict_attention_simt(const float* q, int64_t q_ld, const float* Kh, const float* Vh, const float* head_scale,
                         int64_t T, float* out, int64_t out_ld, cudaStream_t s);
 

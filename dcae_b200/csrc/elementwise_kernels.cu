@@ -354,10 +354,12 @@ extern "C" int dcae_op_layernorm(const float* x, int64_t x_ld, const float* gamm
   ProfileScope prof(DCAE_PROF_OTHER, 0.0, stream);
   const dcae_planes o16 = planes_or_null(out16);
   DCAE_REQUIRE(x && gamma && beta && (out || o16.hi) && planes_ok(out16), "dcae_op_layernorm: null pointer / bad planes");
-  DCAE_REQUIRE(C % 128 == 0 && C >= 128 && C <= 1024, "dcae_op_layernorm: C=%d must be a multiple of 128 in [128,1024]", C);
   DCAE_REQUIRE(aligned16(x) && aligned16(out) && aligned16(gamma) && aligned16(beta) && x_ld % 4 == 0 && out_ld % 4 == 0,
                "dcae_op_layernorm: 16-byte alignment required");
   if (T == 0) return DCAE_OK;
+  // the dictionary module's widths (multiples of 128) keep their fully unrolled kernel; the transform stacks'
+  // 96 / 144 / 192 channels (dcae.py:349,352) take the guarded one in transform_kernels.cu
+  if (C % 128 != 0 || C < 128 || C > 1024) return layernorm_any(x, x_ld, gamma, beta, C, T, out, out_ld, o16, (cudaStream_t)stream);
   const unsigned blocks = (unsigned)((T + 7) / 8);
   cudaStream_t s = (cudaStream_t)stream;
   switch (C / 128) {

@@ -19,6 +19,7 @@ struct SimtGemmParams {
 __device__ __forceinline__ float apply_act(float v, int act) {
   if (act == DCAE_ACT_GELU) return gelu_erf(v);
   if (act == DCAE_ACT_HALF_TANH) return 0.5f * tanhf(v);
+  if (act == DCAE_ACT_RELU) return fmaxf(v, 0.f);
   return v;
 }
 

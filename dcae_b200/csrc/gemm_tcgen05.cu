@@ -57,6 +57,7 @@ struct TcParams {
 __device__ __forceinline__ float act_apply(float v, int act) {
   if (act == DCAE_ACT_GELU) return gelu_erf(v);
   if (act == DCAE_ACT_HALF_TANH) return 0.5f * tanhf(v);
+  if (act == DCAE_ACT_RELU) return fmaxf(v, 0.f);
   return v;
 }
 

@@ -129,6 +129,9 @@ __device__ __forceinline__ void finalize_block(float* r, const dcae_epilogue& e,
   } else if (act == DCAE_ACT_HALF_TANH) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) r[j] = 0.5f * tanhf(r[j]);
+  } else if (act == DCAE_ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) r[j] = fmaxf(r[j], 0.f);
   }
   if (e.residual) {
     const float4* rp = reinterpret_cast<const float4*>(e.residual + token * e.residual_ld + n0);

@@ -216,6 +216,7 @@ __device__ __forceinline__ void warp_transpose32(float* r, int lane) {
 __device__ __forceinline__ float epi_act(float v, int act) {
   if (act == DCAE_ACT_GELU) return gelu_erf(v);
   if (act == DCAE_ACT_HALF_TANH) return 0.5f * tanhf(v);
+  if (act == DCAE_ACT_RELU) return fmaxf(v, 0.f);
   return v;
 }
 
@@ -282,6 +283,9 @@ __device__ __forceinline__ void epi_block(float* r, const dcae_epilogue& e, int 
   } else if (act == DCAE_ACT_HALF_TANH) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) r[j] = 0.5f * tanhf(r[j]);
+  } else if (act == DCAE_ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) r[j] = fmaxf(r[j], 0.f);
   }
   if (e.residual) {
 #pragma unroll

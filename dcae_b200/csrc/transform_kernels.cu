@@ -1,0 +1,321 @@
+// Token-major kernels of the transform stacks around the entropy model (SURVEY 8f N3 / N4:
+// /root/reference/models/dcae.py:152-383 blocks, :541-582 g_a / g_s / h_a / h_z_s1 / h_z_s2):
+//   * window attention of the Swin blocks (WMSA, dcae.py:228-298): W and SW (cyclic shift + mask) windows,
+//     relative position bias, softmax in registers, no sim / probs tensor in HBM;
+//   * LayerNorm for any channel count (the dictionary module's LayerNorm kernel needs C % 128 == 0);
+//   * space-to-depth / depth-to-space: a stride-2 convolution is a stride-1 3x3 convolution over the 2x2
+//     space-to-depth image and a stride-2 transposed convolution is a stride-1 3x3 convolution producing the four
+//     output phases (weights re-indexed at pack time, dcae_b200/transforms.py), so both run on the 3x3 implicit
+//     GEMM (kernel 2) unchanged.
+// All HBM-bound, fp32 in / fp32 (+ optional fp16 hi/lo planes) out, no atomics, deterministic.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace dcae {
+namespace {
+
+__device__ __forceinline__ void store_plane1(const dcae_planes& p, int64_t row, int col, float v) {
+  unsigned short h, l;
+  f16_split(v, h, l);
+  static_cast<unsigned short*>(p.hi)[row * p.ld + col] = h;
+  static_cast<unsigned short*>(p.lo)[row * p.ld + col] = l;
+}
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm, one warp per token, any C % 4 == 0 up to 1024 (V = ceil(C / 128) float4 per lane).
+// ---------------------------------------------------------------------------------------------
+template <int V>
+__global__ void __launch_bounds__(256) layernorm_any_kernel(const float* __restrict__ x, int64_t x_ld, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, int C4, int64_t T, float* __restrict__ out,
+                                                            int64_t out_ld, const dcae_planes o16) {
+  const int lane = threadIdx.x & 31;
+  const int64_t t = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (t >= T) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + t * x_ld);
+  float4 v[V];
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < V; ++k) {
+    const int c = lane + 32 * k;
+    v[k] = c < C4 ? __ldg(xr + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+  }
+  const float inv_c = 1.0f / (float)(4 * C4);
+  const float mean = warp_sum(s) * inv_c;
+  float q = 0.f;
+#pragma unroll
+  for (int k = 0; k < V; ++k) {
+    if (lane + 32 * k < C4) {
+      const float a = v[k].x - mean, b = v[k].y - mean, c = v[k].z - mean, d = v[k].w - mean;
+      q += (a * a + b * b) + (c * c + d * d);
+    }
+  }
+  const float rstd = 1.0f / sqrtf(warp_sum(q) * inv_c + 1e-5f);
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(beta);
+#pragma unroll
+  for (int k = 0; k < V; ++k) {
+    const int c = lane + 32 * k;
+    if (c < C4) {
+      const float4 g = __ldg(g4 + c), b = __ldg(b4 + c);
+      float4 o;
+      o.x = (v[k].x - mean) * rstd * g.x + b.x;
+      o.y = (v[k].y - mean) * rstd * g.y + b.y;
+      o.z = (v[k].z - mean) * rstd * g.z + b.z;
+      o.w = (v[k].w - mean) * rstd * g.w + b.w;
+      if (out) *reinterpret_cast<float4*>(out + t * out_ld + 4 * c) = o;
+      if (o16.hi) store_planes4(o16, t, 4 * c, o);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Window attention (dcae.py:262-291).  One block per window, heads in sequence; 4 threads per query row:
+// thread (i, c4) owns the keys j = c4 + 4 jj.  q, k, v of the head sit in shared memory (rows padded to HD + 1
+// floats: conflict-free for both access patterns), logits / probabilities stay in registers.
+// ---------------------------------------------------------------------------------------------
+struct WinArgs {
+  const float* qkv; int64_t ld; int q_col, k_col, v_col;
+  int n_heads, shift, B, h, w, nwx, nwy;
+  const float* rel;            // [n_heads, 2P-1, 2P-1]
+  float scale;
+  float* out; int64_t out_ld; dcae_planes o16;
+};
+
+template <int HD, int P>
+__global__ void __launch_bounds__(4 * P * P) window_attention_kernel(const WinArgs a) {
+  constexpr int PP = P * P, NJ = PP / 4, LDS = HD + 1, R = 2 * P - 1, DQ = HD / 4;
+  __shared__ float sq[PP * LDS], sk[PP * LDS], sv[PP * LDS];
+  __shared__ float sbias[R * R];
+  const int tid = threadIdx.x, i = tid >> 2, c4 = tid & 3;
+  const int wx = (int)(blockIdx.x % a.nwx), wy = (int)(blockIdx.x / a.nwx), b = (int)blockIdx.y;
+  const int py = i / P, px = i % P;
+  // rolled[r] = x[(r + shift) mod size] (torch.roll by -shift, dcae.py:270); the result goes back to the same token (:289)
+  int yy = wy * P + py + a.shift; if (yy >= a.h) yy -= a.h;
+  int xx = wx * P + px + a.shift; if (xx >= a.w) xx -= a.w;
+  const int64_t tok = ((int64_t)b * a.h + yy) * a.w + xx;
+  // SW mask (generate_mask, dcae.py:244-260): in the last window row / column the wrapped part may not see the rest
+  const bool last_row = a.shift > 0 && wy == a.nwy - 1, last_col = a.shift > 0 && wx == a.nwx - 1;
+  const int sp = P - a.shift;
+  for (int e = 0; e < a.n_heads; ++e) {
+    __syncthreads();
+    const float* row = a.qkv + tok * a.ld + e * HD;
+#pragma unroll
+    for (int d = 0; d < DQ; ++d) {
+      const int dd = c4 * DQ + d;
+      sq[i * LDS + dd] = __ldg(row + a.q_col + dd);
+      sk[i * LDS + dd] = __ldg(row + a.k_col + dd);
+      sv[i * LDS + dd] = __ldg(row + a.v_col + dd);
+    }
+    for (int t = tid; t < R * R; t += 4 * PP) sbias[t] = __ldg(a.rel + (int64_t)e * R * R + t);
+    __syncthreads();
+    float s[NJ];
+    float m = -INFINITY;
+#pragma unroll
+    for (int jj = 0; jj < NJ; ++jj) {
+      const int j = c4 + 4 * jj;
+      float acc = 0.f;
+#pragma unroll
+      for (int d = 0; d < HD; ++d) acc = fmaf(sq[i * LDS + d], sk[j * LDS + d], acc);
+      const int qy = j / P, qx = j % P;
+      acc = acc * a.scale + sbias[(py - qy + P - 1) * R + (px - qx + P - 1)];
+      const bool masked = (last_row && ((py < sp) != (qy < sp))) || (last_col && ((px < sp) != (qx < sp)));
+      s[jj] = masked ? -INFINITY : acc;
+      m = fmaxf(m, s[jj]);
+    }
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+    float sum = 0.f;
+#pragma unroll
+    for (int jj = 0; jj < NJ; ++jj) {
+      s[jj] = expf(s[jj] - m);
+      sum += s[jj];
+    }
+    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+    const float inv = 1.0f / sum;
+    float o[HD];
+#pragma unroll
+    for (int d = 0; d < HD; ++d) o[d] = 0.f;
+#pragma unroll
+    for (int jj = 0; jj < NJ; ++jj) {
+      const int j = c4 + 4 * jj;
+      const float pj = s[jj] * inv;
+#pragma unroll
+      for (int d = 0; d < HD; ++d) o[d] = fmaf(pj, sv[j * LDS + d], o[d]);
+    }
+#pragma unroll
+    for (int d = 0; d < HD; ++d) {
+      o[d] += __shfl_xor_sync(0xffffffffu, o[d], 1);
+      o[d] += __shfl_xor_sync(0xffffffffu, o[d], 2);
+    }
+#pragma unroll
+    for (int d = 0; d < HD; ++d) {
+      if (d / DQ == c4) {
+        if (a.out) a.out[tok * a.out_ld + e * HD + d] = o[d];
+        if (a.o16.hi) store_plane1(a.o16, tok, e * HD + d, o[d]);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// space-to-depth: out[(b, y', x'), (sy*2 + sx) * Cs + c] = x[(b, 2y' + sy, 2x' + sx), c]  (0 outside / for c >= C)
+// depth-to-space: out[(b, 2y + py, 2x + px), c] = x[(b, y, x), (py*2 + px) * Cs + c]     (0 for C <= c < Cpad)
+// one thread per output float4 (scalar variant when a channel count is not a multiple of 4)
+// ---------------------------------------------------------------------------------------------
+template <int VEC>
+__global__ void __launch_bounds__(256) space_to_depth_kernel(const float* __restrict__ x, int64_t ld, int C, int Cs, int B, int h, int w,
+                                                             int h2, int w2, float* __restrict__ out, int64_t out_ld, const dcae_planes o16) {
+  const int cv = Cs / VEC;                     // vectors per sub-pixel slot
+  const int64_t n = (int64_t)B * h2 * w2 * 4 * cv;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % cv) * VEC;
+    int64_t r = idx / cv;
+    const int sub = (int)(r & 3); r >>= 2;
+    const int x2 = (int)(r % w2); r /= w2;
+    const int y2 = (int)(r % h2);
+    const int b = (int)(r / h2);
+    const int yy = 2 * y2 + (sub >> 1), xx = 2 * x2 + (sub & 1);
+    const int64_t ot = ((int64_t)b * h2 + y2) * w2 + x2;
+    const bool in = yy < h && xx < w;
+    const float* src = x + (((int64_t)b * h + yy) * w + xx) * ld + c;
+    if (VEC == 4) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (in && c + 3 < C) v = __ldg(reinterpret_cast<const float4*>(src));
+      else if (in && c < C) { v.x = __ldg(src); if (c + 1 < C) v.y = __ldg(src + 1); if (c + 2 < C) v.z = __ldg(src + 2); }
+      if (out) *reinterpret_cast<float4*>(out + ot * out_ld + sub * Cs + c) = v;
+      if (o16.hi) store_planes4(o16, ot, sub * Cs + c, v);
+    } else {
+      const float v = (in && c < C) ? __ldg(src) : 0.f;
+      if (out) out[ot * out_ld + sub * Cs + c] = v;
+      if (o16.hi) store_plane1(o16, ot, sub * Cs + c, v);
+    }
+  }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256) depth_to_space_kernel(const float* __restrict__ x, int64_t ld, int Cs, int C, int Cpad, int B, int h, int w,
+                                                             float* __restrict__ out, int64_t out_ld, const dcae_planes o16) {
+  const int cv = Cpad / VEC;
+  const int H = 2 * h, W = 2 * w;
+  const int64_t n = (int64_t)B * H * W * cv;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % cv) * VEC;
+    int64_t r = idx / cv;
+    const int X = (int)(r % W); r /= W;
+    const int Y = (int)(r % H);
+    const int b = (int)(r / H);
+    const int sub = (Y & 1) * 2 + (X & 1);
+    const float* src = x + (((int64_t)b * h + (Y >> 1)) * w + (X >> 1)) * ld + sub * Cs + c;
+    const int64_t ot = ((int64_t)b * H + Y) * W + X;
+    if (VEC == 4) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c + 3 < C) v = __ldg(reinterpret_cast<const float4*>(src));
+      else if (c < C) { v.x = __ldg(src); if (c + 1 < C) v.y = __ldg(src + 1); if (c + 2 < C) v.z = __ldg(src + 2); }
+      if (out) *reinterpret_cast<float4*>(out + ot * out_ld + c) = v;
+      if (o16.hi) store_planes4(o16, ot, c, v);
+    } else {
+      const float v = c < C ? __ldg(src) : 0.f;
+      if (out) out[ot * out_ld + c] = v;
+      if (o16.hi) store_plane1(o16, ot, c, v);
+    }
+  }
+}
+
+inline unsigned grid_cap(int64_t n, int threads) {
+  int64_t b = (n + threads - 1) / threads;
+  const int64_t cap = (int64_t)num_sms() * 16;
+  return (unsigned)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace
+
+// called by dcae_op_layernorm (elementwise_kernels.cu) for channel counts its C % 128 == 0 kernel does not take
+int layernorm_any(const float* x, int64_t x_ld, const float* gamma, const float* beta, int C, int64_t T, float* out, int64_t out_ld,
+                  dcae_planes o16, cudaStream_t s) {
+  DCAE_REQUIRE(C % 4 == 0 && C >= 4 && C <= 1024, "dcae_op_layernorm: C=%d must be a multiple of 4 in [4,1024]", C);
+  const unsigned blocks = (unsigned)((T + 7) / 8);
+  const int C4 = C / 4;
+  switch ((C4 + 31) / 32) {
+#define LN_CASE(V) case V: layernorm_any_kernel<V><<<blocks, 256, 0, s>>>(x, x_ld, gamma, beta, C4, T, out, out_ld, o16); break;
+    LN_CASE(1) LN_CASE(2) LN_CASE(3) LN_CASE(4) LN_CASE(5) LN_CASE(6) LN_CASE(7) LN_CASE(8)
+#undef LN_CASE
+  }
+  DCAE_LAUNCH_CHECK();
+  return DCAE_OK;
+}
+
+}  // namespace dcae
+
+using namespace dcae;
+
+extern "C" int dcae_op_window_attention(const float* qkv, int64_t ld, int32_t q_col, int32_t k_col, int32_t v_col, int32_t C,
+                                        int32_t head_dim, int32_t window, int32_t shift, const float* rel_bias, int32_t B, int32_t h,
+                                        int32_t w, float* out, int64_t out_ld, const dcae_planes* out16, void* stream) {
+  ProfileScope prof(DCAE_PROF_ATTN, 4.0 * (double)B * h * w * (double)window * window * (double)C, stream);
+  const dcae_planes o16 = planes_or_null(out16);
+  DCAE_REQUIRE(qkv && rel_bias && (out || o16.hi) && planes_ok(out16), "dcae_op_window_attention: null pointer / bad planes");
+  DCAE_REQUIRE((window == 4 || window == 8) && (head_dim == 8 || head_dim == 16 || head_dim == 32),
+               "dcae_op_window_attention: window %d / head_dim %d not supported (window 4 or 8, head_dim 8, 16 or 32)", window, head_dim);
+  DCAE_REQUIRE(C > 0 && C % head_dim == 0, "dcae_op_window_attention: C=%d is not a multiple of head_dim=%d", C, head_dim);
+  DCAE_REQUIRE(B >= 0 && h > 0 && w > 0 && h % window == 0 && w % window == 0,
+               "dcae_op_window_attention: the token grid %dx%d must be a multiple of the window %d (dcae.py:271)", h, w, window);
+  DCAE_REQUIRE(shift == 0 || shift == window / 2, "dcae_op_window_attention: shift must be 0 (W) or window/2 (SW)");
+  DCAE_REQUIRE(q_col >= 0 && k_col >= 0 && v_col >= 0 && q_col + C <= ld && k_col + C <= ld && v_col + C <= ld && (!out || out_ld >= C),
+               "dcae_op_window_attention: column windows exceed the leading dimension");
+  DCAE_REQUIRE(B <= 65535, "dcae_op_window_attention: batch too large");
+  if (B == 0) return DCAE_OK;
+  WinArgs a;
+  a.qkv = qkv; a.ld = ld; a.q_col = q_col; a.k_col = k_col; a.v_col = v_col;
+  a.n_heads = C / head_dim; a.shift = shift; a.B = B; a.h = h; a.w = w; a.nwx = w / window; a.nwy = h / window;
+  a.rel = rel_bias; a.scale = 1.0f / sqrtf((float)head_dim);
+  a.out = out; a.out_ld = out_ld; a.o16 = o16;
+  const dim3 grid((unsigned)(a.nwx * a.nwy), (unsigned)B);
+  cudaStream_t s = (cudaStream_t)stream;
+#define WIN_CASE(HD, P) if (head_dim == HD && window == P) window_attention_kernel<HD, P><<<grid, 4 * P * P, 0, s>>>(a);
+  WIN_CASE(8, 4) WIN_CASE(16, 4) WIN_CASE(32, 4) WIN_CASE(8, 8) WIN_CASE(16, 8) WIN_CASE(32, 8)
+#undef WIN_CASE
+  DCAE_LAUNCH_CHECK();
+  return DCAE_OK;
+}
+
+extern "C" int dcae_op_space_to_depth(const float* x, int64_t ld, int32_t C, int32_t Cs, int32_t B, int32_t h, int32_t w, float* out,
+                                      int64_t out_ld, const dcae_planes* out16, void* stream) {
+  ProfileScope prof(DCAE_PROF_OTHER, 0.0, stream);
+  const dcae_planes o16 = planes_or_null(out16);
+  DCAE_REQUIRE(x && (out || o16.hi) && planes_ok(out16), "dcae_op_space_to_depth: null pointer / bad planes");
+  DCAE_REQUIRE(C > 0 && Cs >= C && Cs % 4 == 0 && ld >= C && (!out || out_ld >= 4 * Cs) && (!o16.hi || o16.ld >= 4 * Cs) && out_ld % 4 == 0 && aligned16(out),
+               "dcae_op_space_to_depth: need C <= Cs, Cs %% 4 == 0, out_ld >= 4 Cs (multiple of 4), 16-byte aligned output");
+  DCAE_REQUIRE(B >= 0 && h > 0 && w > 0, "dcae_op_space_to_depth: bad token grid");
+  const int h2 = (h + 1) / 2, w2 = (w + 1) / 2;
+  const int64_t n4 = (int64_t)B * h2 * w2 * Cs;      // float4 outputs (4 sub-pixels x Cs / 4)
+  if (n4 == 0) return DCAE_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (ld % 4 == 0 && aligned16(x))
+    space_to_depth_kernel<4><<<grid_cap(n4, 256), 256, 0, s>>>(x, ld, C, Cs, B, h, w, h2, w2, out, out_ld, o16);
+  else
+    space_to_depth_kernel<1><<<grid_cap(n4 * 4, 256), 256, 0, s>>>(x, ld, C, Cs, B, h, w, h2, w2, out, out_ld, o16);
+  DCAE_LAUNCH_CHECK();
+  return DCAE_OK;
+}
+
+extern "C" int dcae_op_depth_to_space(const float* x, int64_t ld, int32_t Cs, int32_t C, int32_t Cpad, int32_t B, int32_t h, int32_t w,
+                                      float* out, int64_t out_ld, const dcae_planes* out16, void* stream) {
+  ProfileScope prof(DCAE_PROF_OTHER, 0.0, stream);
+  const dcae_planes o16 = planes_or_null(out16);
+  DCAE_REQUIRE(x && (out || o16.hi) && planes_ok(out16), "dcae_op_depth_to_space: null pointer / bad planes");
+  DCAE_REQUIRE(C > 0 && Cs >= C && Cpad >= C && ld >= 4 * Cs && (!out || out_ld >= Cpad) && (!o16.hi || o16.ld >= Cpad),
+               "dcae_op_depth_to_space: need C <= Cs, C <= Cpad <= out_ld, ld >= 4 Cs");
+  DCAE_REQUIRE(B >= 0 && h > 0 && w > 0, "dcae_op_depth_to_space: bad token grid");
+  const int64_t n = (int64_t)B * 4 * h * w * Cpad;
+  if (n == 0) return DCAE_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (Cpad % 4 == 0 && Cs % 4 == 0 && ld % 4 == 0 && out_ld % 4 == 0 && aligned16(x) && aligned16(out))
+    depth_to_space_kernel<4><<<grid_cap(n / 4, 256), 256, 0, s>>>(x, ld, Cs, C, Cpad, B, h, w, out, out_ld, o16);
+  else
+    depth_to_space_kernel<1><<<grid_cap(n, 256), 256, 0, s>>>(x, ld, Cs, C, Cpad, B, h, w, out, out_ld, o16);
+  DCAE_LAUNCH_CHECK();
+  return DCAE_OK;
+}

@@ -177,7 +177,7 @@ typedef struct {
 } dcae_operand;
 int64_t dcae_planes_bytes(int64_t T, int32_t cols);
 
-enum { DCAE_ACT_NONE = 0, DCAE_ACT_GELU = 1, DCAE_ACT_HALF_TANH = 2 };
+enum { DCAE_ACT_NONE = 0, DCAE_ACT_GELU = 1, DCAE_ACT_HALF_TANH = 2, DCAE_ACT_RELU = 3 /* dcae.py:135-140 */ };
 
 /* out[t, n] = act_n( acc[t, n] + bias[n] + addend[t, n] ) + residual[t, n] * res_scale[n]
  * act applies to columns n < act_cols (all columns if act_cols <= 0 or >= N).
@@ -215,7 +215,8 @@ int dcae_split_f16_weight(const float* w, int32_t N, int32_t taps, int32_t kc, f
 int dcae_op_gemm(const dcae_operand* a, const dcae_weight* w, const dcae_epilogue* e, int math, void* stream);
 int dcae_split_tf32(const float* w, float* w_hi, float* w_lo, int64_t n, void* stream);
 
-/* LayerNorm over C channels per token, eps 1e-5 (dcae.py:461,465,467,471). */
+/* LayerNorm over C channels per token, eps 1e-5 (dcae.py:461,465,467,471; the Swin blocks' ln1 / ln2, :349,352).
+ * C: any multiple of 4 up to 1024. */
 int dcae_op_layernorm(const float* x, int64_t x_ld, const float* gamma, const float* beta, int32_t C,
                       int64_t T, float* out, int64_t out_ld, const dcae_planes* out16, void* stream);
 /* out = gelu(x) (exact erf form), [T, C] (dcae.py:421-423 prologue GELU of the dense block). */
@@ -267,6 +268,33 @@ int dcae_op_nchw_to_tokens(const float* src, int32_t B, int32_t C, int64_t HW, f
 int dcae_op_tokens_to_nchw(const float* src, int64_t src_ld, int32_t B, int32_t C, int64_t HW, float* dst, void* stream);
 int dcae_op_tokens_to_nchw_i32(const int32_t* src, int64_t src_ld, int32_t B, int32_t C, int64_t HW, int32_t* dst, void* stream);
 int dcae_op_nchw_to_tokens_i32(const int32_t* src, int32_t B, int32_t C, int64_t HW, int32_t* dst, int64_t dst_ld, void* stream);
+
+/* --------------------------------------------------------------------------------------------
+ * Operators of the transform stacks around the entropy model (h_a, h_z_s1, h_z_s2, g_a, g_s;
+ * dcae.py:152-383, 541-582).  dcae_b200/transforms.py composes them with dcae_op_gemm / layernorm / dwconv3x3.
+ * ------------------------------------------------------------------------------------------*/
+
+/* WMSA core (dcae.py:262-291) on a token grid, windows of `window` x `window` tokens (4 or 8), heads of head_dim
+ * (8, 16 or 32) channels:
+ *   out[t, e*hd : (e+1)*hd] = softmax_j( q_e[t] . k_e[j] / sqrt(hd) + rel_bias[e, dy, dx] (+ SW mask) ) v_e[j]
+ * over the tokens j of t's window.  q / k / v of head e are the columns q_col / k_col / v_col + e*hd of `qkv`
+ * (the '(threeh c)' order of embedding_layer, :275-276).  shift = 0: W windows; shift = window / 2: SW windows,
+ * i.e. the cyclic roll of :270 / :289 and generate_mask (:244-260) folded into the indexing.  rel_bias is
+ * relative_position_params as the state dict holds it, [n_heads, 2*window-1, 2*window-1] contiguous (:240, 293-296).
+ * h and w must be multiples of window. */
+int dcae_op_window_attention(const float* qkv, int64_t ld, int32_t q_col, int32_t k_col, int32_t v_col, int32_t C,
+                             int32_t head_dim, int32_t window, int32_t shift, const float* rel_bias, int32_t B, int32_t h,
+                             int32_t w, float* out, int64_t out_ld, const dcae_planes* out16, void* stream);
+/* out[(b, y', x'), (sy*2 + sx)*Cs + c] = x[(b, 2y' + sy, 2x' + sx), c] for c < C, 0 elsewhere (c >= C, odd edge);
+ * output grid ceil(h/2) x ceil(w/2), 4*Cs columns.  With the weights re-indexed at pack time a stride-2 k x k
+ * convolution (conv(), dcae.py:35-42) becomes a stride-1 3x3 convolution over this image (dcae_op_gemm, taps = 9). */
+int dcae_op_space_to_depth(const float* x, int64_t ld, int32_t C, int32_t Cs, int32_t B, int32_t h, int32_t w, float* out,
+                           int64_t out_ld, const dcae_planes* out16, void* stream);
+/* out[(b, 2y + py, 2x + px), c] = x[(b, y, x), (py*2 + px)*Cs + c] for c < C, 0 for C <= c < Cpad; output grid
+ * 2h x 2w.  A stride-2 transposed convolution (deconv(), dcae.py:44-52) is a stride-1 3x3 convolution producing
+ * the four output phases as 4*Cs channels, then this rearrangement. */
+int dcae_op_depth_to_space(const float* x, int64_t ld, int32_t Cs, int32_t C, int32_t Cpad, int32_t B, int32_t h, int32_t w,
+                           float* out, int64_t out_ld, const dcae_planes* out16, void* stream);
 
 /* Coder hand-off (replaces the per-slice `.tolist()` of dcae.py:742-743 on the device side): the int32
  * symbols / indexes of a compress() call, in coder order, packed to int16 / uint8 for one small D2H copy.  Symbols

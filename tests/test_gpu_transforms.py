@@ -1,0 +1,206 @@
+"""The transform stacks around the entropy model on the CUDA library: new kernels one by one
+against torch / the restated operator contract, every stack against the reference's own module outputs (golden fixture
++ the real classes when staged), and the full reference `DCAE` with every sub-module on the library."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from _emul_kernels import TorchKernels
+from _util import mismatch_rate, rel_err
+from dcae_b200 import _lib
+from dcae_b200.transforms import (STACKS, Act, LibKernels, TransformStack, conv_s2_to_gemm, deconv_s2_to_gemm, init_transform_params,
+                                  linear_to_gemm, pad8, pad32)
+from oracle.reference_loader import load_reference_dcae_module, reference_available
+
+pytestmark = pytest.mark.gpu
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+DEV = "cuda:0"
+# fp32-parity modes; the stacks are ~90 dependent dense layers deep, so the per-tensor bound is looser than one layer's
+STACK_TOL = {"f16x3": 5e-5, "fp32": 2e-5}
+
+
+def _gen(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+def _act(t2d, B, h, w):
+    return Act(t2d.to(DEV).contiguous(), B, h, w)
+
+
+@pytest.mark.parametrize("C", [4, 96, 144, 192, 320, 256])
+def test_layernorm_any_channel_count(C):
+    K = LibKernels(DEV)
+    ld = pad32(C)
+    x = torch.zeros(1000, ld)
+    x[:, :C] = 3.0 * torch.randn(1000, C, generator=_gen(C)) + 0.7
+    g, b = torch.randn(C, generator=_gen(C + 1)), torch.randn(C, generator=_gen(C + 2))
+    got = K.layernorm(_act(x, 1, 10, 100), K.vector(g), K.vector(b), C).buf.cpu()
+    want = F.layer_norm(x[:, :C], (C,), g, b, 1e-5)
+    assert rel_err(got[:, :C], want) < 2e-6
+    assert float(got[:, C:].abs().max()) == 0.0 if ld > C else True
+
+
+@pytest.mark.parametrize("hd,window,shift", [(8, 8, 0), (8, 8, 4), (16, 8, 4), (32, 8, 0), (32, 8, 4), (32, 4, 0), (32, 4, 2), (16, 4, 2), (8, 4, 0)])
+def test_window_attention_against_the_restated_contract(hd, window, shift):
+    """dcae_op_window_attention == WMSA's core (dcae.py:262-291) as restated in tests/_emul_kernels.py (which the CPU suite
+    pins against the reference modules): relative position bias, SW roll + mask, per-head softmax."""
+    heads, B, h, w = 3, 2, 3 * window, 2 * window
+    C = heads * hd
+    cp = pad32(C)
+    g = _gen(hd * 100 + window * 10 + shift)
+    qkv = torch.zeros(B * h * w, 3 * cp)
+    for j in range(3):
+        qkv[:, j * cp:j * cp + C] = 1.5 * torch.randn(B * h * w, C, generator=g)
+    rel = torch.randn(heads, 2 * window - 1, 2 * window - 1, generator=g)
+    want = TorchKernels().window_attention(Act(qkv, B, h, w), C, cp, hd, window, shift, rel).buf
+    K = LibKernels(DEV)
+    got = K.window_attention(_act(qkv, B, h, w), C, cp, hd, window, shift, K.tensor(rel)).buf.cpu()
+    assert rel_err(got, want) < 2e-6
+
+
+@pytest.mark.skipif(not reference_available(), reason="reference models/dcae.py not staged")
+@pytest.mark.parametrize("typ", ["W", "SW"])
+def test_window_attention_inside_the_reference_wmsa(typ):
+    """The reference's own WMSA module (dcae.py:228-298) with its embedding / output Linear layers run by torch and only the
+    core replaced by the kernel."""
+    ref = load_reference_dcae_module()
+    torch.manual_seed(4)
+    C, hd, P, B, h, w = 96, 16, 8, 2, 16, 24
+    m = ref.WMSA(C, C, hd, P, typ).eval()
+    with torch.no_grad():
+        m.relative_position_params.copy_(0.5 * torch.randn(m.relative_position_params.shape))
+        x = torch.randn(B, h, w, C)
+        want = m(x)
+        qkv = m.embedding_layer(x).reshape(B * h * w, 3 * C)
+        K = LibKernels(DEV)
+        core = K.window_attention(_act(qkv, B, h, w), C, C, hd, P, P // 2 if typ == "SW" else 0, K.tensor(m.relative_position_params)).buf.cpu()
+        got = m.linear(core).reshape(B, h, w, C)
+    assert rel_err(got, want) < 2e-6
+
+
+@pytest.mark.parametrize("C,ld,hw", [(3, 4, (8, 12)), (3, 3, (7, 9)), (96, 96, (7, 10)), (144, 160, (6, 8))])
+def test_space_to_depth_and_depth_to_space(C, ld, hw):
+    B, (h, w) = 2, hw
+    x = torch.zeros(B * h * w, ld)
+    x[:, :C] = torch.randn(B * h * w, C, generator=_gen(C + h))
+    cs = pad8(C)
+    E, K = TorchKernels(), LibKernels(DEV)
+    want = E.space_to_depth(Act(x, B, h, w), C, cs)
+    got = K.space_to_depth(_act(x, B, h, w), C, cs)
+    assert (got.h, got.w) == (want.h, want.w) and torch.equal(got.buf.cpu(), want.buf)
+    cpad = pad32(C) if C > 4 else 4
+    back_w = E.depth_to_space(want, cs, C, cpad)
+    back_g = K.depth_to_space(got, cs, C, cpad)
+    assert (back_g.h, back_g.w) == (back_w.h, back_w.w) and torch.equal(back_g.buf.cpu(), back_w.buf)
+
+
+@pytest.mark.parametrize("math", ["f16x3", "fp32"])
+def test_relu_epilogue_and_narrow_layers(math):
+    """DCAE_ACT_RELU and the small layer shapes the transform stacks bring (N = 32 / 64 / 96 / 160, K = 32 / 64 / 96 / 160)."""
+    K = LibKernels(DEV, math)
+    E = TorchKernels()
+    B, h, w = 2, 9, 11
+    for N, k in ((32, 96), (64, 32), (96, 64), (160, 160)):
+        g = _gen(N + k)
+        x = torch.randn(B * h * w, k, generator=g)
+        wt, b = torch.randn(N, k, generator=g) / k ** 0.5, torch.randn(N, generator=g)
+        res = torch.randn(B * h * w, N, generator=g)
+        want = E.gemm(Act(x, B, h, w), E.pack_gemm(wt, b), act=_lib.ACT_RELU, residual=Act(res, B, h, w)).buf
+        got = K.gemm(_act(x, B, h, w), K.pack_gemm(wt, b), act=_lib.ACT_RELU, residual=_act(res, B, h, w)).buf.cpu()
+        assert rel_err(got, want) < 1e-5, (N, k)
+        assert float((got - res).min()) >= 0.0
+
+
+@pytest.mark.parametrize("math", ["f16x3", "fp32"])
+@pytest.mark.parametrize("k", [3, 5])
+def test_stride2_conv_and_transposed_conv_on_the_library(math, k):
+    g = _gen(50 + k)
+    K = LibKernels(DEV, math)
+    cin, cout, B, h, w = 96, 144, 2, 10, 14
+    wt, b = torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5, torch.randn(cout, generator=g)
+    x = torch.randn(B, cin, h, w, generator=g)
+    want = F.conv2d(x, wt, b, stride=2, padding=k // 2)
+    cs = pad8(cin)
+    a = K.gemm(K.space_to_depth(K.to_tokens(x, pad32(cin)), cin, cs), K.pack_gemm(conv_s2_to_gemm(wt, pad32(cout), cs), b, taps=9))
+    assert rel_err(K.to_nchw(a, cout).cpu(), want) < 1e-5
+    wt2, b2 = torch.randn(cin, cout, k, k, generator=g) / (cin * k * k / 4) ** 0.5, torch.randn(cout, generator=g)
+    want2 = F.conv_transpose2d(x, wt2, b2, stride=2, padding=k // 2, output_padding=1)
+    cso = pad8(cout)
+    pg = K.pack_gemm(deconv_s2_to_gemm(wt2, cso, pad32(cin)), torch.cat([b2, b2.new_zeros(cso - cout)]).repeat(4), taps=9)
+    a2 = K.depth_to_space(K.gemm(K.to_tokens(x, pad32(cin)), pg), cso, cout, pad32(cout))
+    assert rel_err(K.to_nchw(a2, cout).cpu(), want2) < 1e-5
+
+
+@pytest.mark.parametrize("math", ["f16x3", "fp32"])
+@pytest.mark.parametrize("stack", STACKS)
+def test_stack_against_the_reference_golden(stack, math):
+    """Every stack on the kernels against tests/golden/transforms.npz = outputs of the reference's own modules (CPU fp32)."""
+    from make_golden_transforms import transform_golden_input
+    want = torch.from_numpy(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "transforms.npz"))[stack])
+    ts = TransformStack(stack, init_transform_params(0, (stack,)), device=DEV, math=math)
+    got = ts.forward(transform_golden_input(stack).to(DEV)).cpu()
+    err = rel_err(got, want)
+    print(f"\n{stack}[{math}] vs the reference module's golden output: {err:.2e}")
+    assert got.shape == want.shape and err < STACK_TOL[math]
+
+
+@pytest.mark.skipif(not reference_available(), reason="reference models/dcae.py not staged")
+@pytest.mark.parametrize("stack,shape", [("g_a", (2, 3, 256, 384)), ("g_s", (2, 320, 16, 24)), ("h_a", (2, 320, 32, 48)), ("h_z_s1", (2, 192, 8, 12))])
+def test_stack_against_the_reference_module_kodak_sized_tiles(stack, shape):
+    """Larger, non-square, B = 2: the reference's real module (CPU fp32) on the same weights and input."""
+    ref = load_reference_dcae_module()
+    torch.manual_seed(0)
+    net = ref.DCAE().eval()
+    P = init_transform_params(1, (stack,))
+    torch.nn.Module.load_state_dict(net, P, strict=False)
+    x = torch.rand(shape, generator=_gen(9)) if stack == "g_a" else torch.randn(shape, generator=_gen(9))
+    with torch.no_grad():
+        want = getattr(net, stack)(x)
+    ts = TransformStack(stack, P, device=DEV, math="f16x3")
+    got = ts.forward(x.to(DEV)).cpu()
+    err = rel_err(got, want)
+    print(f"\n{stack} {shape}: f16x3 kernels vs the reference module (CPU fp32): {err:.2e}")
+    assert err < STACK_TOL["f16x3"]
+    # determinism and batch invariance: image 1 alone gives the same bits
+    again = ts.forward(x[1:].to(DEV)).cpu()
+    assert torch.equal(again[0], got[1])
+
+
+@pytest.mark.skipif(not reference_available(), reason="reference models/dcae.py not staged")
+def test_full_reference_dcae_with_every_submodule_on_the_library(lively_params):
+    """`DCAE.forward` (dcae.py:623-677) as written, with g_a / h_a / h_z_s1 / h_z_s2 / g_s (accelerate_transforms), the slice-loop
+    modules + GaussianConditional (accelerate) and the EntropyBottleneck all on libdcae_b200.so, against the untouched
+    class run by torch on the same GPU with the reference's evaluation flags."""
+    from dcae_b200 import EntropyBottleneck, accelerate
+    from dcae_b200.transforms import accelerate_transforms
+    from oracle.reference_loader import build_reference_net
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cudnn.enabled = False
+    try:
+        P = dict(lively_params)
+        P.update(init_transform_params(2))
+        plain = build_reference_net(P).cuda()
+        fast = build_reference_net(P).cuda()
+        accelerate(fast, device=DEV, math="f16x3")
+        stacks = accelerate_transforms(fast, device=DEV, math="f16x3")
+        x = torch.rand(1, 3, 256, 256, generator=_gen(1234)).cuda()
+        lib = _lib.load()
+        n0 = lib.dcae_launch_count()
+        with torch.no_grad():
+            want, got = plain(x), fast(x)
+        assert set(stacks) == set(STACKS)
+        e_y = rel_err(got["para"]["y"], want["para"]["y"])
+        e_x = rel_err(got["x_hat"], want["x_hat"])
+        flips = mismatch_rate(torch.round(got["para"]["y"] - got["para"]["means"]), torch.round(want["para"]["y"] - want["para"]["means"]))
+        print(f"\nfull DCAE on the library vs the untouched class: y {e_y:.2e}, x_hat {e_x:.2e}, symbol flips {flips:.2e}")
+        assert e_y < STACK_TOL["f16x3"]
+        assert flips < 2e-3
+        if flips == 0.0:
+            assert e_x < 1e-4
+    finally:
+        torch.backends.cudnn.enabled = True
