@@ -45,6 +45,9 @@ CONFIGS = {
             workload="DCAE entropy-model rate-distortion training step (MSE lambda = 0.013: forward, train.py:82-88 loss, backward, grad clip 1.0, Adam) on 8 x 256x256 crops per GPU, DDP gradient all-reduce over NCCL (BASELINE config #4)"),
     5: dict(H=2160, W=3840, batch=4, mode="forward", tag="3840x2160",
             workload="DCAE entropy-model forward (slice loop), synthetic 4K 3840x2160 images, 4 per GPU per step (BASELINE config #5)"),
+    # beyond the north star: the WHOLE model -- g_a, h_a, entropy bottleneck, h_z_s1 / h_z_s2, slice loop, g_s
+    6: dict(H=512, W=768, batch=16, mode="codec", tag="768x512 (whole codec)",
+            workload="whole DCAE.forward (g_a, h_a, EntropyBottleneck, h_z_s1, h_z_s2, slice loop, g_s: dcae.py:623-677), batch 16 synthetic 768x512 images per GPU"),
 }
 
 
@@ -492,6 +495,199 @@ def run_training(args):
         dist.destroy_process_group()
 
 
+# ---- config 6: the whole model on the library ------------------------------------------------------
+def _codec_params(seed=0):
+    from dcae_b200.params import init_entropy_params
+    from dcae_b200.transforms import init_transform_params
+    P = dict(init_entropy_params(seed, "lively"))
+    P.update(init_transform_params(seed))
+    return P
+
+
+def reference_codec_rate(cfg, device, n_images, steps, warmup):
+    """The reference's own `DCAE.forward` (unmodified models/dcae.py staged in oracle/_ref; EntropyBottleneck = the loader's
+    stub, GaussianConditional = the oracle restatement: compressai is absent) by eager PyTorch, fp32, the reference's
+    evaluation flags.  -> (images/s, seconds per step) or (None, None) without the staged file."""
+    from oracle import reference_loader as rl
+    if not rl.reference_available():
+        return None, None
+    saved = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32, torch.backends.cudnn.enabled)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cudnn.enabled = False
+    try:
+        net = rl.build_reference_net(_codec_params()).to(device)
+        x = torch.rand(n_images, 3, (cfg["H"] + 127) // 128 * 128, (cfg["W"] + 127) // 128 * 128, generator=torch.Generator().manual_seed(1234)).to(device)
+        cuda = torch.device(device).type == "cuda"
+        with torch.no_grad():
+            for _ in range(warmup):
+                net(x)
+            if cuda:
+                torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                net(x)
+            if cuda:
+                torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / max(steps, 1)
+        return n_images / dt, dt
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32, torch.backends.cudnn.enabled = saved
+
+
+def run_codec(args):
+    """config 6: `dcae_b200.DCAECodec.forward` = the reference's whole `DCAE.forward` on the library, images sharded over
+    the ranks like the slice loop (no data-path collective)."""
+    cfg = CONFIGS[6]
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    from dcae_b200 import _lib
+    from dcae_b200.codec import DCAECodec
+    lib = _lib.load()
+    B = args.batch or cfg["batch"]
+    H, W = (cfg["H"] + 127) // 128 * 128, (cfg["W"] + 127) // 128 * 128
+    codec = DCAECodec(_codec_params(), device=dev, math=args.math, lanes=args.lanes)
+    host_x = torch.rand(B, 3, H, W, generator=torch.Generator().manual_seed(1234 + rank)).pin_memory()
+    dev_x = host_x.to(dev)
+    host_out = torch.empty(B, 3, H, W).pin_memory()
+    host_bits = torch.empty(2).pin_memory()
+
+    def step_resident():
+        return codec.forward(dev_x)
+
+    def step_e2e():
+        x = host_x.to(dev, non_blocking=True)
+        o = codec.forward(x)
+        host_out.copy_(o["x_hat"], non_blocking=True)
+        host_bits.copy_(torch.stack([o["log2_lik_sum_y"].reshape(()), torch.log2(o["likelihoods"]["z"]).sum()]), non_blocking=True)
+        return o
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        barrier()
+        return float(ms) / steps
+
+    sampler = ClockSampler(local) if rank == 0 and not args.no_clock_sampler else None
+    warm = max(args.warmup, 3)
+    t_w = time.perf_counter()
+    n_warm = 0
+    while n_warm < warm or (time.perf_counter() - t_w) < args.warmup_seconds:
+        step_resident()
+        torch.cuda.synchronize()
+        n_warm += 1
+    if sampler:
+        sampler.mark()
+    ms_step = timed(step_resident, args.steps)
+    clocks = sampler.stop() if sampler else None
+    ms_e2e = timed(step_e2e, args.steps)
+
+    # launches of one step: the library's counter restarts when the slice loop loads its inputs, so read it on both sides
+    torch.cuda.synchronize()
+    c_prev = int(lib.dcae_launch_count())
+    y = codec.stacks["g_a"](dev_x)
+    z = codec.stacks["h_a"](y)
+    z_hat, _ = codec.entropy_bottleneck(z, training=False)
+    ls, lm = codec.stacks["h_z_s1"](z_hat), codec.stacks["h_z_s2"](z_hat)
+    c_front = int(lib.dcae_launch_count()) - c_prev
+    o = codec.loop.forward(y, ls, lm)
+    codec.stacks["g_s"](o["y_hat"])
+    launches = c_front + int(lib.dcae_launch_count())
+    torch.cuda.synchronize()
+
+    # where the step goes: CUDA events around the stages, and the library's per-family profile (every op timed alone)
+    def stage_times():
+        names = ("g_a", "h_a", "entropy_bottleneck", "h_z_s1", "h_z_s2", "slice_loop", "g_s")
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
+        ev[0].record()
+        y = codec.stacks["g_a"](dev_x); ev[1].record()
+        z = codec.stacks["h_a"](y); ev[2].record()
+        z_hat, _ = codec.entropy_bottleneck(z, training=False); ev[3].record()
+        ls = codec.stacks["h_z_s1"](z_hat); ev[4].record()
+        lm = codec.stacks["h_z_s2"](z_hat); ev[5].record()
+        o = codec.loop.forward(y, ls, lm); ev[6].record()
+        codec.stacks["g_s"](o["y_hat"]); ev[7].record()
+        torch.cuda.synchronize()
+        return {n: ev[i].elapsed_time(ev[i + 1]) for i, n in enumerate(names)}
+    stages = stage_times() if rank == 0 else None
+    fam = None
+    if rank == 0:
+        import ctypes as C
+        ms = (C.c_double * 4)(); work = (C.c_double * 4)(); ln = (C.c_int64 * 4)()
+        saved_lanes = codec.loop.lanes
+        codec.loop.lanes = 1
+        _lib.check(lib.dcae_profile_start(), "profile_start")
+        codec.forward(dev_x)
+        torch.cuda.synchronize()
+        _lib.check(lib.dcae_profile_stop(ms, work, ln), "profile_stop")
+        codec.loop.lanes = saved_lanes
+        fam = {n: {"ms_per_step": ms[i], "launches_per_step": int(ln[i]), "work_per_step": work[i]} for i, n in enumerate(("gemm", "attention", "gc", "other"))}
+    peaks = load_peaks()
+    cpu_baseline = torch_gpu_baseline = None
+    if rank == 0 and not args.no_gpu_baseline:
+        try:
+            n_g = min(B, 4)
+            rate, dt = reference_codec_rate(cfg, dev, n_g, 3, 1)
+            if rate:
+                torch_gpu_baseline = {"value": rate, "unit": "images/s", "ms_per_step": dt * 1e3, "kind": "reference",
+                                      "sample": f"3 steps x {n_g} images of 768x512 after 1 warm-up: the reference's own DCAE.forward by eager PyTorch on this GPU (fp32, TF32 off, cuDNN off: eval.py:3182-3187, 3904)"}
+        except Exception as e:                      # noqa: BLE001
+            torch_gpu_baseline = {"value": None, "error": repr(e)[:200]}
+    if rank == 0 and not args.no_cpu_baseline:
+        torch.set_num_threads(os.cpu_count() or 1)
+        rate, dt = reference_codec_rate(cfg, "cpu", 1, 1, 0)
+        if rate:
+            cpu_baseline = {"value": rate, "unit": "images/s", "cores": os.cpu_count(), "kind": "reference", "ms_per_step": dt * 1e3,
+                            "sample": "1 step x 1 image of 768x512, no warm-up: the reference's own DCAE.forward, torch fp32 on all host threads"}
+    if rank == 0:
+        imgs = B * world
+        g = fam["gemm"] if fam else None
+        achieved = (g["work_per_step"] / (g["ms_per_step"] * 1e-3) / 1e12) if g and g["ms_per_step"] > 0 else None
+        peak = peaks["tc_sustained"]
+        line = {
+            "metric": "whole-codec images/sec @768x512", "value": imgs / (ms_step * 1e-3), "unit": "images/s",
+            "n_gpus": world, "steps": args.steps, "warmup": warm, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 (fp16 hi+lo planes = 22-bit operands, 3-pass tcgen05, fp32 accumulate)" if args.math == "f16x3" else args.math, "data": "synthetic",
+            "config": {"workload": cfg["workload"], "config": 6, "mode": "codec", "batch_per_gpu": B, "math": args.math,
+                       "weights": "random-init (seeded: init_entropy_params + init_transform_params)", "lanes_per_gpu": args.lanes,
+                       "l2": "no flush needed: per-step working set (several GB of activations) >> 126 MB L2", "warmup_steps_run": n_warm,
+                       "parallelism": f"{world} independent image shards"},
+            "e2e": {"value": imgs / (ms_e2e * 1e-3), "unit": "images/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": host_x.numel() * 4, "d2h_bytes_per_step": host_out.numel() * 4 + 8,
+                    "how": "per step: pinned host images -> device, DCAECodec.forward, x_hat and the two log2-likelihood sums -> pinned host (copies on the compute stream, not overlapped)"},
+            "gpu_launches": launches * args.steps, "gpu_launches_per_step": launches,
+            "clocks": clocks, "stages_ms": stages, "kernel_families": fam,
+            "roofline": {"kernel": "gemm_f16x3 family over the whole model", "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                         "frac": (achieved / peak) if achieved and peak else None, "traffic": None,
+                         "note": "achieved = algorithmic 2*T*N*K flop of every dense-layer launch (zero-padded channels and the zero taps of the space-to-depth / 4-phase forms included) / their summed CUDA-event time; 3-pass fp16 ceiling = 1/3 of the peak"},
+            "cpu_baseline": cpu_baseline, "torch_gpu_baseline": torch_gpu_baseline,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 class _null:
     def __enter__(self):
         return self
@@ -526,6 +722,8 @@ def main():
         return run_reference(args)
     if args.config == 4:
         return run_training(args)
+    if args.config == 6:
+        return run_codec(args)
     cfg = CONFIGS[args.config]
     compress = cfg["mode"] == "compress"
 

@@ -9,6 +9,8 @@ Public surface (mirrors the reference's operator interface for this path only):
   EntropyModel, SliceLoopFunction -- the training form (autograd: kernels forward, torch-graph recompute backward)
   ans.BufferedRansEncoder / RansDecoder -- the native range coder with compressai.ans' interface
   init_entropy_params   -- deterministic random-init weights with the reference's state-dict keys
+  TransformStack, accelerate_transforms, init_transform_params -- g_a / g_s / h_a / h_z_s1 / h_z_s2 on the library (dcae_b200/transforms.py)
+  DCAECodec             -- the whole model (forward / compress / decompress / update) from a reference state dict
 """
 from .params import init_entropy_params, entropy_param_shapes  # noqa: F401
 
@@ -30,6 +32,12 @@ def __getattr__(name):
     if name == "EntropyBottleneck":
         from .entropy_bottleneck import EntropyBottleneck
         return EntropyBottleneck
+    if name in ("TransformStack", "accelerate_transforms", "init_transform_params", "transform_param_shapes"):
+        from . import transforms
+        return getattr(transforms, name)
+    if name == "DCAECodec":
+        from .codec import DCAECodec
+        return DCAECodec
     if name == "GaussianConditional":
         from .gaussian_conditional import GaussianConditional
         return GaussianConditional
