@@ -71,9 +71,11 @@ __global__ void __launch_bounds__(256) layernorm_any_kernel(const float* __restr
 }
 
 // ---------------------------------------------------------------------------------------------
-// Window attention (dcae.py:262-291).  One block per window, heads in sequence; 4 threads per query row:
-// thread (i, c4) owns the keys j = c4 + 4 jj.  q, k, v of the head sit in shared memory (rows padded to HD + 1
-// floats: conflict-free for both access patterns), logits / probabilities stay in registers.
+// Window attention (dcae.py:262-291).  One block per window, heads in sequence.  Four threads share a pair of query
+// rows (i2, i2 + PP/2): thread (i2, c4) owns the keys j = c4 + 4 jj.  The two query rows live in registers, K and V of
+// the head in shared memory (rows padded to HD + 4 floats: 16-byte aligned and conflict-free for the float4 reads), so
+// every float4 of K / V read from shared memory feeds 8 FMAs (two rows x four dims); logits / probabilities stay in
+// registers, no sim / probs tensor exists in HBM.
 // ---------------------------------------------------------------------------------------------
 struct WinArgs {
   const float* qkv; int64_t ld; int q_col, k_col, v_col;
@@ -84,77 +86,134 @@ struct WinArgs {
 };
 
 template <int HD, int P>
-__global__ void __launch_bounds__(4 * P * P) window_attention_kernel(const WinArgs a) {
-  constexpr int PP = P * P, NJ = PP / 4, LDS = HD + 1, R = 2 * P - 1, DQ = HD / 4;
-  __shared__ float sq[PP * LDS], sk[PP * LDS], sv[PP * LDS];
+__global__ void __launch_bounds__(2 * P * P) window_attention_kernel(const WinArgs a) {
+  constexpr int PP = P * P, HALF = PP / 2, NJ = PP / 4, LDS = HD + 4, R = 2 * P - 1, DQ = HD / 4, NT = 2 * PP;
+  __shared__ __align__(16) float sk[PP * LDS];
+  __shared__ __align__(16) float sv[PP * LDS];
   __shared__ float sbias[R * R];
-  const int tid = threadIdx.x, i = tid >> 2, c4 = tid & 3;
+  __shared__ int64_t stok[PP];
+  const int tid = threadIdx.x, i2 = tid >> 2, c4 = tid & 3;
   const int wx = (int)(blockIdx.x % a.nwx), wy = (int)(blockIdx.x / a.nwx), b = (int)blockIdx.y;
-  const int py = i / P, px = i % P;
   // rolled[r] = x[(r + shift) mod size] (torch.roll by -shift, dcae.py:270); the result goes back to the same token (:289)
-  int yy = wy * P + py + a.shift; if (yy >= a.h) yy -= a.h;
-  int xx = wx * P + px + a.shift; if (xx >= a.w) xx -= a.w;
-  const int64_t tok = ((int64_t)b * a.h + yy) * a.w + xx;
+  if (tid < PP) {
+    int yy = wy * P + tid / P + a.shift; if (yy >= a.h) yy -= a.h;
+    int xx = wx * P + tid % P + a.shift; if (xx >= a.w) xx -= a.w;
+    stok[tid] = ((int64_t)b * a.h + yy) * a.w + xx;
+  }
   // SW mask (generate_mask, dcae.py:244-260): in the last window row / column the wrapped part may not see the rest
   const bool last_row = a.shift > 0 && wy == a.nwy - 1, last_col = a.shift > 0 && wx == a.nwx - 1;
   const int sp = P - a.shift;
+  int py[2], px[2];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) { py[r] = (i2 + r * HALF) / P; px[r] = (i2 + r * HALF) % P; }
+  __syncthreads();
+  const int64_t tok[2] = {stok[i2], stok[i2 + HALF]};
   for (int e = 0; e < a.n_heads; ++e) {
-    __syncthreads();
-    const float* row = a.qkv + tok * a.ld + e * HD;
-#pragma unroll
-    for (int d = 0; d < DQ; ++d) {
-      const int dd = c4 * DQ + d;
-      sq[i * LDS + dd] = __ldg(row + a.q_col + dd);
-      sk[i * LDS + dd] = __ldg(row + a.k_col + dd);
-      sv[i * LDS + dd] = __ldg(row + a.v_col + dd);
+    __syncthreads();                       // the previous head is done with sk / sv / sbias
+    for (int idx = tid; idx < PP * DQ; idx += NT) {
+      const int t = idx / DQ, d4 = idx - t * DQ;
+      const float* row = a.qkv + stok[t] * a.ld + e * HD + 4 * d4;
+      *reinterpret_cast<float4*>(sk + t * LDS + 4 * d4) = __ldg(reinterpret_cast<const float4*>(row + a.k_col));
+      *reinterpret_cast<float4*>(sv + t * LDS + 4 * d4) = __ldg(reinterpret_cast<const float4*>(row + a.v_col));
     }
-    for (int t = tid; t < R * R; t += 4 * PP) sbias[t] = __ldg(a.rel + (int64_t)e * R * R + t);
+    for (int t = tid; t < R * R; t += NT) sbias[t] = __ldg(a.rel + (int64_t)e * R * R + t);
+    float q[2][HD];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const float4* qp = reinterpret_cast<const float4*>(a.qkv + tok[r] * a.ld + a.q_col + e * HD);
+#pragma unroll
+      for (int d4 = 0; d4 < DQ; ++d4) {
+        const float4 v = __ldg(qp + d4);
+        q[r][4 * d4] = v.x; q[r][4 * d4 + 1] = v.y; q[r][4 * d4 + 2] = v.z; q[r][4 * d4 + 3] = v.w;
+      }
+    }
     __syncthreads();
-    float s[NJ];
-    float m = -INFINITY;
+    float s[2][NJ];
+    float m[2] = {-INFINITY, -INFINITY};
 #pragma unroll
     for (int jj = 0; jj < NJ; ++jj) {
       const int j = c4 + 4 * jj;
-      float acc = 0.f;
+      float acc0 = 0.f, acc1 = 0.f;
 #pragma unroll
-      for (int d = 0; d < HD; ++d) acc = fmaf(sq[i * LDS + d], sk[j * LDS + d], acc);
+      for (int d4 = 0; d4 < DQ; ++d4) {
+        const float4 kv = *reinterpret_cast<const float4*>(sk + j * LDS + 4 * d4);
+        acc0 = fmaf(q[0][4 * d4], kv.x, acc0); acc1 = fmaf(q[1][4 * d4], kv.x, acc1);
+        acc0 = fmaf(q[0][4 * d4 + 1], kv.y, acc0); acc1 = fmaf(q[1][4 * d4 + 1], kv.y, acc1);
+        acc0 = fmaf(q[0][4 * d4 + 2], kv.z, acc0); acc1 = fmaf(q[1][4 * d4 + 2], kv.z, acc1);
+        acc0 = fmaf(q[0][4 * d4 + 3], kv.w, acc0); acc1 = fmaf(q[1][4 * d4 + 3], kv.w, acc1);
+      }
       const int qy = j / P, qx = j % P;
-      acc = acc * a.scale + sbias[(py - qy + P - 1) * R + (px - qx + P - 1)];
-      const bool masked = (last_row && ((py < sp) != (qy < sp))) || (last_col && ((px < sp) != (qx < sp)));
-      s[jj] = masked ? -INFINITY : acc;
-      m = fmaxf(m, s[jj]);
-    }
-    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
-    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
-    float sum = 0.f;
+      const float acc[2] = {acc0, acc1};
 #pragma unroll
-    for (int jj = 0; jj < NJ; ++jj) {
-      s[jj] = expf(s[jj] - m);
-      sum += s[jj];
+      for (int r = 0; r < 2; ++r) {
+        const float v = acc[r] * a.scale + sbias[(py[r] - qy + P - 1) * R + (px[r] - qx + P - 1)];
+        const bool masked = (last_row && ((py[r] < sp) != (qy < sp))) || (last_col && ((px[r] < sp) != (qx < sp)));
+        s[r][jj] = masked ? -INFINITY : v;
+        m[r] = fmaxf(m[r], s[r][jj]);
+      }
     }
-    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-    const float inv = 1.0f / sum;
-    float o[HD];
+    float inv[2];
 #pragma unroll
-    for (int d = 0; d < HD; ++d) o[d] = 0.f;
+    for (int r = 0; r < 2; ++r) {
+      m[r] = fmaxf(m[r], __shfl_xor_sync(0xffffffffu, m[r], 1));
+      m[r] = fmaxf(m[r], __shfl_xor_sync(0xffffffffu, m[r], 2));
+      float sum = 0.f;
+#pragma unroll
+      for (int jj = 0; jj < NJ; ++jj) {
+        s[r][jj] = expf(s[r][jj] - m[r]);
+        sum += s[r][jj];
+      }
+      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+      inv[r] = 1.0f / sum;
+    }
+    float o[2][HD];
+#pragma unroll
+    for (int d = 0; d < HD; ++d) { o[0][d] = 0.f; o[1][d] = 0.f; }
 #pragma unroll
     for (int jj = 0; jj < NJ; ++jj) {
       const int j = c4 + 4 * jj;
-      const float pj = s[jj] * inv;
+      const float p0 = s[0][jj] * inv[0], p1 = s[1][jj] * inv[1];
 #pragma unroll
-      for (int d = 0; d < HD; ++d) o[d] = fmaf(pj, sv[j * LDS + d], o[d]);
+      for (int d4 = 0; d4 < DQ; ++d4) {
+        const float4 vv = *reinterpret_cast<const float4*>(sv + j * LDS + 4 * d4);
+        o[0][4 * d4] = fmaf(p0, vv.x, o[0][4 * d4]); o[1][4 * d4] = fmaf(p1, vv.x, o[1][4 * d4]);
+        o[0][4 * d4 + 1] = fmaf(p0, vv.y, o[0][4 * d4 + 1]); o[1][4 * d4 + 1] = fmaf(p1, vv.y, o[1][4 * d4 + 1]);
+        o[0][4 * d4 + 2] = fmaf(p0, vv.z, o[0][4 * d4 + 2]); o[1][4 * d4 + 2] = fmaf(p1, vv.z, o[1][4 * d4 + 2]);
+        o[0][4 * d4 + 3] = fmaf(p0, vv.w, o[0][4 * d4 + 3]); o[1][4 * d4 + 3] = fmaf(p1, vv.w, o[1][4 * d4 + 3]);
+      }
     }
+    // sum over the four key owners of the row pair, then thread c4 keeps and writes dims [c4 DQ, (c4 + 1) DQ)
 #pragma unroll
-    for (int d = 0; d < HD; ++d) {
-      o[d] += __shfl_xor_sync(0xffffffffu, o[d], 1);
-      o[d] += __shfl_xor_sync(0xffffffffu, o[d], 2);
-    }
+    for (int r = 0; r < 2; ++r) {
+      float mine[DQ];
 #pragma unroll
-    for (int d = 0; d < HD; ++d) {
-      if (d / DQ == c4) {
-        if (a.out) a.out[tok * a.out_ld + e * HD + d] = o[d];
-        if (a.o16.hi) store_plane1(a.o16, tok, e * HD + d, o[d]);
+      for (int d = 0; d < HD; ++d) {
+        float v = o[r][d];
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        if (d / DQ == c4) mine[d % DQ] = v;
+      }
+      const int col = e * HD + c4 * DQ;
+      if (a.out) {
+        float* op = a.out + tok[r] * a.out_ld + col;
+        if (DQ == 2) *reinterpret_cast<float2*>(op) = make_float2(mine[0], mine[1]);
+        else {
+#pragma unroll
+          for (int d4 = 0; d4 < DQ / 4; ++d4) *reinterpret_cast<float4*>(op + 4 * d4) = make_float4(mine[4 * d4], mine[4 * d4 + 1], mine[4 * d4 + 2], mine[4 * d4 + 3]);
+        }
+      }
+      if (a.o16.hi) {
+        if (DQ == 2) {
+          uint32_t hw, lw;
+          f16_split2(mine[0], mine[1], hw, lw);
+          *reinterpret_cast<uint32_t*>(static_cast<__half*>(a.o16.hi) + tok[r] * a.o16.ld + col) = hw;
+          *reinterpret_cast<uint32_t*>(static_cast<__half*>(a.o16.lo) + tok[r] * a.o16.ld + col) = lw;
+        } else {
+#pragma unroll
+          for (int d4 = 0; d4 < DQ / 4; ++d4)
+            store_planes4(a.o16, tok[r], col + 4 * d4, make_float4(mine[4 * d4], mine[4 * d4 + 1], mine[4 * d4 + 2], mine[4 * d4 + 3]));
+        }
       }
     }
   }
@@ -266,6 +325,8 @@ extern "C" int dcae_op_window_attention(const float* qkv, int64_t ld, int32_t q_
   DCAE_REQUIRE(q_col >= 0 && k_col >= 0 && v_col >= 0 && q_col + C <= ld && k_col + C <= ld && v_col + C <= ld && (!out || out_ld >= C),
                "dcae_op_window_attention: column windows exceed the leading dimension");
   DCAE_REQUIRE(B <= 65535, "dcae_op_window_attention: batch too large");
+  DCAE_REQUIRE(aligned16(qkv) && ld % 4 == 0 && q_col % 4 == 0 && k_col % 4 == 0 && v_col % 4 == 0 && aligned16(out) && out_ld % 4 == 0,
+               "dcae_op_window_attention: qkv / out must be 16-byte aligned with ld and column offsets multiples of 4");
   if (B == 0) return DCAE_OK;
   WinArgs a;
   a.qkv = qkv; a.ld = ld; a.q_col = q_col; a.k_col = k_col; a.v_col = v_col;
@@ -274,7 +335,7 @@ extern "C" int dcae_op_window_attention(const float* qkv, int64_t ld, int32_t q_
   a.out = out; a.out_ld = out_ld; a.o16 = o16;
   const dim3 grid((unsigned)(a.nwx * a.nwy), (unsigned)B);
   cudaStream_t s = (cudaStream_t)stream;
-#define WIN_CASE(HD, P) if (head_dim == HD && window == P) window_attention_kernel<HD, P><<<grid, 4 * P * P, 0, s>>>(a);
+#define WIN_CASE(HD, P) if (head_dim == HD && window == P) window_attention_kernel<HD, P><<<grid, 2 * P * P, 0, s>>>(a);
   WIN_CASE(8, 4) WIN_CASE(16, 4) WIN_CASE(32, 4) WIN_CASE(8, 8) WIN_CASE(16, 8) WIN_CASE(32, 8)
 #undef WIN_CASE
   DCAE_LAUNCH_CHECK();

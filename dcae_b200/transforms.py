@@ -201,13 +201,18 @@ def deconv_s2_to_gemm(w: torch.Tensor, cs_out: int, c_pad: int) -> torch.Tensor:
 
 # ---- activations and the kernel backend ----------------------------------------------------------------------------
 
+F32, P16 = 1, 2          # which forms of a result its consumers read: fp32 [T, ld] and / or fp16 hi/lo planes
+
+
 @dataclass
 class Act:
-    """Token-major activation: buf [T, ld] fp32 (ld = padded channel count), token grid (B, h, w)."""
-    buf: torch.Tensor
+    """Token-major activation on the token grid (B, h, w): `buf` = fp32 [T, ld] (ld = padded channel count) and / or
+    `p16` = (hi, lo) fp16 planes [T, pad64(ld)], the form the f16x3 GEMMs read by TMA (value = hi + lo, 22 bits)."""
+    buf: Optional[torch.Tensor]
     B: int
     h: int
     w: int
+    p16: Optional[Tuple[torch.Tensor, torch.Tensor]] = None
 
     @property
     def T(self) -> int:
@@ -215,7 +220,7 @@ class Act:
 
     @property
     def ld(self) -> int:
-        return self.buf.shape[1]
+        return self.buf.shape[1] if self.buf is not None else self.p16[0].shape[1]
 
 
 class PackedGemm:
@@ -229,16 +234,31 @@ class PackedGemm:
         self.keep: list = []
 
 
+def pad64(c: int) -> int:
+    return (c + 63) // 64 * 64
+
+
 class LibKernels:
-    """The operators on libdcae_b200.so (device tensors in, device tensors out, everything on the current stream)."""
+    """The operators on libdcae_b200.so (device tensors in, device tensors out, everything on the current stream).
+
+    Data flow in the f16x3 / f16 modes: every producer writes the form(s) its consumers read (`want` = F32 | P16) --
+    fp16 hi/lo planes for GEMM operands, straight from the producing kernel (LayerNorm, window attention, depthwise
+    conv, GEMM epilogue, space-to-depth / depth-to-space), fp32 for residuals and element-wise consumers -- so no
+    conversion pass runs between layers and nothing is written that nobody reads.  Other math modes stay fp32.
+
+    Buffers come from a pool keyed by (kind, rows, columns, written columns): a buffer whose only reference is the pool's
+    is free (everything runs on one stream, so reuse is ordered).  Planes are allocated pad64(columns) wide and zeroed
+    once; no kernel writes the padding, which the GEMM's 64-column TMA boxes over-read against zero weights."""
 
     def __init__(self, device="cuda:0", math: str = "f16x3"):
         if math not in _lib.MATH:
             raise ValueError(f"math must be one of {sorted(_lib.MATH)}")
         self.device = torch.device(device)
         self.math = math
+        self.planes = math in ("f16x3", "f16")
         self.lib = _lib.load()
         self._scratch: Optional[torch.Tensor] = None
+        self._pool: Dict[tuple, list] = {}
 
     # -- helpers
     def _s(self) -> int:
@@ -247,8 +267,40 @@ class LibKernels:
     def tensor(self, t: torch.Tensor) -> torch.Tensor:
         return t.detach().to(self.device, torch.float32).contiguous()
 
-    def empty(self, T: int, ld: int, zero: bool = False) -> torch.Tensor:
-        return (torch.zeros if zero else torch.empty)(T, ld, device=self.device, dtype=torch.float32)
+    def _take(self, key, make):
+        import sys
+        lst = self._pool.setdefault(key, [])
+        for i in range(len(lst)):
+            if sys.getrefcount(lst[i]) == 2:          # the list and getrefcount's own argument: nobody else holds it
+                return lst[i]
+        lst.append(make())
+        return lst[-1]
+
+    def clear_pool(self) -> None:
+        self._pool.clear()
+
+    def _f32(self, T: int, ld: int, cols: int) -> torch.Tensor:
+        """fp32 [T, ld] of which a kernel writes the first `cols` columns; the rest stays zero."""
+        make = (lambda: torch.zeros(T, ld, device=self.device)) if ld > cols else (lambda: torch.empty(T, ld, device=self.device))
+        return self._take(("f32", T, ld, cols), make)
+
+    def _p16(self, T: int, cols: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        ld = pad64(cols)
+        z = torch.zeros if ld > cols else torch.empty
+        pair = self._take(("p16", T, ld, cols), lambda: torch.stack([z(T, ld, dtype=torch.float16, device=self.device) for _ in range(2)]))
+        return pair            # [2, T, ld]: hi = pair[0], lo = pair[1]
+
+    @staticmethod
+    def _pl(p16) -> _lib.Planes:
+        return _lib.Planes(p16[0].data_ptr(), p16[1].data_ptr(), p16[0].stride(0))
+
+    def _outs(self, T: int, ld: int, cols: int, want: int):
+        """(fp32 buffer or None, planes or None) for a result of `cols` written columns."""
+        if not self.planes:
+            want = F32
+        buf = self._f32(T, ld, cols) if want & F32 else None
+        p16 = self._p16(T, ld) if want & P16 else None
+        return buf, p16
 
     def _planes_scratch(self, T: int, k: int) -> Tuple[int, int]:
         n = int(self.lib.dcae_planes_bytes(T, k))
@@ -270,7 +322,7 @@ class LibKernels:
                 _lib.check(self.lib.dcae_split_tf32(w.data_ptr(), hi.data_ptr(), lo.data_ptr(), w.numel(), self._s()), "dcae_split_tf32")
                 W.w_hi, W.w_lo = hi.data_ptr(), lo.data_ptr()
                 pg.keep += [hi, lo]
-            elif self.math in ("f16x3", "f16"):
+            elif self.planes:
                 from .weights import f16_weight_planes
                 h16, l16, K16, descale = f16_weight_planes(self.lib, w, taps, self._s())
                 W.w16_hi, W.w16_lo, W.K16, W.descale = h16.data_ptr(), l16.data_ptr(), K16, descale
@@ -285,13 +337,14 @@ class LibKernels:
         return self.tensor(t)
 
     # -- operators
-    def to_tokens(self, x: torch.Tensor, ld: int) -> Act:
+    def to_tokens(self, x: torch.Tensor, ld: int, want: int = F32) -> Act:
         """NCHW -> token-major with `ld` columns (columns >= C are zero)."""
         B, C, H, W = x.shape
         x = self.tensor(x)
-        out = self.empty(B * H * W, ld, zero=ld > C)
-        _lib.check(self.lib.dcae_op_nchw_to_tokens(x.data_ptr(), B, C, H * W, out.data_ptr(), ld, None, self._s()), "dcae_op_nchw_to_tokens")
-        return Act(out, B, H, W)
+        buf, p16 = self._outs(B * H * W, ld, C, want)
+        _lib.check(self.lib.dcae_op_nchw_to_tokens(x.data_ptr(), B, C, H * W, _lib.ptr(buf), ld, self._pl(p16) if p16 is not None else None,
+                                                   self._s()), "dcae_op_nchw_to_tokens")
+        return Act(buf, B, H, W, p16)
 
     def to_nchw(self, a: Act, C: int) -> torch.Tensor:
         out = torch.empty(a.B, C, a.h, a.w, device=self.device, dtype=torch.float32)
@@ -299,62 +352,78 @@ class LibKernels:
         return out
 
     def gemm(self, a: Act, pg: PackedGemm, act: int = _lib.ACT_NONE, residual: Optional[Act] = None,
-             res_scale: Optional[torch.Tensor] = None) -> Act:
+             res_scale: Optional[torch.Tensor] = None, want: int = F32) -> Act:
         """out[T, N] = act(A[T, taps*k] W^T + bias) + residual * res_scale, A = the first K / taps columns of `a`."""
         k = pg.K // pg.taps
         assert k <= a.ld and k % 32 == 0, (k, a.ld)
-        out = self.empty(a.T, pg.N)
-        pbase, pbytes = (self._planes_scratch(a.T, k) if self.math in ("f16x3", "f16") else (None, 0))
-        A = _lib.Operand(a.buf.data_ptr(), a.ld, 0, k, 0, 0, pg.taps, a.B, a.h, a.w, pbase, pbytes)
+        buf, p16 = self._outs(a.T, pg.N, pg.N, want)
+        A = _lib.Operand()
+        A.col0, A.k0, A.taps, A.B, A.h, A.w = 0, k, pg.taps, a.B, a.h, a.w
+        if self.planes and a.p16 is not None:
+            A.src16 = self._pl(a.p16)                 # the producer wrote the operand planes: no split pass
+            A.ld = a.p16[0].stride(0)
+        else:
+            A.base, A.ld = a.buf.data_ptr(), a.buf.shape[1]
+            if self.planes:
+                A.planes, A.planes_bytes = self._planes_scratch(a.T, k)
         e = _lib.Epilogue()
         e.bias = pg.bias.data_ptr()
         if residual is not None:
-            assert residual.ld >= pg.N and residual.T == a.T
-            e.residual, e.residual_ld = residual.buf.data_ptr(), residual.ld
+            assert residual.buf is not None and residual.buf.shape[1] >= pg.N and residual.T == a.T
+            e.residual, e.residual_ld = residual.buf.data_ptr(), residual.buf.shape[1]
             e.res_scale = _lib.ptr(res_scale)
         e.act = act
-        e.out, e.out_ld = out.data_ptr(), pg.N
+        if buf is not None:
+            e.out, e.out_ld = buf.data_ptr(), pg.N
+        if p16 is not None:
+            e.out16 = self._pl(p16)
         _lib.check(self.lib.dcae_op_gemm(A, pg.struct, e, _lib.MATH[self.math], self._s()), "dcae_op_gemm")
-        return Act(out, a.B, a.h, a.w)
+        return Act(buf, a.B, a.h, a.w, p16)
 
-    def layernorm(self, a: Act, gamma: torch.Tensor, beta: torch.Tensor, C: int) -> Act:
-        out = self.empty(a.T, a.ld, zero=a.ld > C)
-        _lib.check(self.lib.dcae_op_layernorm(a.buf.data_ptr(), a.ld, gamma.data_ptr(), beta.data_ptr(), C, a.T, out.data_ptr(), a.ld,
-                                              None, self._s()), "dcae_op_layernorm")
-        return Act(out, a.B, a.h, a.w)
+    def layernorm(self, a: Act, gamma: torch.Tensor, beta: torch.Tensor, C: int, want: int = F32) -> Act:
+        ld = a.buf.shape[1]
+        buf, p16 = self._outs(a.T, ld, C, want)
+        _lib.check(self.lib.dcae_op_layernorm(a.buf.data_ptr(), ld, gamma.data_ptr(), beta.data_ptr(), C, a.T, _lib.ptr(buf), ld,
+                                              self._pl(p16) if p16 is not None else None, self._s()), "dcae_op_layernorm")
+        return Act(buf, a.B, a.h, a.w, p16)
 
-    def window_attention(self, qkv: Act, C: int, c_pad: int, head_dim: int, window: int, shift: int, rel: torch.Tensor) -> Act:
-        out = self.empty(qkv.T, c_pad, zero=c_pad > C)
-        _lib.check(self.lib.dcae_op_window_attention(qkv.buf.data_ptr(), qkv.ld, 0, c_pad, 2 * c_pad, C, head_dim, window, shift,
-                                                     rel.data_ptr(), qkv.B, qkv.h, qkv.w, out.data_ptr(), c_pad, None, self._s()),
-                   "dcae_op_window_attention")
-        return Act(out, qkv.B, qkv.h, qkv.w)
+    def window_attention(self, qkv: Act, C: int, c_pad: int, head_dim: int, window: int, shift: int, rel: torch.Tensor, want: int = F32) -> Act:
+        buf, p16 = self._outs(qkv.T, c_pad, C, want)
+        _lib.check(self.lib.dcae_op_window_attention(qkv.buf.data_ptr(), qkv.buf.shape[1], 0, c_pad, 2 * c_pad, C, head_dim, window, shift,
+                                                     rel.data_ptr(), qkv.B, qkv.h, qkv.w, _lib.ptr(buf), c_pad,
+                                                     self._pl(p16) if p16 is not None else None, self._s()), "dcae_op_window_attention")
+        return Act(buf, qkv.B, qkv.h, qkv.w, p16)
 
-    def dwconv_glu(self, f: Act, wt9c: torch.Tensor, bias: torch.Tensor, hid: int) -> Act:
+    def dwconv_glu(self, f: Act, wt9c: torch.Tensor, bias: torch.Tensor, hid: int, want: int = F32) -> Act:
         """gelu(dw3x3(f[:, :hid]) + bias) * f[:, hid:2 hid]   (ConvolutionalGLU, dcae.py:323-326)."""
-        out = self.empty(f.T, hid)
-        _lib.check(self.lib.dcae_op_dwconv3x3(f.buf.data_ptr(), f.ld, wt9c.data_ptr(), bias.data_ptr(), hid, f.B, f.h, f.w, _lib.ACT_GELU,
-                                              f.buf.data_ptr() + 4 * hid, f.ld, out.data_ptr(), hid, None, self._s()), "dcae_op_dwconv3x3")
-        return Act(out, f.B, f.h, f.w)
+        buf, p16 = self._outs(f.T, hid, hid, want)
+        ld = f.buf.shape[1]
+        _lib.check(self.lib.dcae_op_dwconv3x3(f.buf.data_ptr(), ld, wt9c.data_ptr(), bias.data_ptr(), hid, f.B, f.h, f.w, _lib.ACT_GELU,
+                                              f.buf.data_ptr() + 4 * hid, ld, _lib.ptr(buf), hid, self._pl(p16) if p16 is not None else None,
+                                              self._s()), "dcae_op_dwconv3x3")
+        return Act(buf, f.B, f.h, f.w, p16)
 
-    def space_to_depth(self, a: Act, C: int, cs: int) -> Act:
+    def space_to_depth(self, a: Act, C: int, cs: int, want: int = F32) -> Act:
         h2, w2 = (a.h + 1) // 2, (a.w + 1) // 2
-        out = self.empty(a.B * h2 * w2, 4 * cs)
-        _lib.check(self.lib.dcae_op_space_to_depth(a.buf.data_ptr(), a.ld, C, cs, a.B, a.h, a.w, out.data_ptr(), 4 * cs, None, self._s()),
-                   "dcae_op_space_to_depth")
-        return Act(out, a.B, h2, w2)
+        buf, p16 = self._outs(a.B * h2 * w2, 4 * cs, 4 * cs, want)
+        _lib.check(self.lib.dcae_op_space_to_depth(a.buf.data_ptr(), a.buf.shape[1], C, cs, a.B, a.h, a.w, _lib.ptr(buf), 4 * cs,
+                                                   self._pl(p16) if p16 is not None else None, self._s()), "dcae_op_space_to_depth")
+        return Act(buf, a.B, h2, w2, p16)
 
-    def depth_to_space(self, a: Act, cs: int, C: int, c_pad: int) -> Act:
-        out = self.empty(4 * a.T, c_pad)
-        _lib.check(self.lib.dcae_op_depth_to_space(a.buf.data_ptr(), a.ld, cs, C, c_pad, a.B, a.h, a.w, out.data_ptr(), c_pad, None, self._s()),
-                   "dcae_op_depth_to_space")
-        return Act(out, a.B, 2 * a.h, 2 * a.w)
+    def depth_to_space(self, a: Act, cs: int, C: int, c_pad: int, want: int = F32) -> Act:
+        buf, p16 = self._outs(4 * a.T, c_pad, c_pad, want)
+        _lib.check(self.lib.dcae_op_depth_to_space(a.buf.data_ptr(), a.buf.shape[1], cs, C, c_pad, a.B, a.h, a.w, _lib.ptr(buf), c_pad,
+                                                   self._pl(p16) if p16 is not None else None, self._s()), "dcae_op_depth_to_space")
+        return Act(buf, a.B, 2 * a.h, 2 * a.w, p16)
 
 
 # ---- blocks -----------------------------------------------------------------------------------------------------------
+# `want` of a block = the forms its successor reads (NEEDS below); inside a block every intermediate is written in the
+# one form its single consumer reads.
 
 class _ResidualBottleneck:
     """ResidualBottleneckBlock(c, c) (dcae.py:152-190): 1x1 -> ReLU -> 3x3 -> ReLU -> 1x1, + x (skip is Identity)."""
+    needs = F32 | P16          # x: residual (fp32) and the operand of conv1 (planes)
 
     def __init__(self, K, P, p: str, c: int):
         mid, cp = c // 2, pad32(c)
@@ -363,26 +432,28 @@ class _ResidualBottleneck:
         self.c2 = K.pack_gemm(conv3x3_to_gemm(P[p + "conv2.weight"], mp, mp), P[p + "conv2.bias"], taps=9)
         self.c3 = K.pack_gemm(linear_to_gemm(P[p + "conv3.weight"], cp, mp), P[p + "conv3.bias"])
 
-    def __call__(self, K, x: Act) -> Act:
-        t = K.gemm(x, self.c1, act=_lib.ACT_RELU)
-        t = K.gemm(t, self.c2, act=_lib.ACT_RELU)
-        return K.gemm(t, self.c3, residual=x)
+    def __call__(self, K, x: Act, want: int = F32) -> Act:
+        t = K.gemm(x, self.c1, act=_lib.ACT_RELU, want=P16)
+        t = K.gemm(t, self.c2, act=_lib.ACT_RELU, want=P16)
+        return K.gemm(t, self.c3, residual=x, want=want)
 
 
 class _ConvS2:
     """conv(cin, cout, k, stride 2) (dcae.py:35-42) = space-to-depth + stride-1 3x3 implicit GEMM."""
+    needs = F32
 
     def __init__(self, K, w: torch.Tensor, b: torch.Tensor, cin: int, cout: int):
         self.cin, self.cout = cin, cout
         self.cs = pad8(cin)
         self.g = K.pack_gemm(conv_s2_to_gemm(w, pad32(cout), self.cs), b, taps=9)
 
-    def __call__(self, K, x: Act) -> Act:
-        return K.gemm(K.space_to_depth(x, self.cin, self.cs), self.g)
+    def __call__(self, K, x: Act, want: int = F32) -> Act:
+        return K.gemm(K.space_to_depth(x, self.cin, self.cs, want=P16), self.g, want=want)
 
 
 class _DeconvS2:
     """deconv(cin, cout, k, stride 2) (dcae.py:44-52) = stride-1 3x3 implicit GEMM to the 4 output phases + depth-to-space."""
+    needs = P16
 
     def __init__(self, K, w: torch.Tensor, b: torch.Tensor, cin: int, cout: int):
         self.cin, self.cout = cin, cout
@@ -390,8 +461,8 @@ class _DeconvS2:
         bias4 = _pad_to(b.reshape(-1), 0, self.cs).repeat(4)
         self.g = K.pack_gemm(deconv_s2_to_gemm(w, self.cs, pad32(cin)), bias4, taps=9)
 
-    def __call__(self, K, x: Act, c_pad: Optional[int] = None) -> Act:
-        return K.depth_to_space(K.gemm(x, self.g), self.cs, self.cout, c_pad or pad32(self.cout))
+    def __call__(self, K, x: Act, want: int = F32, c_pad: Optional[int] = None) -> Act:
+        return K.depth_to_space(K.gemm(x, self.g, want=F32), self.cs, self.cout, c_pad or pad32(self.cout), want=want)
 
 
 class _SwinLayer:
@@ -421,19 +492,20 @@ class _SwinLayer:
         self.s1 = K.vector(P[p + "res_scale_1.scale"], cp, 1.0)
         self.s2 = K.vector(P[p + "res_scale_2.scale"], cp, 1.0)
 
-    def __call__(self, K, x: Act) -> Act:
-        t = K.layernorm(x, *self.ln1, self.c)
-        t = K.gemm(t, self.qkv)
-        t = K.window_attention(t, self.c, self.cp, self.hd, self.window, self.shift, self.rel)
-        x = K.gemm(t, self.proj, residual=x, res_scale=self.s1)
-        t = K.layernorm(x, *self.ln2, self.c)
-        t = K.gemm(t, self.fc1)
-        t = K.dwconv_glu(t, self.dw_w, self.dw_b, self.hid)
-        return K.gemm(t, self.fc2, residual=x, res_scale=self.s2)
+    def __call__(self, K, x: Act, want: int = F32) -> Act:
+        t = K.layernorm(x, *self.ln1, self.c, want=P16)
+        t = K.gemm(t, self.qkv, want=F32)
+        t = K.window_attention(t, self.c, self.cp, self.hd, self.window, self.shift, self.rel, want=P16)
+        x = K.gemm(t, self.proj, residual=x, res_scale=self.s1, want=F32)
+        t = K.layernorm(x, *self.ln2, self.c, want=P16)
+        t = K.gemm(t, self.fc1, want=F32)
+        t = K.dwconv_glu(t, self.dw_w, self.dw_b, self.hid, want=P16)
+        return K.gemm(t, self.fc2, residual=x, res_scale=self.s2, want=want)
 
 
 class _Swin:
     """SwinBlockWithConvMulti (dcae.py:362-383): n alternating W / SW layers, then conv3x3 + x."""
+    needs = F32
 
     def __init__(self, K, P, p: str, c: int, head_dim: int, window: int, n: int):
         self.c, self.window = c, window
@@ -441,15 +513,15 @@ class _Swin:
         cp = pad32(c)
         self.conv = K.pack_gemm(conv3x3_to_gemm(P[p + "conv.weight"], cp, cp), P[p + "conv.bias"], taps=9)
 
-    def __call__(self, K, x: Act) -> Act:
+    def __call__(self, K, x: Act, want: int = F32) -> Act:
         if x.h <= self.window or x.w <= self.window or x.h % self.window or x.w % self.window:
             # dcae.py:374-377 pads inputs no larger than the window (and its `trans_x + x` then only works when the padded
             # and the original sizes agree); grids that are not a multiple of the window fail in the reference's rearrange
             raise _lib.DcaeError(f"Swin block: token grid {x.h}x{x.w} must be a multiple of the window {self.window} and larger than it")
         t = x
-        for layer in self.layers:
-            t = layer(K, t)
-        return K.gemm(t, self.conv, residual=x)
+        for j, layer in enumerate(self.layers):
+            t = layer(K, t, want=P16 if j == len(self.layers) - 1 else F32)      # the last layer feeds the 3x3 conv only
+        return K.gemm(t, self.conv, residual=x, want=want)
 
 
 class TransformStack:
@@ -501,14 +573,17 @@ class TransformStack:
         if x.dim() != 4 or x.shape[1] != self.c_in:
             raise ValueError(f"{self.stack}: expected [B, {self.c_in}, H, W], got {tuple(x.shape)}")
         K = self.K
-        # the first operator decides the entry layout: a stride-2 conv reads C columns of any ld, a GEMM reads pad32(C)
-        ld_in = pad32(self.c_in) if self.blocks[0][0] != "conv" else (self.c_in + 3) // 4 * 4
-        a = K.to_tokens(x, ld_in)
-        for j, (kind, blk) in enumerate(self.blocks):
-            if kind == "deconv" and j == len(self.blocks) - 1:
-                a = blk(K, a, c_pad=(self.c_out + 3) // 4 * 4)     # nothing reads padded columns behind the last operator
+        blocks = self.blocks
+        # the first operator decides the entry layout: a stride-2 conv reads C fp32 columns of any ld, a GEMM reads pad32(C)
+        ld_in = pad32(self.c_in) if blocks[0][0] != "conv" else (self.c_in + 3) // 4 * 4
+        a = K.to_tokens(x, ld_in, want=blocks[0][1].needs)
+        for j, (kind, blk) in enumerate(blocks):
+            last = j == len(blocks) - 1
+            want = F32 if last else blocks[j + 1][1].needs            # the forms the successor reads
+            if kind == "deconv" and last:
+                a = blk(K, a, want=want, c_pad=(self.c_out + 3) // 4 * 4)     # nothing reads padded columns behind the last operator
             else:
-                a = blk(K, a)
+                a = blk(K, a, want=want)
         return K.to_nchw(a, self.c_out)
 
     __call__ = forward
@@ -534,4 +609,4 @@ def accelerate_transforms(net: torch.nn.Module, device="cuda:0", math: str = "f1
 
 
 __all__ = ["TransformStack", "init_transform_params", "LibKernels", "Act", "ARCH", "STACKS", "accelerate_transforms", "transform_param_shapes",
-           "conv_s2_to_gemm", "deconv_s2_to_gemm", "conv3x3_to_gemm", "linear_to_gemm", "pad32", "pad8"]
+           "conv_s2_to_gemm", "deconv_s2_to_gemm", "conv3x3_to_gemm", "linear_to_gemm", "pad32", "pad8", "F32", "P16"]

@@ -1,4 +1,5 @@
-"""TEST INFRASTRUCTURE ONLY: torch-CPU restatement of the C-ABI operator contracts (include/dcae_b200.h) that
+"""TEST INFRASTRUCTURE ONLY (every result is kept in fp32; the `want` form flags of the CUDA backend are accepted and
+ignored): torch-CPU restatement of the C-ABI operator contracts (include/dcae_b200.h) that
 `dcae_b200.transforms` composes.  It lets the CPU suite check the host logic -- weight re-indexing (stride-2 conv as
 space-to-depth + 3x3, transposed conv as 3x3 + depth-to-space, channel padding, qkv layout) and the block composition
 -- against the reference's real modules without a GPU.  Each method follows the header comment of the operator it
@@ -27,7 +28,7 @@ class TorchKernels:
         pg.w, pg.bias = self.tensor(w2d), self.tensor(_pad_to(bias.reshape(-1), 0, w2d.shape[0]))
         return pg
 
-    def to_tokens(self, x, ld):
+    def to_tokens(self, x, ld, want=1):
         B, C, H, W = x.shape
         out = torch.zeros(B * H * W, ld)
         out[:, :C] = x.permute(0, 2, 3, 1).reshape(-1, C)
@@ -36,7 +37,7 @@ class TorchKernels:
     def to_nchw(self, a, C):
         return a.buf[:, :C].reshape(a.B, a.h, a.w, C).permute(0, 3, 1, 2).contiguous()
 
-    def gemm(self, a, pg, act=_lib.ACT_NONE, residual=None, res_scale=None):
+    def gemm(self, a, pg, act=_lib.ACT_NONE, residual=None, res_scale=None, want=1):
         """dcae_op_gemm: A = the first K / taps columns, gathered over the 9 taps of a 3x3 / stride 1 / pad 1 window when
         taps = 9, K ordered tap-major (tap = 3 (dy + 1) + (dx + 1))."""
         k = pg.K // pg.taps
@@ -56,12 +57,12 @@ class TorchKernels:
             acc = acc + (r * res_scale.double() if res_scale is not None else r)
         return Act(acc.float(), a.B, a.h, a.w)
 
-    def layernorm(self, a, gamma, beta, C):
+    def layernorm(self, a, gamma, beta, C, want=1):
         out = torch.zeros_like(a.buf)
         out[:, :C] = F.layer_norm(a.buf[:, :C], (C,), gamma, beta, 1e-5)
         return Act(out, a.B, a.h, a.w)
 
-    def window_attention(self, qkv, C, c_pad, head_dim, window, shift, rel):
+    def window_attention(self, qkv, C, c_pad, head_dim, window, shift, rel, want=1):
         """dcae_op_window_attention, written per token from the header comment (slow, small cases only)."""
         B, h, w, P = qkv.B, qkv.h, qkv.w, window
         q = qkv.buf[:, 0:C].reshape(B, h, w, C)
@@ -94,13 +95,13 @@ class TorchKernels:
                         out[:, yy, xx, :C] = o[:, a_, b_]
         return Act(out.reshape(B * h * w, c_pad), B, h, w)
 
-    def dwconv_glu(self, f, wt9c, bias, hid):
+    def dwconv_glu(self, f, wt9c, bias, hid, want=1):
         x = f.buf[:, :hid].reshape(f.B, f.h, f.w, hid).permute(0, 3, 1, 2)
         y = F.conv2d(x, wt9c.t().reshape(hid, 1, 3, 3), bias, padding=1, groups=hid)
         y = F.gelu(y).permute(0, 2, 3, 1).reshape(f.T, hid) * f.buf[:, hid:2 * hid]
         return Act(y.contiguous(), f.B, f.h, f.w)
 
-    def space_to_depth(self, a, C, cs):
+    def space_to_depth(self, a, C, cs, want=1):
         h2, w2 = (a.h + 1) // 2, (a.w + 1) // 2
         img = torch.zeros(a.B, 2 * h2, 2 * w2, C)
         img[:, :a.h, :a.w] = a.buf[:, :C].reshape(a.B, a.h, a.w, C)
@@ -110,7 +111,7 @@ class TorchKernels:
                 out[:, :, :, sy * 2 + sx, :C] = img[:, sy::2, sx::2]
         return Act(out.reshape(a.B * h2 * w2, 4 * cs), a.B, h2, w2)
 
-    def depth_to_space(self, a, cs, C, c_pad):
+    def depth_to_space(self, a, cs, C, c_pad, want=1):
         x = a.buf[:, :4 * cs].reshape(a.B, a.h, a.w, 4, cs)
         out = torch.zeros(a.B, 2 * a.h, 2 * a.w, c_pad)
         for py in (0, 1):
