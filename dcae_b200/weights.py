@@ -15,14 +15,16 @@ from .params import (CC_HID1, CC_HID2, DICT_DIM, DICT_NUM, HEAD_DIM, HEAD_NUM, M
                      SLICE_CH, cq, cs)
 
 
-def f16_weight_planes(lib, w: torch.Tensor, taps: int, stream):
+def f16_weight_planes(lib, w: torch.Tensor, taps: int, stream, amax: float | None = None):
     """fp16 hi/lo planes of w * 2^e (e chosen so max|w| 2^e lands in [8192, 16384): w_lo stays a normal fp16),
-    each tap's channel run padded to a multiple of 64.  Returns (hi, lo, K16, descale = 2^-e)."""
+    each tap's channel run padded to a multiple of 64.  Returns (hi, lo, K16, descale = 2^-e).
+    amax: max|w| when the caller already has it (one batched reduction + one sync for many weights, see PackedWeights)."""
     import math
     N, K = w.shape
     kc = K // taps
     Kp = (kc + 63) // 64 * 64
-    amax = float(w.abs().max())
+    if amax is None:
+        amax = float(w.abs().max())
     e = math.floor(math.log2(16384.0 / amax)) if amax > 0 else 0
     e = max(min(e, 24), -24)
     hi = torch.empty(N, taps * Kp, dtype=torch.float16, device=w.device)
@@ -45,11 +47,48 @@ class PackedWeights:
         self.want_f16 = math in ("all", "f16x3", "f16")
         self.lib = _lib.load()
         self.array = (_lib.SliceWeights * NUM_SLICES)()
+        self._pending: list = []          # (weight tensor, taps, key): fp16 planes made in one batch, see _flush_f16
         with torch.cuda.device(device):
             dt = params["dt"].to(device, torch.float32).contiguous()
             for i in range(NUM_SLICES):
                 self._pack_slice(i, params, dt, self.array[i])
+            self._flush_f16()
             torch.cuda.synchronize(device)
+
+    def _flush_f16(self) -> None:
+        """The scaled fp16 planes of every queued weight.  Their power-of-two scales need max|w|: ONE batched reduction and
+        one device->host copy for all 125 weights (a repack per optimizer step used to pay 125 synchronising `abs().max()`).
+        The queue is keyed by the fp32 weight's device pointer (or ("k" / "v", slice) for the dictionary side): ctypes
+        copies a struct on assignment, so the planes are written through VIEWS of the fields of `self.array` afterwards."""
+        if not self._pending:
+            return
+        import ctypes as C
+        s = _lib.current_stream(self.device)
+        amax = torch.stack(torch._foreach_norm([w for w, _, _ in self._pending], float("inf"))).tolist()
+        made = {}
+        for (w, taps, key), a in zip(self._pending, amax):
+            h16, l16, K16, descale = f16_weight_planes(self.lib, w, taps, s, amax=a)
+            self._keep += [h16, l16]
+            made[key] = (h16.data_ptr(), l16.data_ptr(), K16, descale)
+        self._pending = []
+
+        def fill(view):
+            m = made.get(view.w)
+            if m is not None:
+                view.w16_hi, view.w16_lo, view.K16, view.descale = m
+
+        for i, W in enumerate(self.array):
+            for name, typ in _lib.SliceWeights._fields_:
+                if typ is _lib.Weight:
+                    fill(getattr(W, name))                      # a view into W's memory, not a copy
+                elif isinstance(typ, type) and issubclass(typ, C.Array) and typ._type_ is _lib.Weight:
+                    arr = getattr(W, name)
+                    for j in range(len(arr)):
+                        fill(arr[j])
+            kv = W.kv
+            if ("k", i) in made:
+                kv.K16_hi, kv.K16_lo, _, kv.k_descale = made[("k", i)]
+                kv.Vt16_hi, kv.Vt16_lo, _, kv.v_descale = made[("v", i)]
 
     # ---- helpers --------------------------------------------------------------------------------
     def _dev(self, t: torch.Tensor) -> torch.Tensor:
@@ -74,9 +113,7 @@ class PackedWeights:
                 _lib.check(self.lib.dcae_split_tf32(w.data_ptr(), hi.data_ptr(), lo.data_ptr(), w.numel(), s), "dcae_split_tf32")
                 out.w_hi, out.w_lo = hi.data_ptr(), lo.data_ptr()
             if self.want_f16:
-                h16, l16, K16, descale = f16_weight_planes(self.lib, w, taps, s)
-                self._keep += [h16, l16]
-                out.w16_hi, out.w16_lo, out.K16, out.descale = h16.data_ptr(), l16.data_ptr(), K16, descale
+                self._pending.append((w, taps, w.data_ptr()))
         return out
 
     @staticmethod
@@ -120,7 +157,7 @@ class PackedWeights:
             setattr(W, f"res_scale_{r}", self._vec(g(f"res_scale_{r}.scale")))
         W.lnx_g, W.lnx_b = self._vec(g("lnx.weight")), self._vec(g("lnx.bias"))
         W.q_trans, W.q_trans_b = self._weight(g("q_trans.weight")), self._vec(g("q_trans.bias"))
-        W.kv = self.dictionary_kv(dt, g("dict_ln.weight"), g("dict_ln.bias"), g("k.weight"), g("k.bias"), g("scale"))
+        W.kv = self.dictionary_kv(dt, g("dict_ln.weight"), g("dict_ln.bias"), g("k.weight"), g("k.bias"), g("scale"), slice_index=i)
         W.linear, W.linear_b = self._weight(g("linear.weight")), self._vec(g("linear.bias"))
         W.ln_mlp_g, W.ln_mlp_b = self._vec(g("ln_mlp.weight")), self._vec(g("ln_mlp.bias"))
         W.fc1, W.fc1_b = self._weight(g("mlp.fc1.weight")), self._vec(g("mlp.fc1.bias"))
@@ -147,7 +184,7 @@ class PackedWeights:
         W.scale3, W.scale3_b = self._weight(self._conv3x3_to_gemm(scale("4.weight")), taps=9), self._vec(scale("4.bias"))
         W.lrp3, W.lrp3_b = self._weight(self._conv3x3_to_gemm(lrp("4.weight")), taps=9), self._vec(lrp("4.bias"))
 
-    def dictionary_kv(self, dt, ln_w, ln_b, k_w, k_b, head_scale) -> _lib.DictKV:
+    def dictionary_kv(self, dt, ln_w, ln_b, k_w, k_b, head_scale, slice_index: int = 0) -> _lib.DictKV:
         """K = k(dict_ln(dt)), V = dict_ln(dt), per head [20, 128, 32] (dcae.py:492-495); batch invariant,
         so computed once here with the library's LayerNorm + fp32 GEMM; plus the TF32 hi/lo splits of K and of
         V transposed per head ([20, 32, 128]) that the tcgen05 attention kernel consumes."""
@@ -178,8 +215,7 @@ class PackedWeights:
             setattr(kv, hi_name, hi.data_ptr())
             setattr(kv, lo_name, lo.data_ptr())
         # fp16 planes for the f16x3 attention kernel: K as the [128, 640] matrix itself, V transposed [640, 128]
-        k_hi, k_lo, _, kv.k_descale = f16_weight_planes(lib, k.contiguous(), 1, s)
-        v_hi, v_lo, _, kv.v_descale = f16_weight_planes(lib, d.t().contiguous(), 1, s)
-        kv.K16_hi, kv.K16_lo, kv.Vt16_hi, kv.Vt16_lo = k_hi.data_ptr(), k_lo.data_ptr(), v_hi.data_ptr(), v_lo.data_ptr()
-        self._keep += [k_hi, k_lo, v_hi, v_lo]
+        kc, vt = k.contiguous(), d.t().contiguous()
+        self._keep += [kc, vt]
+        self._pending += [(kc, 1, ("k", slice_index)), (vt, 1, ("v", slice_index))]
         return kv
