@@ -10,7 +10,8 @@ Public surface (mirrors the reference's operator interface for this path only):
   ans.BufferedRansEncoder / RansDecoder -- the native range coder with compressai.ans' interface
   init_entropy_params   -- deterministic random-init weights with the reference's state-dict keys
   TransformStack, accelerate_transforms, init_transform_params -- g_a / g_s / h_a / h_z_s1 / h_z_s2 on the library (dcae_b200/transforms.py)
-  DCAECodec             -- the whole model (forward / compress / decompress / update) from a reference state dict
+  DCAECodec             -- the whole model (forward / compress / decompress / update, image <-> .bin container) from a reference state dict
+  container             -- the reference's bitstream container and image padding (compress_and_decompress.py:48-148)
 """
 from .params import init_entropy_params, entropy_param_shapes  # noqa: F401
 
@@ -35,6 +36,9 @@ def __getattr__(name):
     if name in ("TransformStack", "accelerate_transforms", "init_transform_params", "transform_param_shapes"):
         from . import transforms
         return getattr(transforms, name)
+    if name == "container":
+        import importlib
+        return importlib.import_module(".container", __name__)
     if name == "DCAECodec":
         from .codec import DCAECodec
         return DCAECodec

@@ -93,5 +93,23 @@ class DCAECodec:
         dec = self.loop.decompress_from_string(strings[0][0], latent_scales, latent_means, self.gaussian_conditional)
         return {"x_hat": self.stacks["g_s"](dec["y_hat"]).clamp_(0, 1)}
 
+    # ---- image <-> container (compress_and_decompress.py:150-215: pad to multiples of 128, compress, save_bin / read_bin,
+    # decompress, crop, clamp); one image per container like the reference
+    def encode_image(self, x: torch.Tensor) -> bytes:
+        """x [1, 3, H, W] in [0, 1] (any H, W >= 1 whose padded size is >= 256) -> the reference's .bin container bytes."""
+        from . import container
+        if x.dim() != 4 or x.size(0) != 1:
+            raise ValueError("the container holds one image: expected [1, 3, H, W]")
+        xp, _ = container.pad(x.to(self.device, torch.float32))
+        enc = self.compress(xp)
+        return container.pack_bin(enc["strings"], x.shape[-2:])
+
+    def decode_image(self, blob: bytes) -> torch.Tensor:
+        """-> x_hat [1, 3, H, W] in [0, 1], cropped back to the size stored in the container."""
+        from . import container
+        strings, z_shape, padding, _ = container.unpack_bin(blob)
+        out = self.decompress(strings, z_shape)
+        return container.crop(out["x_hat"], padding).clamp_(0, 1)
+
 
 __all__ = ["DCAECodec"]

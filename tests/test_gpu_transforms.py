@@ -251,3 +251,23 @@ def test_codec_object_forward_compress_decompress(lively_params):
         assert 0.75 * est < bits < 1.25 * est + 512
     finally:
         _reference_flags(False)
+
+
+def test_codec_image_to_container_and_back(lively_params):
+    """compress_and_decompress.py:150-215 end to end on the library: an image whose sides are no multiple of 128 -> centred zero
+    padding -> compress -> the reference's .bin container -> decompress -> crop; equals the forward pass's x_hat."""
+    from dcae_b200 import DCAECodec, container
+    P = dict(lively_params)
+    P.update(init_transform_params(2))
+    codec = DCAECodec(P, device=DEV)
+    codec.update()
+    x = torch.rand(1, 3, 300, 517, generator=_gen(5)).cuda()
+    blob = codec.encode_image(x)
+    h, w = __import__("struct").unpack(">HH", blob[:4])
+    assert (h, w) == (300, 517)
+    x_hat = codec.decode_image(blob)
+    assert x_hat.shape == x.shape and float(x_hat.min()) >= 0.0 and float(x_hat.max()) <= 1.0
+    xp, padding = container.pad(x)
+    want = container.crop(codec.forward(xp)["x_hat"], padding).clamp(0, 1)
+    assert torch.equal(x_hat, want)
+    print(f"\ncontainer: {len(blob)} bytes for a 300x517 image ({8 * len(blob) / (300 * 517):.3f} bpp with random-init weights)")
