@@ -866,7 +866,7 @@ def main():
                    "tf32": "gemm_tcgen05_kernel", "fp32": "gemm_simt_kernel"}[args.math],
         "bound": "tensor", "achieved": gemm_tflops, "peak": tc_peak, "unit": "TFLOP/s", "frac": gemm_tflops / tc_peak,
         "traffic": ncu_traffic("prof_gemm_final_summary.csv") if args.math == "f16x3" else None,
-        "traffic_note": "mean dram__bytes_read + write per launch over the launches of profiles/r01/prof_gemm_final_summary.csv (ncu --set full, same command); operands are L2-resident between layers, so DRAM traffic is below the algorithmic operand bytes",
+        "traffic_note": "mean dram__bytes_read + write per launch over the launches of profiles/r02/prof_gemm_final_summary.csv (ncu --set full, same command); operands are L2-resident between layers, so DRAM traffic is below the algorithmic operand bytes",
         "note": (f"achieved = algorithmic 2*T*N*K flop of all {fam['gemm']['launches_per_step']} dense-layer launches of a step / "
                  f"their summed CUDA-event time; peak = {peaks['src']} sustained dense bf16 (kernel timed inside a long step). "
                  + {"f16": "Reduced-precision fast mode: one fp16 MMA per algorithmic MAC (hi planes only).",

@@ -259,6 +259,8 @@ class LibKernels:
         self.lib = _lib.load()
         self._scratch: Optional[torch.Tensor] = None
         self._pool: Dict[tuple, list] = {}
+        self._pool_bytes = 0
+        self.max_pool_bytes = 64 << 30
 
     # -- helpers
     def _s(self) -> int:
@@ -269,15 +271,32 @@ class LibKernels:
 
     def _take(self, key, make):
         import sys
+        key = key + (self._s(),)                      # reuse is ordered by the stream: one pool per stream
         lst = self._pool.setdefault(key, [])
         for i in range(len(lst)):
             if sys.getrefcount(lst[i]) == 2:          # the list and getrefcount's own argument: nobody else holds it
                 return lst[i]
-        lst.append(make())
-        return lst[-1]
+        if self._pool_bytes > self.max_pool_bytes:    # many different input shapes: drop what is free before growing further
+            self.clear_pool(only_free=True)
+            lst = self._pool.setdefault(key, [])
+        t = make()
+        self._pool_bytes += t.numel() * t.element_size()
+        lst.append(t)
+        return t
 
-    def clear_pool(self) -> None:
-        self._pool.clear()
+    def clear_pool(self, only_free: bool = False) -> None:
+        import sys
+        if not only_free:
+            self._pool.clear()
+            self._pool_bytes = 0
+            return
+        for key in list(self._pool):
+            kept = []
+            for i in range(len(self._pool[key])):
+                if sys.getrefcount(self._pool[key][i]) > 2:
+                    kept.append(self._pool[key][i])
+            self._pool[key] = kept
+        self._pool_bytes = sum(t.numel() * t.element_size() for lst in self._pool.values() for t in lst)
 
     def _f32(self, T: int, ld: int, cols: int) -> torch.Tensor:
         """fp32 [T, ld] of which a kernel writes the first `cols` columns; the rest stays zero."""
