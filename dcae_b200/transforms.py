@@ -246,9 +246,10 @@ class LibKernels:
     conv, GEMM epilogue, space-to-depth / depth-to-space), fp32 for residuals and element-wise consumers -- so no
     conversion pass runs between layers and nothing is written that nobody reads.  Other math modes stay fp32.
 
-    Buffers come from a pool keyed by (kind, rows, columns, written columns): a buffer whose only reference is the pool's
-    is free (everything runs on one stream, so reuse is ordered).  Planes are allocated pad64(columns) wide and zeroed
-    once; no kernel writes the padding, which the GEMM's 64-column TMA boxes over-read against zero weights."""
+    Buffers with padding columns (planes are pad64(columns) wide because the GEMM's 64-column TMA boxes over-read the
+    padding against zero weights; LayerNorm / attention outputs of the 144-channel level) come from a pool keyed by
+    (kind, rows, columns, written columns, stream): zeroed once, no kernel ever writes the padding, and a buffer whose
+    only reference is the pool's is free (reuse is ordered by the stream).  Everything else is torch.empty."""
 
     def __init__(self, device="cuda:0", math: str = "f16x3"):
         if math not in _lib.MATH:
@@ -299,15 +300,18 @@ class LibKernels:
         self._pool_bytes = sum(t.numel() * t.element_size() for lst in self._pool.values() for t in lst)
 
     def _f32(self, T: int, ld: int, cols: int) -> torch.Tensor:
-        """fp32 [T, ld] of which a kernel writes the first `cols` columns; the rest stays zero."""
-        make = (lambda: torch.zeros(T, ld, device=self.device)) if ld > cols else (lambda: torch.empty(T, ld, device=self.device))
-        return self._take(("f32", T, ld, cols), make)
+        """fp32 [T, ld] of which a kernel writes the first `cols` columns; the rest stays zero (pooled: zeroed once).
+        Fully written buffers come from torch's caching allocator, which shares memory across shapes."""
+        if ld == cols:
+            return torch.empty(T, ld, device=self.device)
+        return self._take(("f32", T, ld, cols), lambda: torch.zeros(T, ld, device=self.device))
 
-    def _p16(self, T: int, cols: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    def _p16(self, T: int, cols: int) -> torch.Tensor:
+        """[2, T, pad64(cols)] fp16: hi = [0], lo = [1]."""
         ld = pad64(cols)
-        z = torch.zeros if ld > cols else torch.empty
-        pair = self._take(("p16", T, ld, cols), lambda: torch.stack([z(T, ld, dtype=torch.float16, device=self.device) for _ in range(2)]))
-        return pair            # [2, T, ld]: hi = pair[0], lo = pair[1]
+        if ld == cols:
+            return torch.empty(2, T, ld, dtype=torch.float16, device=self.device)
+        return self._take(("p16", T, ld, cols), lambda: torch.zeros(2, T, ld, dtype=torch.float16, device=self.device))
 
     @staticmethod
     def _pl(p16) -> _lib.Planes:
