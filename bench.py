@@ -715,6 +715,7 @@ def main():
     ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the eager-PyTorch-on-GPU oracle leg")
     ap.add_argument("--no-clock-sampler", action="store_true", help="diagnostic: do not poll NVML during the timed region")
     ap.add_argument("--gc-micro-mb", type=int, default=1024, help="footprint of the kernel-3 HBM microbenchmark")
+    ap.add_argument("--no-whole-codec", action="store_true", help="skip the secondary whole-model figure of the default line")
     args = ap.parse_args()
     if args.mode:
         CONFIGS[args.config] = dict(CONFIGS[args.config], mode=args.mode)
@@ -915,6 +916,15 @@ def main():
         except Exception as e:                      # noqa: BLE001  (a baseline leg must never take the bench line down)
             torch_gpu_baseline = {"value": None, "error": repr(e)[:200]}
 
+    # secondary figure (never the headline): the WHOLE model on the library, SURVEY 8f N3 / N4 -- see `--config 6` for the full line
+    whole_codec = None
+    if rank == 0 and world == 1 and args.config == 2 and not args.no_whole_codec:
+        try:
+            torch.cuda.empty_cache()
+            whole_codec = whole_codec_figure(dev, args.math, B, cfg)
+        except Exception as e:                      # noqa: BLE001
+            whole_codec = {"value": None, "error": repr(e)[:200]}
+
     if rank == 0:
         imgs = B * world
         line = {
@@ -945,10 +955,44 @@ def main():
             "bpp": bpp,
             "cpu_baseline": cpu_baseline,
             "torch_gpu_baseline": torch_gpu_baseline,
+            "whole_codec": whole_codec,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def whole_codec_figure(dev, math, B, cfg):
+    """`DCAECodec.forward` (g_a, h_a, entropy bottleneck, h_z_s1 / h_z_s2, slice loop, g_s) on B images of the config's size:
+    5 device-timed steps after 3 warm-ups, plus the per-stage CUDA-event times of one more."""
+    from dcae_b200.codec import DCAECodec
+    codec = DCAECodec(_codec_params(), device=dev, math=math)
+    H, W = (cfg["H"] + 127) // 128 * 128, (cfg["W"] + 127) // 128 * 128
+    x = torch.rand(B, 3, H, W, generator=torch.Generator().manual_seed(1234)).to(dev)
+    for _ in range(3):
+        codec.forward(x)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        codec.forward(x)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    names = ("g_a", "h_a", "entropy_bottleneck", "h_z_s1", "h_z_s2", "slice_loop", "g_s")
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
+    ev[0].record()
+    y = codec.stacks["g_a"](x); ev[1].record()
+    z = codec.stacks["h_a"](y); ev[2].record()
+    z_hat, _ = codec.entropy_bottleneck(z, training=False); ev[3].record()
+    ls = codec.stacks["h_z_s1"](z_hat); ev[4].record()
+    lm = codec.stacks["h_z_s2"](z_hat); ev[5].record()
+    o = codec.loop.forward(y, ls, lm); ev[6].record()
+    codec.stacks["g_s"](o["y_hat"]); ev[7].record()
+    torch.cuda.synchronize()
+    return {"metric": "whole-codec images/sec @768x512 (secondary figure; `bench.py --config 6` prints the full line)", "value": B / (ms * 1e-3), "unit": "images/s",
+            "ms_per_step": ms, "batch": B, "stages_ms": {n: ev[i].elapsed_time(ev[i + 1]) for i, n in enumerate(names)},
+            "what": "DCAECodec.forward = the reference's whole DCAE.forward (dcae.py:623-677) on libdcae_b200.so, inputs resident, 5 steps after 3 warm-ups"}
 
 
 def gc_microbench(dev, lib, mb, peaks, variant="compress", lik_math="fast"):
