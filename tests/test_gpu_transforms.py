@@ -271,3 +271,35 @@ def test_codec_image_to_container_and_back(lively_params):
     want = container.crop(codec.forward(xp)["x_hat"], padding).clamp(0, 1)
     assert torch.equal(x_hat, want)
     print(f"\ncontainer: {len(blob)} bytes for a 300x517 image ({8 * len(blob) / (300 * 517):.3f} bpp with random-init weights)")
+
+
+def test_codec_cuda_graph_replay(lively_params):
+    """DCAECodec.capture(): the whole forward (561 launches, the slice loop's lanes and side stream included) as one CUDA
+    graph; the input is captured by address, every replay gives the bits of the eager call."""
+    import time
+    from dcae_b200 import DCAECodec
+    P = dict(lively_params)
+    P.update(init_transform_params(2))
+    codec = DCAECodec(P, device=DEV)
+    x = torch.rand(1, 3, 512, 768, generator=_gen(41)).cuda()
+    want = {k: v.clone() for k, v in (("x_hat", codec.forward(x)["x_hat"]), ("y", codec.forward(x)["para"]["y"]), ("lik", codec.forward(x)["likelihoods"]["y"]))}
+    replay, out = codec.capture(x)
+    replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out["x_hat"], want["x_hat"]) and torch.equal(out["para"]["y"], want["y"]) and torch.equal(out["likelihoods"]["y"], want["lik"])
+    x2 = torch.rand(1, 3, 512, 768, generator=_gen(42)).cuda()
+    want2 = codec.forward(x2)["x_hat"].clone()
+    x.copy_(x2)
+    replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out["x_hat"], want2)
+
+    def timed(fn, n=20):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(n):
+            fn()
+        torch.cuda.synchronize()
+        return 1e3 * (time.perf_counter() - t0) / n
+    t_eager, t_graph = timed(lambda: codec.forward(x)), timed(replay)
+    print(f"\nwhole codec, one 768x512 image: {t_eager:.2f} ms per eager forward (stream launches), {t_graph:.2f} ms per graph replay")
