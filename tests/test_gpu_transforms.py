@@ -303,3 +303,42 @@ def test_codec_cuda_graph_replay(lively_params):
         return 1e3 * (time.perf_counter() - t0) / n
     t_eager, t_graph = timed(lambda: codec.forward(x)), timed(replay)
     print(f"\nwhole codec, one 768x512 image: {t_eager:.2f} ms per eager forward (stream launches), {t_graph:.2f} ms per graph replay")
+
+
+@pytest.mark.skipif(not reference_available(), reason="reference models/dcae.py not staged")
+def test_reference_compress_decompress_text_with_everything_on_the_library(lively_params):
+    """The REAL `DCAE` class: `compress()` and `decompress()` (dcae.py:698-761, 859-910) run as written with ALL sub-modules
+    on the library -- transforms (accelerate_transforms), slice loop + GaussianConditional (accelerate), EntropyBottleneck,
+    the native coder for both strings.  With torch's h_z_s / g_s convolutions out of the picture the decoder regenerates the
+    encoder's tensors bit for bit WITHOUT the reference's cuDNN-off flag: x_hat(decompress) == clamp(x_hat(forward)) exactly."""
+    import tempfile
+    from dcae_b200 import EntropyBottleneck, accelerate, ans
+    from dcae_b200.transforms import accelerate_transforms
+    from oracle import entropy_bottleneck as oeb
+    from oracle.reference_loader import build_reference_net
+    P = dict(lively_params)
+    P.update(init_transform_params(2))
+    net = build_reference_net(P).cuda().eval()
+    eb = EntropyBottleneck(192)
+    eb.load_state_dict(oeb.init_params(192, seed=4, trained_like=True), strict=False)
+    eb.update()
+    net.entropy_bottleneck = eb.cuda().eval()
+    accelerate(net, device=DEV)
+    accelerate_transforms(net, device=DEV)
+    ref = load_reference_dcae_module()
+    saved = ref.BufferedRansEncoder, ref.RansDecoder
+    ref.BufferedRansEncoder, ref.RansDecoder = ans.BufferedRansEncoder, ans.RansDecoder
+    x = torch.rand(1, 3, 256, 256, generator=_gen(8)).cuda()
+    cwd = os.getcwd()
+    try:
+        with tempfile.TemporaryDirectory() as td, torch.no_grad():
+            os.makedirs(os.path.join(td, "output", "debug"))           # compress() writes debug dumps there (dcae.py:707, 758)
+            os.chdir(td)
+            enc = net.compress(x)
+            dec = net.decompress(enc["strings"], enc["shape"])
+            fwd = net(x)
+    finally:
+        os.chdir(cwd)
+        ref.BufferedRansEncoder, ref.RansDecoder = saved
+    assert isinstance(enc["strings"][0][0], bytes) and isinstance(enc["strings"][1][0], bytes)
+    assert torch.equal(dec["x_hat"], fwd["x_hat"].clamp(0, 1))
