@@ -592,9 +592,20 @@ class TransformStack:
         self.c_in = first[1]
         self.c_out = last[2]
 
+    # widest intermediate of a stack, in fp32 elements per input position (tokens of the finest level x its widest buffer,
+    # the fc1 output of 4 C columns): the element-wise kernels address with 32-bit offsets, so one call must stay below 2^32
+    _ELEMS_PER_INPUT_POSITION = {"g_a": 4 * 96 / 4, "g_s": 64 * 4 * 96, "h_a": 4 * 192 / 4, "h_z_s1": 16 * 4 * 320, "h_z_s2": 16 * 4 * 320}
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         if x.dim() != 4 or x.shape[1] != self.c_in:
             raise ValueError(f"{self.stack}: expected [B, {self.c_in}, H, W], got {tuple(x.shape)}")
+        per_image = x.shape[2] * x.shape[3] * self._ELEMS_PER_INPUT_POSITION[self.stack]
+        max_b = max(1, int((1 << 31) // max(per_image, 1)))           # half of the limit: headroom for padded widths
+        if x.shape[0] > max_b:                                         # images are independent: run the batch in slices
+            return torch.cat([self._forward(x[i:i + max_b]) for i in range(0, x.shape[0], max_b)], dim=0)
+        return self._forward(x)
+
+    def _forward(self, x: torch.Tensor) -> torch.Tensor:
         K = self.K
         blocks = self.blocks
         # the first operator decides the entry layout: a stride-2 conv reads C fp32 columns of any ld, a GEMM reads pad32(C)

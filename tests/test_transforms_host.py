@@ -148,3 +148,14 @@ def test_golden_fixture_is_reproduced_by_the_emulated_composition(stack):
     ts = TransformStack(stack, init_transform_params(0, (stack,)), kernels=TorchKernels())
     got = ts.forward(transform_golden_input(stack))
     assert got.shape == want.shape and rel_err(got, want) < 2e-5
+
+
+def test_large_batches_run_in_slices():
+    """One call must stay below 2^32 elements per buffer (32-bit offsets in the element-wise kernels): bigger batches are cut
+    into slices of independent images; the result is the same bits."""
+    from dcae_b200.transforms import init_transform_params
+    ts = TransformStack("h_a", init_transform_params(0, ("h_a",)), kernels=TorchKernels())
+    x = torch.randn(3, 320, 16, 16, generator=torch.Generator().manual_seed(1))
+    whole = ts.forward(x)
+    ts._ELEMS_PER_INPUT_POSITION = dict(ts._ELEMS_PER_INPUT_POSITION, h_a=(1 << 31) / (16 * 16) / 2 + 1)      # forces slices of one image
+    assert torch.equal(ts.forward(x), whole)
