@@ -149,7 +149,8 @@ def test_stack_against_the_reference_golden(stack, math):
 
 
 @pytest.mark.skipif(not reference_available(), reason="reference models/dcae.py not staged")
-@pytest.mark.parametrize("stack,shape", [("g_a", (2, 3, 256, 384)), ("g_s", (2, 320, 16, 24)), ("h_a", (2, 320, 32, 48)), ("h_z_s1", (2, 192, 8, 12))])
+@pytest.mark.parametrize("stack,shape", [("g_a", (2, 3, 256, 384)), ("g_s", (2, 320, 16, 24)), ("h_a", (2, 320, 32, 48)), ("h_z_s1", (2, 192, 8, 12)),
+                                         ("g_a", (2, 3, 512, 768)), ("g_s", (2, 320, 32, 48)), ("h_z_s2", (2, 192, 8, 12))])   # Kodak-sized (config #2)
 def test_stack_against_the_reference_module_kodak_sized_tiles(stack, shape):
     """Larger, non-square, B = 2: the reference's real module (CPU fp32) on the same weights and input."""
     ref = load_reference_dcae_module()
