@@ -34,6 +34,7 @@ with open(out_path, "w") as f:
         if c["total"] == 0:
             continue
         tot.update(c)
+        name = name.replace("(anonymous namespace)::", "")
         name = re.sub(r"\(.*", "", name).replace("void ", "").replace("dcae::", "")[:94]
         f.write(f"{name:96s} {c['total']:6d} " + " ".join(f"{c[p]:12d}" for p in pats) + "\n")
     f.write(f"{'ALL KERNELS':96s} {tot['total']:6d} " + " ".join(f"{tot[p]:12d}" for p in pats) + "\n")
