@@ -99,3 +99,27 @@ def test_product_never_imports_the_oracle():
         for f in fs:
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 assert "oracle" not in open(os.path.join(dp, f)).read().replace("cpu_baseline", ""), f
+
+
+def test_transform_operators_validate_their_arguments_before_any_launch(lib):
+    """The argument checks of the transform-stack operators (include/dcae_b200.h) answer DCAE_E_INVALID with a message and
+    launch nothing: callable without a GPU (pointers are never dereferenced on the host)."""
+    fake = 0x1000                       # a non-null, 16-byte aligned "device pointer"
+    err = lambda: lib.dcae_last_error().decode()
+    # window 5 is not supported; head_dim must divide C; grid must be a multiple of the window; shift is 0 or window / 2
+    assert lib.dcae_op_window_attention(fake, 288, 0, 96, 192, 96, 8, 5, 0, fake, 1, 16, 16, fake, 96, None, None) == -1 and "window" in err()
+    assert lib.dcae_op_window_attention(fake, 288, 0, 96, 192, 100, 8, 8, 0, fake, 1, 16, 16, fake, 100, None, None) == -1 and "head_dim" in err()
+    assert lib.dcae_op_window_attention(fake, 288, 0, 96, 192, 96, 8, 8, 0, fake, 1, 12, 16, fake, 96, None, None) == -1 and "multiple of the window" in err()
+    assert lib.dcae_op_window_attention(fake, 288, 0, 96, 192, 96, 8, 8, 3, fake, 1, 16, 16, fake, 96, None, None) == -1 and "shift" in err()
+    assert lib.dcae_op_window_attention(fake, 200, 0, 96, 192, 96, 8, 8, 0, fake, 1, 16, 16, fake, 96, None, None) == -1 and "leading dimension" in err()
+    assert lib.dcae_op_window_attention(None, 288, 0, 96, 192, 96, 8, 8, 0, fake, 1, 16, 16, fake, 96, None, None) == -1
+    # B = 0: nothing to do, no launch
+    assert lib.dcae_op_window_attention(fake, 288, 0, 96, 192, 96, 8, 8, 0, fake, 0, 16, 16, fake, 96, None, None) == 0
+    # space-to-depth: the slot must hold the channels and be a multiple of 4; depth-to-space: the input must hold 4 slots
+    assert lib.dcae_op_space_to_depth(fake, 96, 96, 90, 1, 8, 8, fake, 384, None, None) == -1 and "Cs" in err()
+    assert lib.dcae_op_space_to_depth(fake, 96, 96, 96, 1, 8, 8, fake, 380, None, None) == -1
+    assert lib.dcae_op_depth_to_space(fake, 100, 96, 96, 96, 1, 8, 8, fake, 96, None, None) == -1 and "ld" in err()
+    assert lib.dcae_op_depth_to_space(fake, 384, 96, 96, 64, 1, 8, 8, fake, 96, None, None) == -1
+    # LayerNorm: any multiple of 4 up to 1024 now, nothing else
+    assert lib.dcae_op_layernorm(fake, 96, fake, fake, 98, 10, fake, 96, None, None) == -1 and "multiple of 4" in err()
+    assert lib.dcae_op_layernorm(fake, 96, fake, fake, 96, 0, fake, 96, None, None) == 0
