@@ -9,6 +9,7 @@
 //     GEMM (kernel 2) unchanged.
 // All HBM-bound, fp32 in / fp32 (+ optional fp16 hi/lo planes) out, no atomics, deterministic.
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -220,6 +221,178 @@ __global__ void __launch_bounds__(2 * P * P) window_attention_kernel(const WinAr
 }
 
 // ---------------------------------------------------------------------------------------------
+// The same operator for 8x8 windows on the warp-level tensor-core path: S = Q K^T and O = P V as m16n8k8 TF32 MMAs with
+// the 3-pass hi/lo split (a_lo b_hi + a_hi b_lo + a_hi b_hi, fp32 accumulate: 21 significant bits per operand, the same
+// class of accuracy as the f16x3 GEMMs).  One block = one window = 4 warps, warp w owns query rows [16 w, 16 w + 16) (window
+// rows 2 w and 2 w + 1) against all 64 keys; K and V of the head sit in shared memory already split into TF32 hi / lo
+// (rows padded to HD + 4 words: conflict-free fragment loads).  The probabilities never change registers between the two
+// products: with the key order inside a k-step chosen as (2t, 2t + 1) <-> slots (t, t + 4), the C fragment of S IS the A
+// fragment of P V.  [A 64-token window is too small a tile for tcgen05 (M = 128 per instruction and a TMEM round trip per
+// head); the SIMT kernel above measured 15 TFLOP/s, bound by shared-memory reads.]
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float to_tf32(float v) {
+  uint32_t o;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(o) : "f"(v));
+  return __uint_as_float(o);
+}
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&d)[4], const float (&a)[4], float b0, float b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(__float_as_uint(a[0])), "r"(__float_as_uint(a[1])), "r"(__float_as_uint(a[2])), "r"(__float_as_uint(a[3])),
+                 "r"(__float_as_uint(b0)), "r"(__float_as_uint(b1)));
+}
+
+template <int HD>
+__global__ void __launch_bounds__(128) window_attention_mma_kernel(const WinArgs a, int C) {
+  // heads are walked in groups of G (GW = G HD contiguous q / k / v columns per shared-memory fill).  G = 32 / HD was measured
+  // (one fill and one barrier pair per 32 columns): head_dim 8 lost 16 % because 41 KB of shared memory per block leave 5
+  // blocks per SM instead of 16; G = 1 it is
+  constexpr int P = 8, PP = 64, G = 1, GW = G * HD, LDS = GW + 4, R = 2 * P - 1, KSTEPS = HD / 8, NT = 128;
+  __shared__ __align__(16) float skh[PP * LDS], skl[PP * LDS], svh[PP * LDS], svl[PP * LDS];
+  __shared__ float sbias[G * R * R];
+  __shared__ int64_t stok[PP];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int wx = (int)(blockIdx.x % a.nwx), wy = (int)(blockIdx.x / a.nwx), b = (int)blockIdx.y;
+  if (tid < PP) {
+    int yy = wy * P + tid / P + a.shift; if (yy >= a.h) yy -= a.h;
+    int xx = wx * P + tid % P + a.shift; if (xx >= a.w) xx -= a.w;
+    stok[tid] = ((int64_t)b * a.h + yy) * a.w + xx;
+  }
+  const bool last_row = a.shift > 0 && wy == a.nwy - 1, last_col = a.shift > 0 && wx == a.nwx - 1;
+  const int sp = P - a.shift;
+  // this thread's two query rows: window position (py, px) = (2 warp + r, g)
+  const int py0 = 2 * warp, px = g;
+  __syncthreads();
+  const int64_t tok0 = stok[16 * warp + g], tok1 = stok[16 * warp + g + 8];
+  for (int e0 = 0; e0 < a.n_heads; e0 += G) {
+    __syncthreads();                       // the previous group is done with shared memory
+    for (int idx = tid; idx < PP * (GW / 4); idx += NT) {
+      const int tk = idx / (GW / 4), d4 = idx - tk * (GW / 4);
+      const int col = e0 * HD + 4 * d4;                       // column inside the q / k / v segment (a tail group ends at C)
+      float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
+      if (col < C) {
+        const float* row = a.qkv + stok[tk] * a.ld + col;
+        kv = __ldg(reinterpret_cast<const float4*>(row + a.k_col));
+        vv = __ldg(reinterpret_cast<const float4*>(row + a.v_col));
+      }
+      float4 kh, kl, vh, vl;
+      kh.x = to_tf32(kv.x); kh.y = to_tf32(kv.y); kh.z = to_tf32(kv.z); kh.w = to_tf32(kv.w);
+      kl.x = to_tf32(kv.x - kh.x); kl.y = to_tf32(kv.y - kh.y); kl.z = to_tf32(kv.z - kh.z); kl.w = to_tf32(kv.w - kh.w);
+      vh.x = to_tf32(vv.x); vh.y = to_tf32(vv.y); vh.z = to_tf32(vv.z); vh.w = to_tf32(vv.w);
+      vl.x = to_tf32(vv.x - vh.x); vl.y = to_tf32(vv.y - vh.y); vl.z = to_tf32(vv.z - vh.z); vl.w = to_tf32(vv.w - vh.w);
+      *reinterpret_cast<float4*>(skh + tk * LDS + 4 * d4) = kh;
+      *reinterpret_cast<float4*>(skl + tk * LDS + 4 * d4) = kl;
+      *reinterpret_cast<float4*>(svh + tk * LDS + 4 * d4) = vh;
+      *reinterpret_cast<float4*>(svl + tk * LDS + 4 * d4) = vl;
+    }
+    for (int i = tid; i < G * R * R; i += NT) sbias[i] = (e0 + i / (R * R) < a.n_heads) ? __ldg(a.rel + (int64_t)e0 * R * R + i) : 0.f;
+    __syncthreads();
+#pragma unroll 1
+    for (int eg = 0; eg < G; ++eg) {
+      const int e = e0 + eg;
+      if (e >= a.n_heads) break;
+      const int hc = eg * HD;              // the head's first column inside the group tile
+      // Q fragments (A operand, 16 x 8 per k-step): a0 = (g, t), a1 = (g + 8, t), a2 = (g, t + 4), a3 = (g + 8, t + 4)
+      float qh[KSTEPS][4], ql[KSTEPS][4];
+      {
+        const float* q0 = a.qkv + tok0 * a.ld + a.q_col + e * HD;
+        const float* q1 = a.qkv + tok1 * a.ld + a.q_col + e * HD;
+#pragma unroll
+        for (int ks = 0; ks < KSTEPS; ++ks) {
+          const float v[4] = {__ldg(q0 + 8 * ks + t), __ldg(q1 + 8 * ks + t), __ldg(q0 + 8 * ks + t + 4), __ldg(q1 + 8 * ks + t + 4)};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { qh[ks][i] = to_tf32(v[i]); ql[ks][i] = to_tf32(v[i] - qh[ks][i]); }
+        }
+      }
+      // S = Q K^T: 8 key tiles of 8; B fragment b0 = K[key n0 + g][8 ks + t], b1 = K[key n0 + g][8 ks + t + 4]
+      float sc[8][4];
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) sc[nt][i] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < KSTEPS; ++ks) {
+          const int o = (8 * nt + g) * LDS + hc + 8 * ks + t;
+          const float bh0 = skh[o], bh1 = skh[o + 4], bl0 = skl[o], bl1 = skl[o + 4];
+          mma_tf32_16x8x8(sc[nt], ql[ks], bh0, bh1);
+          mma_tf32_16x8x8(sc[nt], qh[ks], bl0, bl1);
+          mma_tf32_16x8x8(sc[nt], qh[ks], bh0, bh1);
+        }
+      }
+      // C fragment: c0 = (g, 2t), c1 = (g, 2t + 1), c2 = (g + 8, 2t), c3 = (g + 8, 2t + 1) of key tile nt -> key (qy, qx) = (nt, 2t + i)
+      const float* bias = sbias + eg * R * R;
+      float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = i >> 1, qx = 2 * t + (i & 1), py = py0 + r, qy = nt;
+          const float v = sc[nt][i] * a.scale + bias[(py - qy + P - 1) * R + (px - qx + P - 1)];
+          const bool masked = (last_row && ((py < sp) != (qy < sp))) || (last_col && ((px < sp) != (qx < sp)));
+          sc[nt][i] = masked ? -INFINITY : v;
+        }
+        m0 = fmaxf(m0, fmaxf(sc[nt][0], sc[nt][1]));
+        m1 = fmaxf(m1, fmaxf(sc[nt][2], sc[nt][3]));
+      }
+      m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+      m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+      float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        sc[nt][0] = expf(sc[nt][0] - m0); sc[nt][1] = expf(sc[nt][1] - m0);
+        sc[nt][2] = expf(sc[nt][2] - m1); sc[nt][3] = expf(sc[nt][3] - m1);
+        s0 += sc[nt][0] + sc[nt][1];
+        s1 += sc[nt][2] + sc[nt][3];
+      }
+      s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+      const float i0 = 1.0f / s0, i1 = 1.0f / s1;
+      // O = P V: k-step j = key tile j with slot t <-> key 8j + 2t, slot t + 4 <-> key 8j + 2t + 1, so that the A fragment
+      // (a0, a1, a2, a3) is (c0, c2, c1, c3) of S; B fragment b0 = V[8j + 2t][n0 + g], b1 = V[8j + 2t + 1][n0 + g]
+      float oc[KSTEPS][4];
+#pragma unroll
+      for (int nd = 0; nd < KSTEPS; ++nd) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) oc[nd][i] = 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float pv[4] = {sc[j][0] * i0, sc[j][2] * i1, sc[j][1] * i0, sc[j][3] * i1};
+        float ph[4], pl[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { ph[i] = to_tf32(pv[i]); pl[i] = to_tf32(pv[i] - ph[i]); }
+#pragma unroll
+        for (int nd = 0; nd < KSTEPS; ++nd) {
+          const int o = (8 * j + 2 * t) * LDS + hc + 8 * nd + g;
+          const float bh0 = svh[o], bh1 = svh[o + LDS], bl0 = svl[o], bl1 = svl[o + LDS];
+          mma_tf32_16x8x8(oc[nd], pl, bh0, bh1);
+          mma_tf32_16x8x8(oc[nd], ph, bl0, bl1);
+          mma_tf32_16x8x8(oc[nd], ph, bh0, bh1);
+        }
+      }
+      // rows g (tok0) and g + 8 (tok1), dims 8 nd + 2t, 2t + 1
+#pragma unroll
+      for (int nd = 0; nd < KSTEPS; ++nd) {
+        const int col = e * HD + 8 * nd + 2 * t;
+        if (a.out) {
+          *reinterpret_cast<float2*>(a.out + tok0 * a.out_ld + col) = make_float2(oc[nd][0], oc[nd][1]);
+          *reinterpret_cast<float2*>(a.out + tok1 * a.out_ld + col) = make_float2(oc[nd][2], oc[nd][3]);
+        }
+        if (a.o16.hi) {
+          uint32_t hw, lw;
+          f16_split2(oc[nd][0], oc[nd][1], hw, lw);
+          *reinterpret_cast<uint32_t*>(static_cast<__half*>(a.o16.hi) + tok0 * a.o16.ld + col) = hw;
+          *reinterpret_cast<uint32_t*>(static_cast<__half*>(a.o16.lo) + tok0 * a.o16.ld + col) = lw;
+          f16_split2(oc[nd][2], oc[nd][3], hw, lw);
+          *reinterpret_cast<uint32_t*>(static_cast<__half*>(a.o16.hi) + tok1 * a.o16.ld + col) = hw;
+          *reinterpret_cast<uint32_t*>(static_cast<__half*>(a.o16.lo) + tok1 * a.o16.ld + col) = lw;
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // space-to-depth: out[(b, y', x'), (sy*2 + sx) * Cs + c] = x[(b, 2y' + sy, 2x' + sx), c]  (0 outside / for c >= C)
 // depth-to-space: out[(b, 2y + py, 2x + px), c] = x[(b, y, x), (py*2 + px) * Cs + c]     (0 for C <= c < Cpad)
 // one thread per output float4 (scalar variant when a channel count is not a multiple of 4)
@@ -335,9 +508,17 @@ extern "C" int dcae_op_window_attention(const float* qkv, int64_t ld, int32_t q_
   a.out = out; a.out_ld = out_ld; a.o16 = o16;
   const dim3 grid((unsigned)(a.nwx * a.nwy), (unsigned)B);
   cudaStream_t s = (cudaStream_t)stream;
+  // 8x8 windows: the warp-MMA kernel (3 x TF32); DCAE_WIN_MMA = 0 selects the fp32 FFMA kernel (the cross-check); 4x4 windows: FFMA
+  static const int use_mma = [] { const char* v = getenv("DCAE_WIN_MMA"); return v ? atoi(v) : 1; }();
+  if (window == 8 && use_mma) {
+    if (head_dim == 8) window_attention_mma_kernel<8><<<grid, 128, 0, s>>>(a, C);
+    else if (head_dim == 16) window_attention_mma_kernel<16><<<grid, 128, 0, s>>>(a, C);
+    else window_attention_mma_kernel<32><<<grid, 128, 0, s>>>(a, C);
+  } else {
 #define WIN_CASE(HD, P) if (head_dim == HD && window == P) window_attention_kernel<HD, P><<<grid, 2 * P * P, 0, s>>>(a);
-  WIN_CASE(8, 4) WIN_CASE(16, 4) WIN_CASE(32, 4) WIN_CASE(8, 8) WIN_CASE(16, 8) WIN_CASE(32, 8)
+    WIN_CASE(8, 4) WIN_CASE(16, 4) WIN_CASE(32, 4) WIN_CASE(8, 8) WIN_CASE(16, 8) WIN_CASE(32, 8)
 #undef WIN_CASE
+  }
   DCAE_LAUNCH_CHECK();
   return DCAE_OK;
 }

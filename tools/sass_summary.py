@@ -1,6 +1,6 @@
 """Static per-kernel SASS instruction counts of libdcae_b200.so -> profiles/r02/sass_summary.txt
 (tcgen05.mma = UTCHMMA, .2CTA = cta_group::2; tcgen05.ld / st = LDTM / STTM; TMA = UTMALDG / UTMASTG;
-tcgen05.commit = UTCBAR; mbarrier = SYNCS).   python tools/sass_summary.py [out.txt]"""
+tcgen05.commit = UTCBAR; mbarrier = SYNCS; HMMA = warp-level mma.sync, the window attention).   python tools/sass_summary.py [out.txt]"""
 import collections
 import os
 import re
@@ -10,7 +10,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 out_path = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "profiles", "r02", "sass_summary.txt")
 sass = subprocess.run(["cuobjdump", "-sass", os.path.join(ROOT, "dcae_b200", "libdcae_b200.so")], capture_output=True, text=True).stdout
-pats = ["UTCHMMA", "UTCHMMA.2CTA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UTCBAR", "SYNCS", "MUFU"]
+pats = ["UTCHMMA", "UTCHMMA.2CTA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UTCBAR", "SYNCS", "MUFU", "HMMA"]
 cur, counts = None, collections.OrderedDict()
 for line in sass.splitlines():
     m = re.match(r"\s*Function : (\S+)", line)
