@@ -322,15 +322,29 @@ __global__ void __launch_bounds__(128) window_attention_mma_kernel(const WinArgs
       // C fragment: c0 = (g, 2t), c1 = (g, 2t + 1), c2 = (g + 8, 2t), c3 = (g + 8, 2t + 1) of key tile nt -> key (qy, qx) = (nt, 2t + i)
       const float* bias = sbias + eg * R * R;
       float m0 = -INFINITY, m1 = -INFINITY;
+      if (last_row || last_col) {          // block-uniform: only the last window row / column of an SW layer carries a mask
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int r = i >> 1, qx = 2 * t + (i & 1), py = py0 + r, qy = nt;
+            const float v = sc[nt][i] * a.scale + bias[(py - qy + P - 1) * R + (px - qx + P - 1)];
+            const bool masked = (last_row && ((py < sp) != (qy < sp))) || (last_col && ((px < sp) != (qx < sp)));
+            sc[nt][i] = masked ? -INFINITY : v;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int r = i >> 1, qx = 2 * t + (i & 1), py = py0 + r, qy = nt;
+            sc[nt][i] = sc[nt][i] * a.scale + bias[(py - qy + P - 1) * R + (px - qx + P - 1)];
+          }
+        }
+      }
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int r = i >> 1, qx = 2 * t + (i & 1), py = py0 + r, qy = nt;
-          const float v = sc[nt][i] * a.scale + bias[(py - qy + P - 1) * R + (px - qx + P - 1)];
-          const bool masked = (last_row && ((py < sp) != (qy < sp))) || (last_col && ((px < sp) != (qx < sp)));
-          sc[nt][i] = masked ? -INFINITY : v;
-        }
         m0 = fmaxf(m0, fmaxf(sc[nt][0], sc[nt][1]));
         m1 = fmaxf(m1, fmaxf(sc[nt][2], sc[nt][3]));
       }
@@ -357,7 +371,7 @@ __global__ void __launch_bounds__(128) window_attention_mma_kernel(const WinArgs
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float pv[4] = {sc[j][0] * i0, sc[j][2] * i1, sc[j][1] * i0, sc[j][3] * i1};
+        const float pv[4] = {sc[j][0], sc[j][2], sc[j][1], sc[j][3]};          // unnormalised (max-subtracted: in (0, 1]); 1 / sum goes onto O
         float ph[4], pl[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) { ph[i] = to_tf32(pv[i]); pl[i] = to_tf32(pv[i] - ph[i]); }
@@ -373,6 +387,7 @@ __global__ void __launch_bounds__(128) window_attention_mma_kernel(const WinArgs
       // rows g (tok0) and g + 8 (tok1), dims 8 nd + 2t, 2t + 1
 #pragma unroll
       for (int nd = 0; nd < KSTEPS; ++nd) {
+        oc[nd][0] *= i0; oc[nd][1] *= i0; oc[nd][2] *= i1; oc[nd][3] *= i1;
         const int col = e * HD + 8 * nd + 2 * t;
         if (a.out) {
           *reinterpret_cast<float2*>(a.out + tok0 * a.out_ld + col) = make_float2(oc[nd][0], oc[nd][1]);
