@@ -137,6 +137,7 @@ struct ProfileScope {
   ~ProfileScope();
   int slot;
   void* stream;
+  bool nvtx;
 };
 
 bool profiling_on();
