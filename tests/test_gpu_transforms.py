@@ -20,7 +20,7 @@ pytestmark = pytest.mark.gpu
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
 DEV = "cuda:0"
 # fp32-parity modes; the stacks are ~90 dependent dense layers deep, so the per-tensor bound is looser than one layer's
-STACK_TOL = {"f16x3": 5e-5, "fp32": 2e-5}
+STACK_TOL = {"f16x3": 5e-5, "fp32": 2e-5, "tf32x3": 5e-5}
 
 
 def _gen(seed):
@@ -343,3 +343,14 @@ def test_reference_compress_decompress_text_with_everything_on_the_library(livel
         ref.BufferedRansEncoder, ref.RansDecoder = saved
     assert isinstance(enc["strings"][0][0], bytes) and isinstance(enc["strings"][1][0], bytes)
     assert torch.equal(dec["x_hat"], fwd["x_hat"].clamp(0, 1))
+
+
+@pytest.mark.parametrize("stack", ["h_a", "h_z_s1", "g_s"])
+def test_stack_in_the_tf32x3_mode(stack):
+    """The third fp32-parity mode of the dense layers (3 x TF32 tcgen05 on fp32 operands, no planes) through the same host code."""
+    from make_golden_transforms import transform_golden_input
+    want = torch.from_numpy(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "transforms.npz"))[stack])
+    got = TransformStack(stack, init_transform_params(0, (stack,)), device=DEV, math="tf32x3").forward(transform_golden_input(stack).to(DEV)).cpu()
+    err = rel_err(got, want)
+    print(f"\n{stack}[tf32x3] vs the reference module's golden output: {err:.2e}")
+    assert err < STACK_TOL["tf32x3"]
